@@ -1,0 +1,411 @@
+"""CPU oracle for the EMR2A retrieval hot path -- TEST INFRASTRUCTURE ONLY.
+
+This file is a numpy restatement of the reference algorithm
+(Ali-Xiyao/emr2a-evidence-grounded-multimodal-retrieval).  It is the checker
+for the CUDA path, never the product: only ``tests/``,
+``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference``
+legs of ``bench.py`` may import it.  Nothing under ``emr2a_b200/`` does.
+
+Parity pin: the reference ships no tests and no golden vectors,
+so the pin is the reference itself, executed in the build container by
+``tests/golden/make_golden.py``; its inputs/outputs are committed under
+``tests/golden/*.npz`` and ``tests/test_oracle_golden.py`` checks every
+function here against them.
+
+Integer label codes replace the reference's ``List[str]`` labels: code ``c``
+stands for ``sorted(set(labels))[c]``.  All comparisons the reference makes on
+strings are equality tests (plus one ``sorted`` for the class list), so the
+mapping is exact.
+
+Tie rule: the reference ranks with ``np.argsort(x)[-k:][::-1]`` (unstable
+introsort; order among exactly equal scores is implementation defined).  The
+oracle fixes the order to (score descending, database index ascending), which
+equals the reference wherever the top-k scores and the (k+1)-th are distinct.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+EPS = 1e-8  # the reference's additive epsilon (python float; a no-op in fp32 for norms >~ 0.1)
+
+
+# --------------------------------------------------------------------------
+# row normalisation / fusion
+# --------------------------------------------------------------------------
+def unit_rows(mat: np.ndarray) -> np.ndarray:
+    """``arr / (||row||_2 + 1e-8)``.
+
+    Follows utils/cv_evaluator.py:95-97 and retrieval/evaluator.py:75-77.
+    """
+    lengths = np.linalg.norm(mat, axis=1, keepdims=True) + EPS
+    return mat / lengths
+
+
+def fuse_concat_cv(img: np.ndarray, txt: np.ndarray) -> np.ndarray:
+    """Image-first concatenation followed by row normalisation.
+
+    Follows utils/cv_evaluator.py:99-105.
+    """
+    return unit_rows(np.concatenate([img, txt], axis=1))
+
+
+def fuse_early(text: np.ndarray, image: np.ndarray,
+               text_weight: float = 1.0, image_weight: float = 1.0) -> np.ndarray:
+    """Text-first weighted concatenation followed by row normalisation.
+
+    Follows retrieval/fusion.py:17-28.
+    """
+    joined = np.concatenate([text * text_weight, image * image_weight], axis=-1)
+    return joined / (np.linalg.norm(joined, axis=1, keepdims=True) + EPS)
+
+
+def rescale_scores(scores: np.ndarray, mode: str = "none") -> np.ndarray:
+    """Per-query score normalisation (none / zscore / minmax).
+
+    Follows retrieval/fusion.py:31-42: moments are taken with numpy in the
+    array dtype, widened to python float, and applied back in the array dtype.
+    """
+    if mode == "zscore":
+        mu = float(scores.mean())
+        sd = float(scores.std())
+        return (scores - mu) / (sd + EPS)
+    if mode == "minmax":
+        lo = float(scores.min())
+        hi = float(scores.max())
+        return (scores - lo) / (hi - lo + EPS)
+    return scores
+
+
+def fuse_late_scores(text_scores: np.ndarray, image_scores: np.ndarray,
+                     text_weight: float = 0.4, score_mode: str = "none") -> np.ndarray:
+    """``w * norm(text) + (1 - w) * norm(image)``.  Follows retrieval/fusion.py:4-14."""
+    t = rescale_scores(text_scores, score_mode)
+    i = rescale_scores(image_scores, score_mode)
+    return text_weight * t + (1 - text_weight) * i
+
+
+def unit_vector(vec: np.ndarray) -> np.ndarray:
+    """Single-vector normalise with a zero guard and no epsilon (utils/common.py:4-8)."""
+    length = np.linalg.norm(vec)
+    return vec if length == 0 else vec / length
+
+
+def fuse_single(text_vec: np.ndarray, image_vec: np.ndarray,
+                text_weight: float = 1.0, image_weight: float = 1.0) -> np.ndarray:
+    """Text-first weighted concat of two vectors, then unit_vector (utils/common.py:11-22)."""
+    joined = np.concatenate([text_vec * float(text_weight), image_vec * float(image_weight)], axis=0)
+    return unit_vector(joined)
+
+
+# --------------------------------------------------------------------------
+# similarity
+# --------------------------------------------------------------------------
+def cosine_one_vs_db(query: np.ndarray, database: np.ndarray) -> np.ndarray:
+    """Cosine of one query against every database row, both re-normalised
+    with the additive epsilon.  Follows retrieval/similarity.py:4-7."""
+    q = query / (np.linalg.norm(query) + EPS)
+    d = database / (np.linalg.norm(database, axis=1, keepdims=True) + EPS)
+    return np.dot(d, q)
+
+
+def euclid_one_vs_db(query: np.ndarray, database: np.ndarray) -> np.ndarray:
+    """``1 - dist / max(dist)``.  Follows retrieval/similarity.py:10-15."""
+    dist = np.linalg.norm(database - query, axis=1)
+    far = np.max(dist)
+    return 1.0 - dist / far if far > 0 else 1.0 - dist
+
+
+def dot_one_vs_db(query: np.ndarray, database: np.ndarray) -> np.ndarray:
+    """Plain ``db @ q`` on pre-normalised rows (utils/cv_evaluator.py:107-112)."""
+    return np.dot(database, query)
+
+
+# --------------------------------------------------------------------------
+# Top-K and votes
+# --------------------------------------------------------------------------
+def topk_desc(scores: np.ndarray, k: int) -> np.ndarray:
+    """Indices of the ``k`` best scores, best first.
+
+    The reference is ``np.argsort(scores)[-k:][::-1]`` (utils/cv_evaluator.py:123,
+    :237; retrieval/evaluator.py:189,204,220,243,272).  Ties are broken here by
+    ascending index (see module docstring).  ``k > len(scores)`` returns all.
+    """
+    order = np.argsort(-scores, kind="stable")
+    return order[:k]
+
+
+def vote_majority(labels: Sequence[int]) -> int:
+    """``Counter(labels).most_common(1)[0][0]``: highest count, ties go to the
+    label whose first occurrence has the best rank (utils/cv_evaluator.py:150,
+    :252, :285)."""
+    seen: Dict[int, int] = {}
+    for lab in labels:
+        seen[lab] = seen.get(lab, 0) + 1
+    best, best_n = None, -1
+    for lab, n in seen.items():       # dict keeps first-occurrence order
+        if n > best_n:
+            best, best_n = lab, n
+    return best
+
+
+def vote_weighted(labels: Sequence[int], scores: Sequence, acc: str = "f64") -> int:
+    """Per-label score sums in rank order; the largest sum wins, ties go to the
+    label inserted first.
+
+    ``acc='f64'``: scores went through ``float()`` first (utils/cv_evaluator.py:125,
+    :239, :142-147, :255-260, :288-293).  ``acc='f32'``: numpy float32 scalars
+    are summed as they are (retrieval/evaluator.py:224-230, :247-253).
+    """
+    sums: Dict[int, object] = {}
+    for lab, sc in zip(labels, scores):
+        sc = float(sc) if acc == "f64" else np.float32(sc)
+        if lab not in sums:
+            sums[lab] = 0.0
+        sums[lab] = sums[lab] + sc
+    best, best_s = None, None
+    for lab, s in sums.items():
+        if best_s is None or s > best_s:
+            best, best_s = lab, s
+    return best
+
+
+# --------------------------------------------------------------------------
+# metrics (utils/metrics.py)
+# --------------------------------------------------------------------------
+def confusion_counts(pred: Sequence[int], truth: Sequence[int], n_classes: int) -> np.ndarray:
+    """``matrix[true, pred] += 1`` (utils/metrics.py:56-75)."""
+    m = np.zeros((n_classes, n_classes), dtype=np.int64)
+    for p, t in zip(pred, truth):
+        if 0 <= p < n_classes and 0 <= t < n_classes:
+            m[t, p] += 1
+    return m
+
+
+def prf_per_class(pred: Sequence[int], truth: Sequence[int], n_classes: int) -> List[Dict[str, float]]:
+    """Per-class precision / recall / F1 / support with 0.0 on empty
+    denominators (utils/metrics.py:30-53)."""
+    pred = np.asarray(pred)
+    truth = np.asarray(truth)
+    out = []
+    for c in range(n_classes):
+        tp = int(np.sum((pred == c) & (truth == c)))
+        fp = int(np.sum((pred == c) & (truth != c)))
+        fn = int(np.sum((pred != c) & (truth == c)))
+        p = tp / (tp + fp) if (tp + fp) > 0 else 0.0
+        r = tp / (tp + fn) if (tp + fn) > 0 else 0.0
+        f = 2 * p * r / (p + r) if (p + r) > 0 else 0.0
+        out.append({"precision": p, "recall": r, "f1": f, "support": int(np.sum(truth == c))})
+    return out
+
+
+# --------------------------------------------------------------------------
+# evaluators
+# --------------------------------------------------------------------------
+def cv_fold_eval(
+    db_img: Optional[np.ndarray], db_txt: Optional[np.ndarray],
+    q_img: Optional[np.ndarray], q_txt: Optional[np.ndarray],
+    db_labels: np.ndarray, q_labels: np.ndarray, n_classes: int,
+    fusion: str = "concat", top_k: int = 5, top_k_list: Sequence[int] = (1, 3, 5, 5),
+    w_text: float = 0.5,
+) -> Dict:
+    """One CV fold from the *processed* (post StandardScaler/PCA/row-normalise)
+    arrays onward.  Follows utils/cv_evaluator.py:186-334.
+
+    Returns integer/array results; the drop-in layer maps them back to the
+    reference's string/list structures.
+    """
+    if fusion == "image_only":
+        db, qs = db_img, q_img
+    elif fusion == "text_only":
+        db, qs = db_txt, q_txt
+    elif fusion == "concat":
+        db, qs = fuse_concat_cv(db_img, db_txt), fuse_concat_cv(q_img, q_txt)
+    elif fusion == "late":
+        db = qs = None
+    else:
+        raise ValueError(f"Unknown fusion type: {fusion}")
+
+    n_q = len(q_labels)
+    kk = min(top_k, len(db_labels))
+    top_idx = np.zeros((n_q, kk), dtype=np.int64)
+    top_scores = np.zeros((n_q, kk), dtype=np.float64)
+    pred_top1 = np.zeros(n_q, dtype=np.int64)
+    pred_vote = np.zeros(n_q, dtype=np.int64)
+    pred_wvote = np.zeros(n_q, dtype=np.int64)
+    hits = {int(k): np.zeros(n_q, dtype=np.int64) for k in top_k_list}
+
+    for i in range(n_q):
+        if fusion == "late":
+            s_img = dot_one_vs_db(q_img[i], db_img)              # :233
+            s_txt = dot_one_vs_db(q_txt[i], db_txt)              # :234
+            sims = w_text * s_txt + (1 - w_text) * s_img         # :235
+        else:
+            sims = dot_one_vs_db(qs[i], db)                      # :122
+        idx = topk_desc(sims, top_k)                             # :123 / :237
+        labs = [int(db_labels[j]) for j in idx]
+        scs = [float(sims[j]) for j in idx]
+        top_idx[i, :len(idx)] = idx
+        top_scores[i, :len(idx)] = scs
+        pred_top1[i] = labs[0]                                   # :249 / :282
+        pred_vote[i] = vote_majority(labs)                       # :252 / :285
+        pred_wvote[i] = vote_weighted(labs, scs, "f64")          # :255-260 / :288-293
+        for k in hits:
+            hits[k][i] = 1 if int(q_labels[i]) in labs[:k] else 0   # :263-267 / :296-300
+
+    q_labels = np.asarray(q_labels)
+    res: Dict = {f"top{k}": float(np.mean(v)) for k, v in hits.items()}
+    res["vote_acc"] = float(np.mean(pred_vote == q_labels))          # :305-307
+    res["weighted_vote_acc"] = float(np.mean(pred_wvote == q_labels))  # :308-310
+    prf = prf_per_class(pred_vote, q_labels, n_classes)              # :314-316
+    res["macro_precision"] = float(np.mean([v["precision"] for v in prf]))
+    res["macro_recall"] = float(np.mean([v["recall"] for v in prf]))
+    res["macro_f1"] = float(np.mean([v["f1"] for v in prf]))
+    res["confusion_top1"] = confusion_counts(pred_top1, q_labels, n_classes)   # :322-324
+    res["confusion_vote"] = confusion_counts(pred_vote, q_labels, n_classes)   # :325-327
+    res.update(top_idx=top_idx, top_scores=top_scores, pred_top1=pred_top1,
+               pred_vote=pred_vote, pred_weighted=pred_wvote,
+               hits={k: v.copy() for k, v in hits.items()})
+    return res
+
+
+def _holdout_topk_acc(db: np.ndarray, qs: np.ndarray, db_labels, q_labels, k: int) -> float:
+    """retrieval/evaluator.py:178-193."""
+    good = 0
+    for i in range(len(qs)):
+        sims = cosine_one_vs_db(qs[i], db)
+        labs = [int(db_labels[j]) for j in topk_desc(sims, k)]
+        good += int(int(q_labels[i]) in labs)
+    return good / len(q_labels)
+
+
+def _holdout_weighted_acc(db: np.ndarray, qs: np.ndarray, db_labels, q_labels) -> float:
+    """retrieval/evaluator.py:210-233 (K fixed at 5, fp32 sums)."""
+    good = 0
+    for i in range(len(qs)):
+        sims = cosine_one_vs_db(qs[i], db)
+        idx = topk_desc(sims, 5)
+        labs = [int(db_labels[j]) for j in idx]
+        good += int(vote_weighted(labs, [sims[j] for j in idx], "f32") == int(q_labels[i]))
+    return good / len(q_labels)
+
+
+def _scores_topk_acc(scores: np.ndarray, db_labels, q_labels, k: int) -> float:
+    """retrieval/evaluator.py:195-208."""
+    good = 0
+    for i in range(len(scores)):
+        labs = [int(db_labels[j]) for j in topk_desc(scores[i], k)]
+        good += int(int(q_labels[i]) in labs)
+    return good / len(q_labels)
+
+
+def _scores_weighted_acc(scores: np.ndarray, db_labels, q_labels) -> float:
+    """retrieval/evaluator.py:235-256."""
+    good = 0
+    for i in range(len(scores)):
+        idx = topk_desc(scores[i], 5)
+        labs = [int(db_labels[j]) for j in idx]
+        good += int(vote_weighted(labs, [scores[i][j] for j in idx], "f32") == int(q_labels[i]))
+    return good / len(q_labels)
+
+
+def holdout_eval(
+    db_txt: Optional[np.ndarray], q_txt: Optional[np.ndarray],
+    db_img: Optional[np.ndarray], q_img: Optional[np.ndarray],
+    db_labels, q_labels, text_weight: float = 0.4, fusion_type: str = "late",
+    score_mode: str = "none", top_k_list: Sequence[int] = (1, 3, 5),
+) -> Dict:
+    """Hold-out evaluator.  Follows retrieval/evaluator.py:94-176; the
+    ``all_top_labels_top5`` entry holds label codes."""
+    out: Dict = {}
+    if fusion_type == "early":
+        if db_txt is None or q_txt is None or db_img is None or q_img is None:
+            raise ValueError("Early fusion requires both text and image embeddings")
+        fdb = fuse_early(db_txt, db_img, text_weight, 1 - text_weight)
+        fq = fuse_early(q_txt, q_img, text_weight, 1 - text_weight)
+        for k in top_k_list:
+            out[f"top{k}"] = _holdout_topk_acc(fdb, fq, db_labels, q_labels, k)
+        out["weighted"] = _holdout_weighted_acc(fdb, fq, db_labels, q_labels)
+        return out
+    if q_txt is not None and db_txt is not None:
+        for k in top_k_list:
+            out[f"text_top{k}"] = _holdout_topk_acc(db_txt, q_txt, db_labels, q_labels, k)
+        out["text_weighted"] = _holdout_weighted_acc(db_txt, q_txt, db_labels, q_labels)
+    if q_img is not None and db_img is not None:
+        for k in top_k_list:
+            out[f"image_top{k}"] = _holdout_topk_acc(db_img, q_img, db_labels, q_labels, k)
+        out["image_weighted"] = _holdout_weighted_acc(db_img, q_img, db_labels, q_labels)
+    if q_txt is not None and q_img is not None:
+        rows = []
+        for i in range(len(q_labels)):
+            st = cosine_one_vs_db(q_txt[i], db_txt)
+            si = cosine_one_vs_db(q_img[i], db_img)
+            rows.append(fuse_late_scores(st, si, text_weight, score_mode))
+        fused = np.array(rows)
+        for k in top_k_list:
+            out[f"top{k}"] = _scores_topk_acc(fused, db_labels, q_labels, k)
+        out["weighted"] = _scores_weighted_acc(fused, db_labels, q_labels)
+        out["all_top_labels_top5"] = [
+            [int(db_labels[j]) for j in topk_desc(fused[i], 5)] for i in range(len(fused))]
+        out["_fused_scores"] = fused
+    return out
+
+
+# --------------------------------------------------------------------------
+# batched helpers for parity tests / CPU-baseline timing
+# --------------------------------------------------------------------------
+def search_topk_batched(qs: np.ndarray, db: np.ndarray, k: int,
+                        q_fold: Optional[np.ndarray] = None,
+                        db_fold: Optional[np.ndarray] = None,
+                        block: int = 256) -> Tuple[np.ndarray, np.ndarray]:
+    """Top-k of ``db @ q`` for many queries at once (sgemm instead of the
+    reference's per-query sgemv: same math, summation order differs by
+    <= ~1e-7).  Rows with ``db_fold == q_fold`` are excluded (the CV rule
+    "never retrieve from the query's own fold", utils/cv_evaluator.py:349-376).
+    Returns (indices int64 [Q,k], scores float32 [Q,k]); -1 pads short rows."""
+    n_q = qs.shape[0]
+    idx_out = np.full((n_q, k), -1, dtype=np.int64)
+    sc_out = np.zeros((n_q, k), dtype=np.float32)
+    for s in range(0, n_q, block):
+        sims = qs[s:s + block] @ db.T
+        if q_fold is not None:
+            sims = np.where(q_fold[s:s + block, None] == db_fold[None, :], -np.inf, sims)
+        for r in range(sims.shape[0]):
+            row = sims[r]
+            if k < row.shape[0]:
+                cand = np.argpartition(-row, k)[:k + 1]
+                # widen to every index tied with the k-th value so the tie rule is global
+                kth = np.sort(row[cand])[::-1][k - 1]
+                cand = np.nonzero(row >= kth)[0]
+            else:
+                cand = np.arange(row.shape[0])
+            order = cand[np.argsort(-row[cand], kind="stable")][:k]
+            order = order[np.isfinite(row[order])]
+            idx_out[s + r, :len(order)] = order
+            sc_out[s + r, :len(order)] = row[order]
+    return idx_out, sc_out
+
+
+def reference_style_search_and_vote(qs: np.ndarray, db: np.ndarray, db_labels: np.ndarray,
+                                    q_labels: np.ndarray, k: int) -> Dict:
+    """The per-query loop exactly as the reference runs it (sgemv + full argsort
+    + python votes): this is what ``bench.py`` times as the CPU baseline.
+    Follows utils/cv_evaluator.py:269-300."""
+    n_q = qs.shape[0]
+    top1 = np.zeros(n_q, np.int64)
+    vote = np.zeros(n_q, np.int64)
+    wvote = np.zeros(n_q, np.int64)
+    idx_all = np.zeros((n_q, k), np.int64)
+    for i in range(n_q):
+        sims = np.dot(db, qs[i])
+        idx = np.argsort(sims)[-k:][::-1]
+        labs = [int(db_labels[j]) for j in idx]
+        scs = [float(sims[j]) for j in idx]
+        idx_all[i] = idx
+        top1[i] = labs[0]
+        vote[i] = vote_majority(labs)
+        wvote[i] = vote_weighted(labs, scs, "f64")
+    return {"top_idx": idx_all, "pred_top1": top1, "pred_vote": vote, "pred_weighted": wvote,
+            "top1": float(np.mean(top1 == q_labels)), "vote_acc": float(np.mean(vote == q_labels)),
+            "weighted_vote_acc": float(np.mean(wvote == q_labels))}

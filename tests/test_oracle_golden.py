@@ -1,0 +1,114 @@
+"""Pin the CPU oracle against vectors produced by running the reference itself
+(tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+
+TOL = 2e-6   # oracle repeats the same numpy ops; only BLAS thread order may differ
+
+
+def test_primitives(golden, oracle):
+    g = golden("primitives.npz")
+    np.testing.assert_allclose(oracle.cosine_one_vs_db(g["cos_q"], g["cos_db"]), g["cos_out"], atol=TOL)
+    np.testing.assert_allclose(oracle.euclid_one_vs_db(g["cos_q"], g["cos_db"]), g["euc_out"], atol=TOL)
+    np.testing.assert_allclose(oracle.fuse_early(g["ef_text"], g["ef_image"]), g["ef_out_11"], atol=TOL)
+    np.testing.assert_allclose(oracle.fuse_early(g["ef_text"], g["ef_image"], 0.4, 0.6), g["ef_out_w"], atol=TOL)
+    for mode in ("none", "zscore", "minmax"):
+        np.testing.assert_allclose(oracle.fuse_late_scores(g["lf_ts"], g["lf_is"], 0.4, mode),
+                                   g[f"lf_out_{mode}"], atol=TOL)
+        np.testing.assert_allclose(oracle.rescale_scores(g["lf_ts"], mode), g[f"ns_out_{mode}"], atol=TOL)
+    np.testing.assert_allclose(oracle.fuse_late_scores(g["lf_ts"], g["lf_is"], 0.7), g["lf_out_w07"], atol=TOL)
+    np.testing.assert_allclose(oracle.unit_rows(g["ef_image"]), g["nr_out"], atol=TOL)
+    np.testing.assert_allclose(oracle.fuse_concat_cv(g["cf_img"], g["cf_txt"]), g["cf_out"], atol=TOL)
+    np.testing.assert_allclose(oracle.dot_one_vs_db(g["cf_out"][2], g["cf_out"]), g["dot_out"], atol=TOL)
+    np.testing.assert_allclose(oracle.unit_vector(g["cos_q"]), g["l2_out"], atol=TOL)
+    assert np.array_equal(oracle.unit_vector(np.zeros(7, np.float32)), g["l2_zero_out"])
+    np.testing.assert_allclose(oracle.fuse_single(g["ef_text"][0], g["ef_image"][0], 0.3, 0.9), g["ce_out"], atol=TOL)
+    assert g["cos_out"].dtype == np.float32 and g["ef_out_11"].dtype == np.float32
+
+
+def test_retrieve_topk(golden, oracle):
+    g = golden("primitives.npz")
+    sims = oracle.dot_one_vs_db(g["cf_out"][2], g["cf_out"])
+    idx = oracle.topk_desc(sims, 5)
+    assert np.array_equal(idx, g["rt_top_idx"])
+    assert np.array_equal(g["rt_labels"][idx], g["rt_top_labels"])
+    np.testing.assert_allclose(sims[idx].astype(np.float64), g["rt_top_scores"], atol=TOL)
+
+
+def test_votes_and_metrics(golden, oracle):
+    g = golden("primitives.npz")
+    vl, vs, true = g["v_labels"], g["v_scores"], g["v_true"]
+    maj = np.array([oracle.vote_majority(list(r)) for r in vl])
+    wv = np.array([oracle.vote_weighted(list(r), list(s), "f64") for r, s in zip(vl, vs)])
+    assert float(np.mean(maj == true)) == float(g["v_acc_major"])
+    assert float(np.mean(wv == true)) == float(g["v_acc_weight"])
+    prf = oracle.prf_per_class(g["m_pred"], g["m_truth"], 4)
+    got = np.array([[p["precision"], p["recall"], p["f1"], p["support"]] for p in prf])
+    np.testing.assert_allclose(got, g["m_prf"], atol=1e-12)
+    assert np.array_equal(oracle.confusion_counts(g["m_pred"], g["m_truth"], 4), g["m_cm"])
+
+
+def test_topk_desc_edges(oracle):
+    s = np.array([0.5, 0.9, 0.9, -1.0, 0.5], dtype=np.float32)
+    assert list(oracle.topk_desc(s, 3)) == [1, 2, 0]          # ties -> lower index first
+    assert list(oracle.topk_desc(s, 9)) == [1, 2, 0, 4, 3]    # k > n -> all
+    assert list(oracle.topk_desc(s, 1)) == [1]
+
+
+def test_cv_fold(golden, oracle):
+    g = golden("cv_small.npz")
+    n, d_img, d_txt, n_cls, pca_dim, top_k = [int(x) for x in g["meta"]]
+    for f in range(5):
+        tr, te = g[f"f{f}_train_idx"], g[f"f{f}_test_idx"]
+        for fusion, w in (("concat", 0.5), ("late", 0.3), ("image_only", 0.5), ("text_only", 0.5)):
+            r = oracle.cv_fold_eval(g[f"f{f}_img_tr"], g[f"f{f}_txt_tr"], g[f"f{f}_img_te"], g[f"f{f}_txt_te"],
+                                    g["labels"][tr], g["labels"][te], n_cls, fusion=fusion, top_k=top_k,
+                                    top_k_list=(1, 3, 5, 5), w_text=w)
+            key = f"f{f}_{fusion}"
+            assert np.array_equal(r["top_idx"], g[key + "_top_idx"]), key
+            np.testing.assert_allclose(r["top_scores"], g[key + "_top_scores"], atol=TOL)
+            got = np.array([r["top1"], r["top3"], r["top5"], r["vote_acc"], r["weighted_vote_acc"],
+                            r["macro_precision"], r["macro_recall"], r["macro_f1"]])
+            np.testing.assert_allclose(got, g[key + "_metrics"], atol=1e-12)
+            assert np.array_equal(r["confusion_top1"], g[key + "_cm_top1"])
+            assert np.array_equal(r["confusion_vote"], g[key + "_cm_vote"])
+            assert np.array_equal(g["labels"][tr][r["top_idx"]], g[key + "_top_labels"])
+
+
+def test_holdout(golden, oracle):
+    g = golden("holdout_small.npz")
+    args = (g["tr_txt"], g["te_txt"], g["tr_img"], g["te_img"], g["tr_labels"], g["te_labels"])
+    runs = {
+        "early": dict(fusion_type="early", text_weight=0.4),
+        "late_none": dict(fusion_type="late", text_weight=0.4, score_mode="none"),
+        "late_zscore": dict(fusion_type="late", text_weight=0.3, score_mode="zscore"),
+        "late_minmax": dict(fusion_type="late", text_weight=0.6, score_mode="minmax"),
+    }
+    for name, kw in runs.items():
+        r = oracle.holdout_eval(*args, top_k_list=(1, 3, 5, 7), **kw)
+        for k, v in zip(g[name + "_keys"], g[name + "_vals"]):
+            assert r[str(k)] == v, (name, k)
+        if name + "_top5" in g:
+            assert np.array_equal(np.array(r["all_top_labels_top5"]), g[name + "_top5"])
+    r = oracle.holdout_eval(None, None, g["tr_img"], g["te_img"], g["tr_labels"], g["te_labels"],
+                            fusion_type="none", top_k_list=(1, 3, 5, 5))
+    for k, v in zip(g["imgonly_keys"], g["imgonly_vals"]):
+        assert r[str(k)] == v
+    sc = g["fs_scores"]
+    assert oracle._scores_topk_acc(sc, g["tr_labels"], g["te_labels"], 3) == float(g["fs_top3"])
+    assert oracle._scores_weighted_acc(sc, g["tr_labels"], g["te_labels"]) == float(g["fs_weighted"])
+
+
+def test_batched_search_matches_loop(oracle):
+    rng = np.random.default_rng(3)
+    db = oracle.unit_rows(rng.standard_normal((500, 32)).astype(np.float32))
+    db[17] = db[400]                                           # exact tie inside the top-k of query 400
+    qs = db[395:405].copy()
+    idx, sc = oracle.search_topk_batched(qs, db, 6)
+    for i in range(len(qs)):
+        ref = oracle.topk_desc(oracle.dot_one_vs_db(qs[i], db), 6)
+        # sgemm vs sgemv may reorder exact ties only when rounding differs; compare as sets + scores
+        assert set(idx[i]) == set(ref)
+    fold_db = rng.integers(0, 5, size=500).astype(np.uint8)
+    idx, sc = oracle.search_topk_batched(qs, db, 6, q_fold=fold_db[395:405], db_fold=fold_db)
+    for i in range(len(qs)):
+        assert np.all(fold_db[idx[i]] != fold_db[395 + i])
