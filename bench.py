@@ -1,0 +1,352 @@
+"""EMR2A retrieval hot path benchmark (BASELINE.json metric: queries/sec, cosine Top-K + vote).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload ("c2", BASELINE.json configs[1]): 1M-case database, 512-d image + 512-d text
+embeddings (fp32, synthetic class-structured Gaussians), concat fusion to 1024-d, 10k queries,
+K=10, 3 classes.  A STEP = the whole hot path over that batch:
+    K1 normalise+fuse (database shard AND queries) -> K2 similarity + fused Top-K
+    -> K3 merge -> [NCCL all-gather of local Top-K + K3 merge when N > 1] -> K4 vote + metrics.
+N > 1: the SAME 1M-row database is sharded row-wise over the ranks (strong scaling).
+
+value  : queries/sec with the raw embeddings resident in HBM.
+e2e    : queries/sec through Engine.search_and_vote_host with the inputs in PINNED HOST
+         memory: every step copies the database shard + queries host->device (chunked,
+         overlapped with compute) and the results device->host.
+roofline: the K2 kernel (tensor pipe): algorithmic FLOPs 2*D*Q*N_local / its CUDA-event time.
+cpu_baseline / --impl reference: the oracle's reference-style loop (np.dot sgemv + full
+         np.argsort + python votes, per query) on the host cores, on a bounded query sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+WORKLOADS = {
+    # name: (n_db, d_img, d_txt, n_q, k, n_classes, seed)
+    "c2": (1_000_000, 512, 512, 10_000, 10, 3, 11),
+    "c2k5": (1_000_000, 512, 512, 10_000, 5, 3, 11),
+    "small": (100_000, 256, 256, 2_048, 10, 3, 11),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("EMR2A_BENCH_WORKLOAD", "c2"), choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default=os.environ.get("EMR2A_BENCH_PRECISION", "bf16x3"))
+    ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("EMR2A_BENCH_CPU_SAMPLE", 48)))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": p["hbm_gbs"], "tflops": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1590.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_leg(db_img, db_txt, q_img, q_txt, db_labels, q_labels, k, sample, full_q):
+    """The reference's algorithm on the host cores (oracle port): normalise + fuse the database
+    once (utils/cv_evaluator.py:95-105), then per query sgemv + argsort + votes (:269-300)."""
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import emr2a_oracle as oracle
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max([i.get("num_threads", 1) for i in threadpool_info()] or [1])
+    except Exception:
+        threads = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    db = oracle.fuse_concat_cv(oracle.unit_rows(db_img), oracle.unit_rows(db_txt))
+    t_prep = time.perf_counter() - t0
+    rng = np.random.default_rng(0)
+    pick = np.sort(rng.choice(len(q_labels), size=min(sample, len(q_labels)), replace=False))
+    qs = oracle.fuse_concat_cv(oracle.unit_rows(q_img[pick]), oracle.unit_rows(q_txt[pick]))
+    t0 = time.perf_counter()
+    res = oracle.reference_style_search_and_vote(qs, db, db_labels, q_labels[pick], k)
+    t_q = (time.perf_counter() - t0) / len(pick)
+    qps = full_q / (t_prep + full_q * t_q)
+    info = {"value": qps, "unit": "queries/s", "cores": int(threads), "kind": "port",
+            "sample": f"{len(pick)} of {full_q} queries against the full {len(db)}-row database "
+                      f"({t_q * 1e3:.1f} ms/query) + one database normalise/fuse pass ({t_prep:.1f} s), "
+                      f"extrapolated to the full step; host has {os.cpu_count()} logical cores"}
+    return info, pick, res
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; the reference is pure Python and
+    /root/reference does not exist on the GPU box), every host thread BLAS can use."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from emr2a_b200 import synth
+    n_db, d_img, d_txt, n_q, k, n_cls, seed = WORKLOADS[args.workload]
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    lab = torch.randint(0, n_cls, (n_db + n_q,), generator=g).numpy().astype(np.int32)
+    cen_i = torch.randn((n_cls, d_img), generator=g).numpy()
+    cen_t = torch.randn((n_cls, d_txt), generator=g).numpy()
+    img = torch.randn((n_db + n_q, d_img), generator=g).numpy()
+    txt = torch.randn((n_db + n_q, d_txt), generator=g).numpy()
+    img += np.float32(synth.SEP) * cen_i[lab]
+    txt += np.float32(synth.SEP) * cen_t[lab]
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import emr2a_oracle as oracle
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max([i.get("num_threads", 1) for i in threadpool_info()] or [1])
+    except Exception:
+        threads = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    db = oracle.fuse_concat_cv(oracle.unit_rows(img[:n_db]), oracle.unit_rows(txt[:n_db]))
+    t_prep = time.perf_counter() - t0
+    sample = max(4, min(args.cpu_sample, 16))
+    qs_all = oracle.fuse_concat_cv(oracle.unit_rows(img[n_db:]), oracle.unit_rows(txt[n_db:]))
+    times = []
+    for s in range(args.warmup + args.steps):
+        lo = (s * sample) % (n_q - sample)
+        t0 = time.perf_counter()
+        oracle.reference_style_search_and_vote(qs_all[lo:lo + sample], db, lab[:n_db], lab[n_db + lo:n_db + lo + sample], k)
+        dt = time.perf_counter() - t0
+        if s >= args.warmup:
+            times.append(dt)
+    t_q = sum(times) / (len(times) * sample)
+    qps = n_q / (t_prep + n_q * t_q)
+    line = {"impl": "reference", "metric": "queries/sec (cosine Top-K + vote)", "value": qps, "unit": "queries/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * (t_prep + n_q * t_q), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {n_db}-case database, {d_img}+{d_txt}-d concat fusion, {n_q} queries, K={k}",
+                       "parallelism": "cpu"},
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": int(threads), "kind": "port",
+                             "sample": f"each step = {sample} queries against the full database ({t_q * 1e3:.1f} ms/query) "
+                                       f"+ amortised database normalise/fuse ({t_prep:.1f} s per {n_q} queries); "
+                                       f"{os.cpu_count()} logical cores"},
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from emr2a_b200 import native, synth
+    from emr2a_b200.dist import gather_keys, shard_range, sharded_search_and_vote
+    from emr2a_b200.engine import get_engine, unpack_keys
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    eng = get_engine(dev)
+
+    n_db, d_img, d_txt, n_q, k, n_cls, seed = WORKLOADS[args.workload]
+    dim = d_img + d_txt
+    lo, hi = shard_range(n_db, rank, world)
+    flags = native.NF_SEGNORM | native.NF_ROWNORM          # normalise each modality, concat, normalise (a12+a13)
+    k_list = [1, 3, 5, k]
+
+    # ---- synthetic inputs, generated on the device (per shard; same rows for any N) ----
+    db_img, _ = synth.device_block(lo, hi - lo, d_img, n_cls, seed, dev, label_seed=seed)
+    db_txt, _ = synth.device_block(lo, hi - lo, d_txt, n_cls, seed + 1, dev, label_seed=seed)
+    # labels must be global (the vote gathers labels by global row index)
+    db_labels = synth.device_labels(0, n_db, n_cls, seed, dev)
+    q_row0 = 50_003_968
+    q_img, q_labels = synth.device_block(q_row0, n_q, d_img, n_cls, seed, dev, label_seed=seed)
+    q_txt, _ = synth.device_block(q_row0, n_q, d_txt, n_cls, seed + 1, dev, label_seed=seed)
+    torch.cuda.synchronize()
+
+    timers = {"k2_start": torch.cuda.Event(enable_timing=True), "k2_end": torch.cuda.Event(enable_timing=True)}
+    k2_ms = []
+
+    def step(record_k2=False):
+        r = sharded_search_and_vote(eng, (db_img, db_txt), (q_img, q_txt), db_labels, q_labels, n_cls, k,
+                                    row_offset=lo, db_flags=flags, q_flags=flags, k_list=k_list,
+                                    precision=args.precision, timers=timers if record_k2 else None)
+        return r
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        res = step()
+    barrier()
+
+    # ---- timed region: device-resident ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    k2_events = []
+    for _ in range(args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        timers["k2_start"], timers["k2_end"] = e0, e1
+        res = step(record_k2=True)
+        k2_events.append((e0, e1))
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    k2_ms = [a.elapsed_time(b) for a, b in k2_events]
+    t = torch.tensor([ms, sum(k2_ms) / len(k2_ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, k2_avg_ms = float(t[0]), float(t[1])
+    ms_per_step = ms_total / args.steps
+    qps = n_q / (ms_per_step / 1e3)
+
+    # ---- e2e: host (pinned) inputs through the public host-buffer API ----
+    e2e = None
+    if not args.no_e2e:
+        h_img = db_img.cpu().pin_memory(); h_txt = db_txt.cpu().pin_memory()
+        hq_img = q_img.cpu().pin_memory(); hq_txt = q_txt.cpu().pin_memory()
+        h_lab = db_labels.cpu().pin_memory(); hq_lab = q_labels.cpu().pin_memory()
+
+        def reduce_fn(keys):
+            return eng.topk_merge(gather_keys(keys), k) if world > 1 else keys
+
+        def e2e_step():
+            return eng.search_and_vote_host((h_img, h_txt), (hq_img, hq_txt), h_lab, hq_lab, n_cls, k,
+                                            db_flags=flags, q_flags=flags, k_list=k_list, precision=args.precision,
+                                            row_offset=lo, reduce_fn=reduce_fn)
+        for _ in range(2):
+            out = e2e_step()
+        barrier()
+        e_steps = max(2, min(args.steps, 5))
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(e_steps):
+            out = e2e_step()
+        t1.record()
+        barrier()
+        te = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e_ms = float(te[0]) / e_steps
+        e2e = {"value": n_q / (e_ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": int(out["h2d_bytes"]),
+               "d2h_bytes_per_step": int(out["d2h_bytes"]), "ms_per_step": e_ms,
+               "api": "emr2a_b200.engine.Engine.search_and_vote_host (pinned host inputs, chunked H2D overlapped with K1/K2)"}
+        # the two paths must agree bit for bit
+        assert torch.equal(out["top_idx"], res["top_idx"].cpu()), "e2e and device-resident results differ"
+        del h_img, h_txt
+
+    # ---- roofline of the dominant kernel (K2, tensor pipe) ----
+    pk = peaks()
+    flops = 2.0 * dim * n_q * (hi - lo)
+    passes = {"bf16x3": 3, "bf16x1": 1, "fp32": 1}[res["precision"]]
+    achieved = flops / (k2_avg_ms / 1e3) / 1e12
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
+                "frac": achieved / pk["tflops"], "traffic": None, "peak_source": pk["src"] + " (bf16 sustained)",
+                "kernel": "tc_topk_kernel (+K3 merge of partial lists, <1%)", "kernel_ms": k2_avg_ms,
+                "issued_tflops": achieved * passes, "issued_frac": achieved * passes / pk["tflops"],
+                "share_of_step": k2_avg_ms / ms_per_step}
+
+    # ---- CPU baseline + parity on the sample (rank 0, N = 1) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu, pick, ref = cpu_reference_leg(db_img.cpu().numpy(), db_txt.cpu().numpy(), q_img.cpu().numpy(),
+                                           q_txt.cpu().numpy(), db_labels.cpu().numpy(), q_labels.cpu().numpy(),
+                                           k, args.cpu_sample, n_q)
+        got_idx = res["top_idx"].cpu().numpy()[pick]
+        got_sc = res["top_scores"].cpu().numpy()[pick]
+        same_rows = float(np.mean(np.all(got_idx == ref["top_idx"], axis=1)))
+        cpu["parity_on_sample"] = {"topk_rows_identical": same_rows,
+                                   "vote_identical": float(np.mean(res["pred_vote"].cpu().numpy()[pick] == ref["pred_vote"])),
+                                   "weighted_vote_identical": float(np.mean(res["pred_weighted"].cpu().numpy()[pick] == ref["pred_weighted"]))}
+
+    if rank == 0:
+        hits = res["hit_counts"][0].cpu().numpy()
+        line = {"metric": "queries/sec (cosine Top-K + vote)", "value": qps, "unit": "queries/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": {"bf16x3": "bf16x3 split (fp32-equivalent), fp32 accumulate", "bf16x1": "bf16, fp32 accumulate",
+                          "fp32": "f32"}[res["precision"]],
+                "data": "synthetic",
+                "config": {"workload": f"{args.workload}: {n_db}-case database, {d_img}+{d_txt}-d concat fusion (fp32 in), "
+                                       f"{n_q} queries, K={k}, {n_cls} classes",
+                           "parallelism": f"database row-sharded x{world}, NCCL all-gather of local Top-K" if world > 1 else "single GPU",
+                           "l2": "inputs (4.1 GB database) larger than L2; no flush needed",
+                           "step": "K1 normalise+fuse (db shard + queries) -> K2 GEMM+Top-K -> K3 merge -> K4 vote"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+                "accuracy": {"top1": float(hits[0]) / n_q, f"top{k}": float(hits[3]) / n_q,
+                             "vote_acc": float(res["vote_counts"][0, 1]) / n_q}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,130 @@
+// C-ABI glue: error text, device check, emr2a_topk_search dispatch.
+#include "common.cuh"
+
+#include <string.h>
+
+namespace emr2a {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+  snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s", static_cast<int>(e), cudaGetErrorString(e), where);
+  cudaGetLastError();
+  return EMR2A_ERR_CUDA;
+}
+int sm_count() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  return n;
+}
+
+// implemented in simt_paths.cu / topk_tc.cu
+size_t simt_topk_workspace_bytes(int64_t Q, int64_t N, int K);
+int simt_topk_search(const float* q, const float* db, int64_t Q, int64_t N, int D, int64_t ldq, int64_t lddb,
+                     const uint8_t* q_fold, const uint8_t* db_fold, int64_t idx_base, int K, uint64_t* out_keys,
+                     void* workspace, size_t ws_bytes, cudaStream_t st);
+size_t tc_topk_workspace_bytes(int64_t Q, int64_t N, int K);
+int tc_topk_search(const uint16_t* q_hi, const uint16_t* q_lo, const uint16_t* db_hi, const uint16_t* db_lo,
+                   int64_t Q, int64_t N, int D, int64_t ldq, int64_t lddb, const uint8_t* q_fold,
+                   const uint8_t* db_fold, int64_t idx_base, int K, int passes, uint64_t* out_keys,
+                   void* workspace, size_t ws_bytes, float* debug_scores, cudaStream_t st);
+
+__global__ void zero_keys_kernel(uint64_t* k, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) k[i] = 0ull;
+}
+
+}  // namespace emr2a
+
+using namespace emr2a;
+
+extern "C" int emr2a_abi_version(void) { return EMR2A_ABI_VERSION; }
+extern "C" const char* emr2a_last_error(void) { return g_err; }
+
+extern "C" int emr2a_device_check(int* sms, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  EMR2A_CUDA_TRY(cudaGetDevice(&dev));
+  int major = 0, minor = 0, n = 0;
+  EMR2A_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  EMR2A_CUDA_TRY(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  EMR2A_CUDA_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  if (sms) *sms = n;
+  if (cc_major) *cc_major = major;
+  if (cc_minor) *cc_minor = minor;
+  if (major != 10) return fail(EMR2A_ERR_UNSUPPORTED, "libemr2a is built for sm_100a only; device is sm_%d%d", major, minor);
+  return EMR2A_OK;
+}
+
+extern "C" size_t emr2a_topk_search_workspace_bytes(int64_t Q, int64_t N, int D, int K, int precision) {
+  (void)D;
+  if (Q <= 0 || N <= 0 || K <= 0) return 256;
+  if (precision == EMR2A_PREC_FP32) return simt_topk_workspace_bytes(Q, N, K) + 256;
+  return tc_topk_workspace_bytes(Q, N, K);
+}
+
+static int topk_search_impl(const float* q_f32, const uint16_t* q_hi, const uint16_t* q_lo, const float* db_f32,
+                            const uint16_t* db_hi, const uint16_t* db_lo, int64_t Q, int64_t N, int D, int64_t ldq,
+                            int64_t lddb, const uint8_t* q_fold, const uint8_t* db_fold, int fold_sorted,
+                            int64_t idx_base, int K, int precision, uint64_t* out_keys, void* workspace,
+                            size_t ws_bytes, float* debug_scores, void* stream) {
+  (void)fold_sorted;   // tile skipping for sorted folds is a scheduling optimisation; results never depend on it
+  if (Q < 0 || N < 0 || D <= 0 || K <= 0 || !out_keys) return fail(EMR2A_ERR_INVALID, "topk_search: bad arguments (Q=%lld N=%lld D=%d K=%d)", (long long)Q, (long long)N, D, K);
+  if ((q_fold == nullptr) != (db_fold == nullptr)) return fail(EMR2A_ERR_INVALID, "topk_search: q_fold and db_fold must be given together");
+  if (idx_base < 0) return fail(EMR2A_ERR_INVALID, "topk_search: negative idx_base");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (Q == 0) return EMR2A_OK;
+  if (N == 0) {
+    const int64_t n = Q * K;
+    zero_keys_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(out_keys, n);
+    EMR2A_LAUNCH_CHECK("zero_keys_kernel");
+    return EMR2A_OK;
+  }
+  switch (precision) {
+    case EMR2A_PREC_FP32:
+      if (!q_f32 || !db_f32) return fail(EMR2A_ERR_INVALID, "topk_search(fp32): q_f32/db_f32 required");
+      if (ldq < D || lddb < D) return fail(EMR2A_ERR_INVALID, "topk_search(fp32): leading dimension smaller than D");
+      return simt_topk_search(q_f32, db_f32, Q, N, D, ldq, lddb, q_fold, db_fold, idx_base, K, out_keys, workspace, ws_bytes, st);
+    case EMR2A_PREC_BF16X3:
+      return tc_topk_search(q_hi, q_lo, db_hi, db_lo, Q, N, D, ldq, lddb, q_fold, db_fold, idx_base, K, 3, out_keys, workspace, ws_bytes, debug_scores, st);
+    case EMR2A_PREC_BF16X1:
+      return tc_topk_search(q_hi, nullptr, db_hi, nullptr, Q, N, D, ldq, lddb, q_fold, db_fold, idx_base, K, 1, out_keys, workspace, ws_bytes, debug_scores, st);
+    default:
+      return fail(EMR2A_ERR_INVALID, "topk_search: unknown precision %d", precision);
+  }
+}
+
+extern "C" int emr2a_topk_search(const float* q_f32, const uint16_t* q_hi, const uint16_t* q_lo, const float* db_f32,
+                                 const uint16_t* db_hi, const uint16_t* db_lo, int64_t Q, int64_t N, int D,
+                                 int64_t ldq, int64_t lddb, const uint8_t* q_fold, const uint8_t* db_fold,
+                                 int fold_sorted, int64_t idx_base, int K, int precision, uint64_t* out_keys,
+                                 void* workspace, size_t ws_bytes, void* stream) {
+  return topk_search_impl(q_f32, q_hi, q_lo, db_f32, db_hi, db_lo, Q, N, D, ldq, lddb, q_fold, db_fold, fold_sorted,
+                          idx_base, K, precision, out_keys, workspace, ws_bytes, nullptr, stream);
+}
+
+// Diagnostics: same as emr2a_topk_search on the tensor-core arms, additionally dumping every
+// score the epilogue saw to debug_scores [Q, N] (tests compare the GEMM itself with the oracle).
+extern "C" int emr2a_debug_topk_search_dump(const uint16_t* q_hi, const uint16_t* q_lo, const uint16_t* db_hi,
+                                            const uint16_t* db_lo, int64_t Q, int64_t N, int D, int64_t ldq,
+                                            int64_t lddb, const uint8_t* q_fold, const uint8_t* db_fold,
+                                            int64_t idx_base, int K, int precision, uint64_t* out_keys,
+                                            void* workspace, size_t ws_bytes, float* debug_scores, void* stream) {
+  if (precision != EMR2A_PREC_BF16X3 && precision != EMR2A_PREC_BF16X1)
+    return fail(EMR2A_ERR_INVALID, "debug dump is for the tensor-core arms only");
+  return topk_search_impl(nullptr, q_hi, q_lo, nullptr, db_hi, db_lo, Q, N, D, ldq, lddb, q_fold, db_fold, 0,
+                          idx_base, K, precision, out_keys, workspace, ws_bytes, debug_scores, stream);
+}

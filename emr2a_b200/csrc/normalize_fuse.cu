@@ -1,0 +1,265 @@
+// K1: fused L2-normalise + weight + concatenate (+ bf16 hi/lo split) -- one pass over HBM.
+//
+// Roofline: HBM-bound.  Algorithmic bytes per row =
+//   (d0 + d1) * sizeof(in)  read  +  (d0 + d1) * 4 (fp32 out, if requested)
+//   + 2 * ld_bf16 * 2 (hi/lo planes, if requested) + 4 (inverse norm, if requested).
+// One warp owns one row; the row lives in registers between the norm reductions and
+// the store (read once, written once), loads are 128-bit and coalesced, streaming
+// (L1::no_allocate).  The arithmetic mirrors the reference op for op -- true IEEE
+// divisions by (sqrt(sum x^2) + 1e-8f) in fp32 -- so the fp32 output differs from
+// numpy only through the summation order of the norm (<= ~1e-7 relative).
+#include "common.cuh"
+
+namespace emr2a {
+
+struct NfParams {
+  const void* seg0;
+  const void* seg1;
+  int64_t n;
+  int d0, d1;
+  int64_t ld0, ld1;
+  float w0, w1;
+  int flags;
+  float* out_f32;
+  int64_t ld_f32;
+  uint16_t* out_hi;
+  uint16_t* out_lo;
+  int64_t ld_bf16;
+  float* inv_norm;
+};
+
+template <typename InT> struct Loader;
+template <> struct Loader<float> {
+  static __device__ __forceinline__ float4 load4(const void* base, int64_t elem) {
+    return ldg_stream_f4(reinterpret_cast<const float4*>(static_cast<const float*>(base) + elem));
+  }
+  static __device__ __forceinline__ float load1(const void* base, int64_t elem) {
+    return __ldg(static_cast<const float*>(base) + elem);
+  }
+};
+template <> struct Loader<__nv_bfloat16> {
+  static __device__ __forceinline__ float4 load4(const void* base, int64_t elem) {
+    uint2 r = ldg_stream_u2(reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(base) + elem));
+    float4 f;
+    f.x = __uint_as_float(r.x << 16);
+    f.y = __uint_as_float(r.x & 0xFFFF0000u);
+    f.z = __uint_as_float(r.y << 16);
+    f.w = __uint_as_float(r.y & 0xFFFF0000u);
+    return f;
+  }
+  static __device__ __forceinline__ float load1(const void* base, int64_t elem) {
+    uint16_t r = __ldg(static_cast<const uint16_t*>(base) + elem);
+    return __uint_as_float(static_cast<uint32_t>(r) << 16);
+  }
+};
+
+__device__ __forceinline__ float sq4(const float4& a) { return a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w; }
+__device__ __forceinline__ void div4(float4& a, float d) {
+  a.x = __fdiv_rn(a.x, d); a.y = __fdiv_rn(a.y, d); a.z = __fdiv_rn(a.z, d); a.w = __fdiv_rn(a.w, d);
+}
+__device__ __forceinline__ void mul4(float4& a, float w) { a.x *= w; a.y *= w; a.z *= w; a.w *= w; }
+
+// Register-cached path: every lane keeps MAXC chunks of 4 elements.
+template <typename InT, int MAXC>
+__global__ void __launch_bounds__(256) normalize_fuse_vec_kernel(const NfParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int c0 = p.d0 >> 2;
+  const int ctot = (p.d0 + p.d1) >> 2;
+  const int cpad = p.out_hi ? static_cast<int>(p.ld_bf16 >> 2) : ctot;
+
+  for (int64_t row = warp0; row < p.n; row += nwarps) {
+    float4 v[MAXC];
+    float ss0 = 0.f, ss1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXC; ++j) {
+      const int c = lane + 32 * j;
+      if (c < c0) {
+        v[j] = Loader<InT>::load4(p.seg0, row * p.ld0 + 4 * c);
+        ss0 += sq4(v[j]);
+      } else if (c < ctot) {
+        v[j] = Loader<InT>::load4(p.seg1, row * p.ld1 + 4 * (c - c0));
+        ss1 += sq4(v[j]);
+      } else {
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    if (p.flags & EMR2A_NF_SEGNORM) {
+      const float n0 = __fsqrt_rn(warp_sum(ss0)) + EMR2A_EPS;
+      const float n1 = __fsqrt_rn(warp_sum(ss1)) + EMR2A_EPS;
+#pragma unroll
+      for (int j = 0; j < MAXC; ++j) {
+        const int c = lane + 32 * j;
+        if (c < c0) div4(v[j], n0); else if (c < ctot) div4(v[j], n1);
+      }
+    }
+    if (p.w0 != 1.0f || p.w1 != 1.0f) {
+#pragma unroll
+      for (int j = 0; j < MAXC; ++j) {
+        const int c = lane + 32 * j;
+        if (c < c0) mul4(v[j], p.w0); else if (c < ctot) mul4(v[j], p.w1);
+      }
+    }
+    float inv = 1.0f;
+    if (p.flags & (EMR2A_NF_ROWNORM | EMR2A_NF_ZERO_GUARD)) {
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < MAXC; ++j) ss += sq4(v[j]);
+      float nrm = __fsqrt_rn(warp_sum(ss));
+      const bool guard = (p.flags & EMR2A_NF_ZERO_GUARD) != 0;
+      if (!guard) nrm += EMR2A_EPS;
+      if (!(guard && nrm == 0.f)) {
+#pragma unroll
+        for (int j = 0; j < MAXC; ++j) div4(v[j], nrm);
+        inv = __fdiv_rn(1.0f, nrm);
+      }
+    }
+    if (p.inv_norm && lane == 0) p.inv_norm[row] = inv;
+    if (p.out_f32) {
+#pragma unroll
+      for (int j = 0; j < MAXC; ++j) {
+        const int c = lane + 32 * j;
+        if (c < ctot) *reinterpret_cast<float4*>(p.out_f32 + row * p.ld_f32 + 4 * c) = v[j];
+      }
+    }
+    if (p.out_hi) {
+#pragma unroll
+      for (int j = 0; j < MAXC; ++j) {
+        const int c = lane + 32 * j;
+        if (c < cpad) {
+          uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
+          split_bf16(v[j].x, h0, l0); split_bf16(v[j].y, h1, l1);
+          split_bf16(v[j].z, h2, l2); split_bf16(v[j].w, h3, l3);
+          uint2 hv = make_uint2(h0 | (static_cast<uint32_t>(h1) << 16), h2 | (static_cast<uint32_t>(h3) << 16));
+          *reinterpret_cast<uint2*>(p.out_hi + row * p.ld_bf16 + 4 * c) = hv;
+          if (p.out_lo) {
+            uint2 lv = make_uint2(l0 | (static_cast<uint32_t>(l1) << 16), l2 | (static_cast<uint32_t>(l3) << 16));
+            *reinterpret_cast<uint2*>(p.out_lo + row * p.ld_bf16 + 4 * c) = lv;
+          }
+        }
+      }
+    }
+  }
+}
+
+// Generic path (any d0/d1/alignment): scalar loads, the row is re-read through L1/L2.
+template <typename InT>
+__global__ void __launch_bounds__(256) normalize_fuse_scalar_kernel(const NfParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int dtot = p.d0 + p.d1;
+  const bool segnorm = (p.flags & EMR2A_NF_SEGNORM) != 0;
+  for (int64_t row = warp0; row < p.n; row += nwarps) {
+    float n0 = 1.f, n1 = 1.f;
+    if (segnorm) {
+      float ss0 = 0.f, ss1 = 0.f;
+      for (int e = lane; e < p.d0; e += 32) { float x = Loader<InT>::load1(p.seg0, row * p.ld0 + e); ss0 += x * x; }
+      for (int e = lane; e < p.d1; e += 32) { float x = Loader<InT>::load1(p.seg1, row * p.ld1 + e); ss1 += x * x; }
+      n0 = __fsqrt_rn(warp_sum(ss0)) + EMR2A_EPS;
+      n1 = __fsqrt_rn(warp_sum(ss1)) + EMR2A_EPS;
+    }
+    auto value = [&](int e) -> float {
+      float x;
+      if (e < p.d0) {
+        x = Loader<InT>::load1(p.seg0, row * p.ld0 + e);
+        if (segnorm) x = __fdiv_rn(x, n0);
+        x *= p.w0;
+      } else {
+        x = Loader<InT>::load1(p.seg1, row * p.ld1 + (e - p.d0));
+        if (segnorm) x = __fdiv_rn(x, n1);
+        x *= p.w1;
+      }
+      return x;
+    };
+    float nrm = 1.f, inv = 1.f;
+    bool divide = false;
+    if (p.flags & (EMR2A_NF_ROWNORM | EMR2A_NF_ZERO_GUARD)) {
+      float ss = 0.f;
+      for (int e = lane; e < dtot; e += 32) { float x = value(e); ss += x * x; }
+      nrm = __fsqrt_rn(warp_sum(ss));
+      const bool guard = (p.flags & EMR2A_NF_ZERO_GUARD) != 0;
+      if (!guard) nrm += EMR2A_EPS;
+      divide = !(guard && nrm == 0.f);
+      if (divide) inv = __fdiv_rn(1.0f, nrm);
+    }
+    if (p.inv_norm && lane == 0) p.inv_norm[row] = inv;
+    const int epad = p.out_hi ? static_cast<int>(p.ld_bf16) : dtot;
+    for (int e = lane; e < epad; e += 32) {
+      float x = 0.f;
+      if (e < dtot) {
+        x = value(e);
+        if (divide) x = __fdiv_rn(x, nrm);
+        if (p.out_f32) p.out_f32[row * p.ld_f32 + e] = x;
+      }
+      if (p.out_hi) {
+        uint16_t h, l;
+        split_bf16(x, h, l);
+        p.out_hi[row * p.ld_bf16 + e] = h;
+        if (p.out_lo) p.out_lo[row * p.ld_bf16 + e] = l;
+      }
+    }
+  }
+}
+
+template <typename InT>
+static int launch_nf(const NfParams& p, bool vec_ok, cudaStream_t st) {
+  const int threads = 256;
+  const int64_t warps_needed = p.n;
+  const int sms = sm_count();
+  const int ctot = (p.d0 + p.d1) >> 2;
+  const int cpad = p.out_hi ? static_cast<int>(p.ld_bf16 >> 2) : ctot;
+  const int cmax = cpad > ctot ? cpad : ctot;
+  int64_t blocks = (warps_needed + 7) / 8;
+  if (vec_ok && cmax <= 32 * 48) {
+    // grid: a multiple of the SM count; resident CTAs per SM depend on the register footprint
+    if (cmax <= 32 * 4) {
+      int64_t cap = static_cast<int64_t>(sms) * 8; if (blocks > cap) blocks = cap;
+      normalize_fuse_vec_kernel<InT, 4><<<static_cast<unsigned>(blocks), threads, 0, st>>>(p);
+    } else if (cmax <= 32 * 8) {
+      int64_t cap = static_cast<int64_t>(sms) * 6; if (blocks > cap) blocks = cap;
+      normalize_fuse_vec_kernel<InT, 8><<<static_cast<unsigned>(blocks), threads, 0, st>>>(p);
+    } else if (cmax <= 32 * 16) {
+      int64_t cap = static_cast<int64_t>(sms) * 3; if (blocks > cap) blocks = cap;
+      normalize_fuse_vec_kernel<InT, 16><<<static_cast<unsigned>(blocks), threads, 0, st>>>(p);
+    } else {
+      int64_t cap = static_cast<int64_t>(sms) * 1; if (blocks > cap) blocks = cap;
+      normalize_fuse_vec_kernel<InT, 48><<<static_cast<unsigned>(blocks), threads, 0, st>>>(p);
+    }
+  } else {
+    int64_t cap = static_cast<int64_t>(sms) * 8; if (blocks > cap) blocks = cap;
+    normalize_fuse_scalar_kernel<InT><<<static_cast<unsigned>(blocks), threads, 0, st>>>(p);
+  }
+  EMR2A_LAUNCH_CHECK("normalize_fuse kernel");
+  return EMR2A_OK;
+}
+
+}  // namespace emr2a
+
+using namespace emr2a;
+
+extern "C" int emr2a_normalize_fuse(const void* seg0, const void* seg1, int64_t n, int d0, int d1,
+                                    int64_t ld0, int64_t ld1, float w0, float w1, int flags, int in_dtype,
+                                    float* out_f32, int64_t ld_f32, uint16_t* out_hi, uint16_t* out_lo,
+                                    int64_t ld_bf16, float* inv_norm_out, void* stream) {
+  if (n < 0 || d0 <= 0 || d1 < 0) return fail(EMR2A_ERR_INVALID, "normalize_fuse: bad shape n=%lld d0=%d d1=%d", (long long)n, d0, d1);
+  if (!seg0 || (d1 > 0 && !seg1)) return fail(EMR2A_ERR_INVALID, "normalize_fuse: null segment pointer");
+  if (ld0 < d0 || (d1 > 0 && ld1 < d1)) return fail(EMR2A_ERR_INVALID, "normalize_fuse: leading dimension smaller than row");
+  if (in_dtype != EMR2A_F32 && in_dtype != EMR2A_BF16) return fail(EMR2A_ERR_INVALID, "normalize_fuse: unknown dtype %d", in_dtype);
+  if (out_lo && !out_hi) return fail(EMR2A_ERR_INVALID, "normalize_fuse: out_lo without out_hi");
+  if (out_f32 && ld_f32 < d0 + d1) return fail(EMR2A_ERR_INVALID, "normalize_fuse: ld_f32 too small");
+  if (out_hi && ld_bf16 < d0 + d1) return fail(EMR2A_ERR_INVALID, "normalize_fuse: ld_bf16 too small");
+  if (n == 0) return EMR2A_OK;
+  NfParams p{seg0, seg1, n, d0, d1, ld0, d1 > 0 ? ld1 : 0, w0, w1, flags,
+             out_f32, ld_f32, out_hi, out_lo, ld_bf16, inv_norm_out};
+  const size_t in_align = in_dtype == EMR2A_F32 ? 16 : 8;
+  auto aligned = [](const void* q, size_t a) { return (reinterpret_cast<uintptr_t>(q) % a) == 0; };
+  bool vec_ok = (d0 % 4 == 0) && (d1 % 4 == 0) && (ld0 % 4 == 0) && (d1 == 0 || ld1 % 4 == 0) &&
+                aligned(seg0, in_align) && (d1 == 0 || aligned(seg1, in_align));
+  if (out_f32) vec_ok = vec_ok && (ld_f32 % 4 == 0) && aligned(out_f32, 16);
+  if (out_hi) vec_ok = vec_ok && (ld_bf16 % 4 == 0) && aligned(out_hi, 8) && (!out_lo || aligned(out_lo, 8));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (in_dtype == EMR2A_F32) return launch_nf<float>(p, vec_ok, st);
+  return launch_nf<__nv_bfloat16>(p, vec_ok, st);
+}

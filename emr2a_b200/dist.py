@@ -1,0 +1,65 @@
+"""Row-sharded database across GPUs: one process per GPU, ``torch.distributed`` (NCCL over
+NVLink/NVSwitch) for the single exchange step of the path -- an all-gather of each rank's
+local Top-K keys (Q x K x 8 bytes), merged by the K3 kernel.  Global row indices travel
+inside the keys, and ties break on the global index, so results are bit-identical for any
+GPU count."""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_rows: int, rank: int, world: int, align: int = 256) -> Tuple[int, int]:
+    """Contiguous, tile-aligned row range [lo, hi) of ``rank``; the last rank takes the tail."""
+    per = (n_rows + world - 1) // world
+    per = (per + align - 1) // align * align
+    lo = min(rank * per, n_rows)
+    hi = min(lo + per, n_rows)
+    return lo, hi
+
+
+def gather_keys(local_keys: torch.Tensor, group=None) -> torch.Tensor:
+    """All-gather [Q, K] packed keys -> [world, Q, K].  Works for CUDA tensors (NCCL) and for
+    CPU tensors (gloo; used by the CPU tests of this plumbing)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return local_keys.unsqueeze(0)
+    local_keys = local_keys.contiguous()
+    out = torch.empty((world,) + tuple(local_keys.shape), dtype=local_keys.dtype, device=local_keys.device)
+    if local_keys.is_cuda:
+        dist.all_gather_into_tensor(out.view(-1), local_keys.view(-1), group=group)
+    else:
+        parts = [out[r] for r in range(world)]
+        dist.all_gather(parts, local_keys, group=group)
+    return out
+
+
+def sharded_search_and_vote(eng, db_segs_local: Sequence, q_segs: Sequence, db_labels_global, q_labels,
+                            n_classes: int, k: int, row_offset: int, db_flags: int, q_flags: int,
+                            q_weights=(1.0, 1.0), k_list=(1, 3, 5), precision: str = "auto",
+                            q_fold=None, db_fold_local=None, q_group=None, n_groups: int = 1,
+                            want_lists: bool = True, timers: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+    """Each rank: K1 on its database shard and on the (replicated) queries, local K2 with
+    ``idx_base = row_offset``; all-gather keys; K3 merge; K4 vote on the merged lists."""
+    n_q = int(q_segs[0].shape[0])
+    n_db = int(db_segs_local[0].shape[0])
+    dim = sum(int(s.shape[1]) for s in db_segs_local if s is not None)
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    prec = eng.pick_precision(n_q, max(n_db, 1) * world, dim, k, precision)
+    db = eng.prepare(db_segs_local[0], db_segs_local[1] if len(db_segs_local) > 1 else None, 1.0, 1.0, db_flags, prec)
+    qs = eng.prepare(q_segs[0], q_segs[1] if len(q_segs) > 1 else None, q_weights[0], q_weights[1], q_flags, prec)
+    if timers is not None:
+        timers["k2_start"].record()
+    keys = eng.topk_search(qs, db, k, prec, q_fold=q_fold, db_fold=db_fold_local, idx_base=row_offset)
+    if timers is not None:
+        timers["k2_end"].record()
+    if world > 1:
+        allk = gather_keys(keys)
+        keys = eng.topk_merge(allk, k)
+    res = eng.vote_metrics(keys, db_labels_global, q_labels, n_classes, k_list=k_list, q_group=q_group,
+                           n_groups=n_groups, want_lists=want_lists)
+    res["keys"] = keys
+    res["precision"] = prec
+    return res

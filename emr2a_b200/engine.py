@@ -1,0 +1,410 @@
+"""Host orchestration of the B200 retrieval hot path.
+
+PyTorch is plumbing here (device memory, streams, pinned staging); every
+computation is a libemr2a.so kernel reached through the C-ABI in
+``include/emr2a.h``.  There is no CPU fallback.
+
+Pipeline (per database/query pair):
+    K1 normalize_fuse  ->  K2 topk_search (+K3 merge of partial lists)  ->  K4 vote_metrics
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import native
+
+_PREC = {"fp32": native.PREC_FP32, "bf16x3": native.PREC_BF16X3, "bf16x1": native.PREC_BF16X1}
+# tensor cores pay off once the contraction is large; below this the exact fp32 arm is used
+_TC_MIN_MACS = float(os.environ.get("EMR2A_TC_MIN_MACS", 2.0e9))
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+@dataclass
+class Operand:
+    """Rows prepared by K1 for K2: fp32 rows and/or bf16 hi/lo planes."""
+    n: int
+    dim: int
+    f32: Optional[torch.Tensor] = None      # [n, dim]
+    hi: Optional[torch.Tensor] = None       # [n, ld] bf16 bits (int16 storage)
+    lo: Optional[torch.Tensor] = None
+    inv_norm: Optional[torch.Tensor] = None
+
+    @property
+    def ld_planes(self) -> int:
+        return 0 if self.hi is None else self.hi.shape[1]
+
+
+class Engine:
+    """One engine per process/GPU (the multi-GPU path runs one process per GPU)."""
+
+    def __init__(self, device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("emr2a_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.lib = native.load()
+        with torch.cuda.device(self.device):
+            self.sm_count, self.cc_major, self.cc_minor = native.device_check()
+        self.launches = 0       # kernels of ours launched through this engine (bench reports it)
+
+    # ------------------------------------------------------------------ utils
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def to_device(self, x, dtype=None) -> torch.Tensor:
+        if isinstance(x, np.ndarray):
+            t = torch.from_numpy(np.ascontiguousarray(x))
+        elif isinstance(x, torch.Tensor):
+            t = x
+        else:
+            t = torch.as_tensor(np.asarray(x))
+        if dtype is not None and t.dtype != dtype:
+            t = t.to(dtype)
+        if t.device != self.device:
+            t = t.to(self.device, non_blocking=True)
+        return t.contiguous()
+
+    def _embedding(self, x) -> Tuple[torch.Tensor, int]:
+        """Device matrix + emr2a dtype code.  float64/float16 inputs are computed in fp32."""
+        if isinstance(x, np.ndarray) and x.dtype not in (np.float32,):
+            x = x.astype(np.float32)
+        t = self.to_device(x)
+        if t.dtype == torch.bfloat16:
+            code = native.BF16
+        else:
+            if t.dtype != torch.float32:
+                t = t.float()
+            code = native.F32
+        if t.dim() == 1:
+            t = t.unsqueeze(0)
+        return t.contiguous(), code
+
+    # --------------------------------------------------------------------- K1
+    def normalize_fuse(self, seg0, seg1=None, w0: float = 1.0, w1: float = 1.0, flags: int = native.NF_ROWNORM,
+                       want_f32: bool = True, want_planes: bool = False, want_lo: bool = True,
+                       want_inv_norm: bool = False) -> Operand:
+        a, code = self._embedding(seg0)
+        n, d0 = a.shape
+        b = None
+        d1 = 0
+        if seg1 is not None:
+            b, code_b = self._embedding(seg1)
+            if b.shape[0] != n:
+                raise ValueError("normalize_fuse: segments have different row counts")
+            if code_b != code:
+                a, b, code = a.float(), b.float(), native.F32
+            d1 = b.shape[1]
+        dim = d0 + d1
+        out = Operand(n=n, dim=dim)
+        if want_f32:
+            out.f32 = torch.empty((n, dim), dtype=torch.float32, device=self.device)
+        ld_planes = 0
+        if want_planes:
+            ld_planes = _round_up(dim, 64)
+            out.hi = torch.empty((n, ld_planes), dtype=torch.int16, device=self.device)
+            if want_lo:
+                out.lo = torch.empty((n, ld_planes), dtype=torch.int16, device=self.device)
+        if want_inv_norm:
+            out.inv_norm = torch.empty((n,), dtype=torch.float32, device=self.device)
+        if n == 0:
+            return out
+        with torch.cuda.device(self.device):
+            native.check(self.lib.emr2a_normalize_fuse(
+                a.data_ptr(), native.ptr(b), n, d0, d1, a.stride(0), b.stride(0) if b is not None else 0,
+                float(w0), float(w1), int(flags), code,
+                native.ptr(out.f32), dim, native.ptr(out.hi), native.ptr(out.lo), ld_planes,
+                native.ptr(out.inv_norm), self._stream()))
+        self.launches += 1
+        return out
+
+    # ----------------------------------------------------------------- scores
+    def scores(self, q: torch.Tensor, db: torch.Tensor) -> torch.Tensor:
+        """Full fp32 score matrix [Q, N] (CUDA cores)."""
+        q = self.to_device(q, torch.float32)
+        db = self.to_device(db, torch.float32)
+        if q.dim() == 1:
+            q = q.unsqueeze(0)
+        Q, D = q.shape
+        N = db.shape[0]
+        if db.shape[1] != D:
+            raise ValueError(f"scores: query dim {D} != database dim {db.shape[1]}")
+        out = torch.empty((Q, N), dtype=torch.float32, device=self.device)
+        if Q and N:
+            with torch.cuda.device(self.device):
+                native.check(self.lib.emr2a_scores(q.data_ptr(), db.data_ptr(), Q, N, D, q.stride(0), db.stride(0),
+                                                   out.data_ptr(), N, self._stream()))
+            self.launches += 1
+        return out
+
+    def euclid_scores(self, q: torch.Tensor, db: torch.Tensor) -> torch.Tensor:
+        q = self.to_device(q, torch.float32).reshape(-1)
+        db = self.to_device(db, torch.float32)
+        N, D = db.shape
+        out = torch.empty((N,), dtype=torch.float32, device=self.device)
+        ws = torch.empty((16,), dtype=torch.uint8, device=self.device)
+        if N:
+            with torch.cuda.device(self.device):
+                native.check(self.lib.emr2a_euclid_scores(q.data_ptr(), db.data_ptr(), N, D, db.stride(0),
+                                                          out.data_ptr(), ws.data_ptr(), 16, self._stream()))
+            self.launches += 2
+        return out
+
+    def late_fuse_scores(self, text_scores, image_scores, w_text: float, mode: int) -> torch.Tensor:
+        ts = self.to_device(text_scores, torch.float32)
+        im = self.to_device(image_scores, torch.float32)
+        one_d = ts.dim() == 1
+        if one_d:
+            ts, im = ts.unsqueeze(0), im.unsqueeze(0)
+        Q, N = ts.shape
+        out = torch.empty((Q, N), dtype=torch.float32, device=self.device)
+        if Q and N:
+            with torch.cuda.device(self.device):
+                native.check(self.lib.emr2a_late_fuse_scores(ts.data_ptr(), im.data_ptr(), Q, N, ts.stride(0),
+                                                             float(np.float32(w_text)), float(np.float32(1 - w_text)),
+                                                             mode, out.data_ptr(), N, self._stream()))
+            self.launches += 1
+        return out[0] if one_d else out
+
+    def topk_from_scores(self, scores, k: int) -> torch.Tensor:
+        s = self.to_device(scores, torch.float32)
+        if s.dim() == 1:
+            s = s.unsqueeze(0)
+        Q, N = s.shape
+        keys = torch.zeros((Q, k), dtype=torch.int64, device=self.device)
+        if Q and N:
+            with torch.cuda.device(self.device):
+                native.check(self.lib.emr2a_topk_from_scores(s.data_ptr(), Q, N, s.stride(0), k, keys.data_ptr(),
+                                                             self._stream()))
+            self.launches += 1
+        return keys
+
+    # --------------------------------------------------------------------- K2
+    def pick_precision(self, Q: int, N: int, D: int, K: int, requested: str = "auto") -> str:
+        req = os.environ.get("EMR2A_PRECISION", requested) if requested == "auto" else requested
+        if req != "auto":
+            if req not in _PREC:
+                raise ValueError(f"unknown precision {req!r}")
+            return req
+        if K <= 32 and float(Q) * float(N) * float(D) >= _TC_MIN_MACS:
+            return "bf16x3"
+        return "fp32"
+
+    def prepare(self, seg0, seg1=None, w0=1.0, w1=1.0, flags=native.NF_ROWNORM, precision="fp32") -> Operand:
+        """K1 with the outputs the chosen K2 arm consumes."""
+        if precision == "fp32":
+            return self.normalize_fuse(seg0, seg1, w0, w1, flags, want_f32=True, want_planes=False)
+        return self.normalize_fuse(seg0, seg1, w0, w1, flags, want_f32=False, want_planes=True,
+                                   want_lo=(precision == "bf16x3"))
+
+    def topk_search(self, q: Operand, db: Operand, k: int, precision: str = "fp32",
+                    q_fold: Optional[torch.Tensor] = None, db_fold: Optional[torch.Tensor] = None,
+                    fold_sorted: bool = False, idx_base: int = 0) -> torch.Tensor:
+        """Packed Top-K keys [Q, k] (int64 storage of the uint64 keys), best first."""
+        if q.dim != db.dim:
+            raise ValueError(f"topk_search: query dim {q.dim} != database dim {db.dim}")
+        prec = _PREC[precision]
+        Q, N, D = q.n, db.n, q.dim
+        keys = torch.empty((Q, k), dtype=torch.int64, device=self.device)
+        if Q == 0:
+            return keys
+        ws_bytes = int(self.lib.emr2a_topk_search_workspace_bytes(Q, N, D, k, prec))
+        ws = torch.empty((ws_bytes + 256,), dtype=torch.uint8, device=self.device)
+        ws_ptr = _round_up(ws.data_ptr(), 256)
+        if prec == native.PREC_FP32:
+            if q.f32 is None or db.f32 is None:
+                raise ValueError("topk_search(fp32) needs fp32 operands")
+            ldq, lddb = q.f32.stride(0), db.f32.stride(0)
+        else:
+            if q.hi is None or db.hi is None or (prec == native.PREC_BF16X3 and (q.lo is None or db.lo is None)):
+                raise ValueError("topk_search(bf16) needs bf16 operand planes")
+            ldq, lddb = q.hi.stride(0), db.hi.stride(0)
+        if q_fold is not None:
+            q_fold = self.to_device(q_fold, torch.uint8)
+            db_fold = self.to_device(db_fold, torch.uint8)
+        with torch.cuda.device(self.device):
+            native.check(self.lib.emr2a_topk_search(
+                native.ptr(q.f32), native.ptr(q.hi), native.ptr(q.lo),
+                native.ptr(db.f32), native.ptr(db.hi), native.ptr(db.lo),
+                Q, N, D, ldq, lddb, native.ptr(q_fold), native.ptr(db_fold), int(fold_sorted),
+                int(idx_base), int(k), prec, keys.data_ptr(), ws_ptr, ws_bytes, self._stream()))
+        self.launches += 2
+        return keys
+
+    # --------------------------------------------------------------------- K3
+    def topk_merge(self, parts: torch.Tensor, k_out: int) -> torch.Tensor:
+        """parts: [P, Q, K_in] packed keys -> [Q, k_out]."""
+        P, Q, K_in = parts.shape
+        parts = parts.contiguous()
+        out = torch.empty((Q, k_out), dtype=torch.int64, device=self.device)
+        if Q:
+            with torch.cuda.device(self.device):
+                native.check(self.lib.emr2a_topk_merge(parts.data_ptr(), P, Q, K_in, Q * K_in, K_in, k_out,
+                                                       out.data_ptr(), self._stream()))
+            self.launches += 1
+        return out
+
+    # --------------------------------------------------------------------- K4
+    def vote_metrics(self, keys: torch.Tensor, db_labels, q_labels, n_classes: int,
+                     k_list: Sequence[int] = (1, 3, 5), wacc_f32: bool = False,
+                     q_group: Optional[torch.Tensor] = None, n_groups: int = 1, label_base: int = 0,
+                     per_query: bool = True, want_lists: bool = True) -> Dict[str, torch.Tensor]:
+        Q, K = keys.shape
+        db_labels = self.to_device(db_labels, torch.int32)
+        q_labels = self.to_device(q_labels, torch.int32)
+        if q_group is not None:
+            q_group = self.to_device(q_group, torch.uint8)
+        nk = len(k_list)
+        dev = self.device
+        counters = torch.zeros((n_groups * (nk + 3 + 1 + 2 * n_classes * n_classes),), dtype=torch.int64, device=dev)
+        o = 0
+        hit = counters[o:o + n_groups * nk]; o += n_groups * nk
+        votes = counters[o:o + n_groups * 3]; o += n_groups * 3
+        sizes = counters[o:o + n_groups]; o += n_groups
+        conf = counters[o:]
+        res: Dict[str, torch.Tensor] = {}
+        if want_lists:
+            res["top_idx"] = torch.empty((Q, K), dtype=torch.int64, device=dev)
+            res["top_scores"] = torch.empty((Q, K), dtype=torch.float32, device=dev)
+            res["top_labels"] = torch.empty((Q, K), dtype=torch.int32, device=dev)
+        if per_query:
+            for name in ("pred_top1", "pred_vote", "pred_weighted"):
+                res[name] = torch.empty((Q,), dtype=torch.int32, device=dev)
+        kl = (C.c_int32 * max(nk, 1))(*[int(k) for k in k_list])
+        if Q:
+            with torch.cuda.device(dev):
+                native.check(self.lib.emr2a_vote_metrics(
+                    keys.data_ptr(), Q, K, db_labels.data_ptr(), int(label_base), q_labels.data_ptr(),
+                    native.ptr(q_group), n_groups, n_classes, kl, nk, int(wacc_f32),
+                    native.ptr(res.get("top_idx")), native.ptr(res.get("top_scores")), native.ptr(res.get("top_labels")),
+                    native.ptr(res.get("pred_top1")), native.ptr(res.get("pred_vote")), native.ptr(res.get("pred_weighted")),
+                    hit.data_ptr(), votes.data_ptr(), conf.data_ptr(), sizes.data_ptr(), self._stream()))
+            self.launches += 1
+        res["hit_counts"] = hit.view(n_groups, nk)
+        res["vote_counts"] = votes.view(n_groups, 3)
+        res["group_sizes"] = sizes
+        res["confusion"] = conf.view(n_groups, 2, n_classes, n_classes)
+        return res
+
+    # --------------------------------------------------------- fused pipeline
+    def search_and_vote(self, db_segs: Sequence, q_segs: Sequence, db_labels, q_labels, n_classes: int, k: int,
+                        db_weights=(1.0, 1.0), q_weights=(1.0, 1.0), db_flags: int = native.NF_ROWNORM,
+                        q_flags: int = native.NF_ROWNORM, k_list: Sequence[int] = (1, 3, 5),
+                        precision: str = "auto", wacc_f32: bool = False, q_fold=None, db_fold=None,
+                        q_group=None, n_groups: int = 1, want_lists: bool = True) -> Dict[str, torch.Tensor]:
+        """normalize+fuse both sides, Top-K search, vote + metrics; everything stays on the device."""
+        n_db = int(db_segs[0].shape[0])
+        n_q = int(q_segs[0].shape[0])
+        dim = sum(int(s.shape[1]) for s in db_segs if s is not None)
+        prec = self.pick_precision(n_q, n_db, dim, k, precision)
+        db = self.prepare(db_segs[0], db_segs[1] if len(db_segs) > 1 else None, db_weights[0], db_weights[1], db_flags, prec)
+        qs = self.prepare(q_segs[0], q_segs[1] if len(q_segs) > 1 else None, q_weights[0], q_weights[1], q_flags, prec)
+        keys = self.topk_search(qs, db, k, prec, q_fold=q_fold, db_fold=db_fold)
+        res = self.vote_metrics(keys, db_labels, q_labels, n_classes, k_list=k_list, wacc_f32=wacc_f32,
+                                q_group=q_group, n_groups=n_groups, want_lists=want_lists)
+        res["keys"] = keys
+        res["precision"] = prec
+        return res
+
+
+    # ----------------------------------------------- host-buffer (end-to-end) path
+    def search_and_vote_host(self, db_segs_host: Sequence, q_segs_host: Sequence, db_labels, q_labels,
+                             n_classes: int, k: int, db_flags: int = native.NF_ROWNORM,
+                             q_flags: int = native.NF_ROWNORM, q_weights=(1.0, 1.0),
+                             k_list: Sequence[int] = (1, 3, 5), precision: str = "auto",
+                             chunk_rows: int = 131072, row_offset: int = 0,
+                             reduce_fn=None) -> Dict[str, object]:
+        """Same pipeline as ``search_and_vote`` for HOST-resident inputs (pinned CPU tensors or
+        numpy): the database streams to the device in row chunks on a copy stream while the
+        previous chunk is normalised and searched on the compute stream; per-chunk Top-K lists
+        are merged by K3, K4 votes, and the results are copied back to the host.
+        ``reduce_fn(keys) -> keys`` lets the multi-GPU caller all-gather + merge before the vote."""
+        def as_host(x):
+            return torch.from_numpy(x) if isinstance(x, np.ndarray) else x
+        db_host = [as_host(s) for s in db_segs_host if s is not None]
+        q_host = [as_host(s) for s in q_segs_host if s is not None]
+        n_db, n_q = int(db_host[0].shape[0]), int(q_host[0].shape[0])
+        dim = sum(int(s.shape[1]) for s in db_host)
+        prec = self.pick_precision(n_q, n_db, dim, k, precision)
+        compute = torch.cuda.current_stream(self.device)
+        copy = torch.cuda.Stream(self.device)
+        h2d = 0
+        q_dev = [s.to(self.device, non_blocking=True) for s in q_host]
+        h2d += sum(s.numel() * s.element_size() for s in q_host)
+        qs = self.prepare(q_dev[0], q_dev[1] if len(q_dev) > 1 else None, q_weights[0], q_weights[1], q_flags, prec)
+        chunk_rows = max(256, min(chunk_rows, max(n_db, 1)))
+        slots = [[torch.empty((chunk_rows, int(s.shape[1])), dtype=s.dtype, device=self.device) for s in db_host]
+                 for _ in range(2)]
+        for slot in slots:
+            for b in slot:
+                b.record_stream(copy)
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        freed = [torch.cuda.Event(), torch.cuda.Event()]
+        parts: List[torch.Tensor] = []
+        n_chunks = 0
+        for c, lo in enumerate(range(0, n_db, chunk_rows)):
+            hi = min(lo + chunk_rows, n_db)
+            sl = c % 2
+            with torch.cuda.stream(copy):
+                if c >= 2:
+                    copy.wait_event(freed[sl])
+                else:
+                    copy.wait_stream(compute)
+                for b, src in zip(slots[sl], db_host):
+                    b[:hi - lo].copy_(src[lo:hi], non_blocking=True)
+                copied[sl].record(copy)
+            h2d += sum((hi - lo) * int(s.shape[1]) * s.element_size() for s in db_host)
+            compute.wait_event(copied[sl])
+            segs = [b[:hi - lo] for b in slots[sl]]
+            db = self.prepare(segs[0], segs[1] if len(segs) > 1 else None, 1.0, 1.0, db_flags, prec)
+            parts.append(self.topk_search(qs, db, k, prec, idx_base=row_offset + lo))
+            freed[sl].record(compute)
+            n_chunks += 1
+        keys = parts[0] if n_chunks == 1 else self.topk_merge(torch.stack(parts), k)
+        if reduce_fn is not None:
+            keys = reduce_fn(keys)
+        db_labels = as_host(db_labels)
+        q_labels = as_host(q_labels)
+        h2d += db_labels.numel() * 4 + q_labels.numel() * 4
+        res = self.vote_metrics(keys, db_labels, q_labels, n_classes, k_list=k_list)
+        out: Dict[str, object] = {"precision": prec, "h2d_bytes": h2d}
+        d2h = 0
+        for name in ("top_idx", "top_scores", "top_labels", "pred_top1", "pred_vote", "pred_weighted",
+                     "hit_counts", "vote_counts", "confusion", "group_sizes"):
+            t = res[name].to("cpu", non_blocking=False)
+            d2h += t.numel() * t.element_size()
+            out[name] = t
+        out["d2h_bytes"] = d2h
+        return out
+
+
+_engines: Dict[int, Engine] = {}
+
+
+def get_engine(device: Optional[torch.device] = None) -> Engine:
+    if not torch.cuda.is_available():
+        raise RuntimeError("emr2a_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+    if idx not in _engines:
+        _engines[idx] = Engine(torch.device("cuda", idx))
+    return _engines[idx]
+
+
+def unpack_keys(keys: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Host-side decode of packed keys (tests / debugging): returns (scores f32, indices int64, -1 = empty)."""
+    k = keys.cpu().numpy().view(np.uint64)
+    o = (k >> np.uint64(32)).astype(np.uint32)
+    neg = (o & np.uint32(0x80000000)) == 0
+    bits = np.where(neg, ~o, o ^ np.uint32(0x80000000)).astype(np.uint32)
+    scores = bits.view(np.float32)
+    idx = (np.uint64(0xFFFFFFFF) - (k & np.uint64(0xFFFFFFFF))).astype(np.int64)
+    idx[k == 0] = -1
+    scores = np.where(k == 0, np.float32(0), scores)
+    return scores, idx

@@ -46,16 +46,19 @@ def label_names(codes: np.ndarray, n_classes: int) -> list:
 
 
 def device_block(row0: int, rows: int, dim: int, n_classes: int, seed: int, device,
-                 sep: float = SEP):
+                 sep: float = SEP, label_seed: int | None = None):
     """Generate rows [row0, row0+rows) of a (virtually unbounded) class-structured
-    database directly on ``device``.  Deterministic per (seed, row0-chunk): the
-    generator is re-seeded per 65536-row chunk so any shard layout reproduces the
-    same rows.  Returns (float32 [rows, dim], int32 labels [rows])."""
+    database directly on ``device``.  Deterministic per (seed, 65536-row chunk): the
+    generators are re-seeded per chunk so any shard layout reproduces the same rows.
+    Labels come from ``label_seed`` (default ``seed``) so several modalities can share
+    one label vector.  Returns (float32 [rows, dim], int32 labels [rows])."""
     import torch
 
     chunk = 65536
+    label_seed = seed if label_seed is None else label_seed
     xs, ls = [], []
     g = torch.Generator(device=device)
+    gl = torch.Generator(device=device)
     gc = torch.Generator(device=device)
     gc.manual_seed(seed * 1000003 + 17)
     centres = torch.randn((n_classes, dim), generator=gc, device=device, dtype=torch.float32)
@@ -63,8 +66,9 @@ def device_block(row0: int, rows: int, dim: int, n_classes: int, seed: int, devi
     end = row0 + rows
     while r < end:
         c0 = (r // chunk) * chunk
+        gl.manual_seed(label_seed * 1000003 + 7919 + c0 // chunk)
         g.manual_seed(seed * 1000003 + 101 + c0 // chunk)
-        lab = torch.randint(0, n_classes, (chunk,), generator=g, device=device, dtype=torch.int32)
+        lab = torch.randint(0, n_classes, (chunk,), generator=gl, device=device, dtype=torch.int32)
         x = torch.randn((chunk, dim), generator=g, device=device, dtype=torch.float32)
         x += sep * centres[lab.long()]
         lo, hi = r - c0, min(end, c0 + chunk) - c0
@@ -72,3 +76,21 @@ def device_block(row0: int, rows: int, dim: int, n_classes: int, seed: int, devi
         ls.append(lab[lo:hi])
         r = c0 + hi
     return torch.cat(xs), torch.cat(ls)
+
+
+def device_labels(row0: int, rows: int, n_classes: int, label_seed: int, device):
+    """Labels of rows [row0, row0+rows) as ``device_block`` assigns them."""
+    import torch
+
+    chunk = 65536
+    gl = torch.Generator(device=device)
+    out = []
+    r, end = row0, row0 + rows
+    while r < end:
+        c0 = (r // chunk) * chunk
+        gl.manual_seed(label_seed * 1000003 + 7919 + c0 // chunk)
+        lab = torch.randint(0, n_classes, (chunk,), generator=gl, device=device, dtype=torch.int32)
+        lo, hi = r - c0, min(end, c0 + chunk) - c0
+        out.append(lab[lo:hi])
+        r = c0 + hi
+    return torch.cat(out)

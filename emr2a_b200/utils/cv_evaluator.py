@@ -1,0 +1,331 @@
+"""``utils.cv_evaluator.CVRetrievalEvaluator`` on the B200.
+
+Same constructor, methods, argument order, defaults, result keys, file formats and
+errors as the reference class (utils/cv_evaluator.py:26-501).  Inside a fold, everything
+after ``process_embeddings`` -- fusion, similarity, Top-K, votes, hit flags and confusion
+counts (reference lines 186-310, a per-query python loop) -- is one K1 -> K2 -> K4 pass
+on the GPU.  StratifiedKFold / StandardScaler / PCA stay on the host (sklearn) exactly
+as in the reference, so the fold membership and the preprocessing are identical.
+"""
+import csv
+import json
+import logging
+import random
+from pathlib import Path
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+from sklearn.decomposition import PCA
+from sklearn.model_selection import StratifiedKFold
+from sklearn.preprocessing import StandardScaler
+
+from .. import native
+from ..engine import get_engine
+from ..labels import encode, gather_lists, score_lists
+from .metrics import confusion_dict, prf_from_confusion
+
+logging.basicConfig(level=logging.INFO, format="%(asctime)s - %(levelname)s - %(message)s")
+logger = logging.getLogger(__name__)
+
+_SUMMARY_METRICS = ("top1", "top3", "top5", "vote_acc", "weighted_vote_acc",
+                    "macro_precision", "macro_recall", "macro_f1")
+
+
+class CVRetrievalEvaluator:
+    def __init__(self, cv_folds: int = 5, pca_dim: int = 128, top_k: int = 5, seed: int = 42):
+        self.cv_folds = cv_folds
+        self.pca_dim = pca_dim
+        self.top_k = top_k
+        self.seed = seed
+        self.rng = np.random.RandomState(seed)
+        self.random = random.Random(seed)
+
+    # ------------------------------------------------------------------ host
+    def stratified_split(self, patient_ids: List[str], labels: List[str]) -> List[Tuple[List[str], List[str]]]:
+        """StratifiedKFold(cv_folds, shuffle=True, random_state=seed) -> (train_ids, test_ids)
+        per fold (utils/cv_evaluator.py:41-54)."""
+        folds = StratifiedKFold(n_splits=self.cv_folds, shuffle=True, random_state=self.seed)
+        ids = np.asarray(patient_ids, dtype=object)
+        return [(ids[tr].tolist(), ids[te].tolist()) for tr, te in folds.split(patient_ids, labels)]
+
+    def _make_serializable(self, obj):
+        """numpy -> python natives for json (utils/cv_evaluator.py:56-71)."""
+        if isinstance(obj, dict):
+            return {k: self._make_serializable(v) for k, v in obj.items()}
+        if isinstance(obj, list):
+            return [self._make_serializable(v) for v in obj]
+        if isinstance(obj, np.ndarray):
+            return obj.tolist()
+        if isinstance(obj, np.integer):
+            return int(obj)
+        if isinstance(obj, np.floating):
+            return float(obj)
+        if isinstance(obj, np.bool_):
+            return bool(obj)
+        return obj
+
+    def process_embeddings(self, train_embeddings: np.ndarray, test_embeddings: np.ndarray
+                           ) -> Tuple[np.ndarray, np.ndarray]:
+        """StandardScaler -> PCA(min(pca_dim, n-1, D)) fitted on the train fold (host,
+        sklearn: utils/cv_evaluator.py:73-93), then row normalisation on the GPU."""
+        scaler = StandardScaler()
+        tr = scaler.fit_transform(train_embeddings)
+        te = scaler.transform(test_embeddings)
+        n_comp = min(self.pca_dim, tr.shape[0] - 1, tr.shape[1])
+        if n_comp > 0:
+            pca = PCA(n_components=n_comp)
+            tr = pca.fit_transform(tr)
+            te = pca.transform(te)
+        return self._normalize_rows(tr), self._normalize_rows(te)
+
+    # ------------------------------------------------------- GPU primitives
+    def _normalize_rows(self, arr: np.ndarray) -> np.ndarray:
+        """``arr / (||row|| + 1e-8)`` (utils/cv_evaluator.py:95-97) -- K1."""
+        arr = np.asarray(arr)
+        out = get_engine().normalize_fuse(arr, flags=native.NF_ROWNORM).f32.cpu().numpy()
+        return out.astype(arr.dtype, copy=False) if arr.dtype == np.float64 else out
+
+    def concat_fusion(self, img_vec: np.ndarray, txt_vec: np.ndarray) -> np.ndarray:
+        """Image-first concat + row normalisation (utils/cv_evaluator.py:99-105) -- one K1 pass."""
+        return get_engine().normalize_fuse(np.asarray(img_vec), np.asarray(txt_vec),
+                                           flags=native.NF_ROWNORM).f32.cpu().numpy()
+
+    def compute_cosine_similarity(self, query_vec: np.ndarray, db_vecs: np.ndarray) -> np.ndarray:
+        """Plain ``db @ q`` on pre-normalised rows (utils/cv_evaluator.py:107-112)."""
+        eng = get_engine()
+        q = np.asarray(query_vec, dtype=np.float32)
+        db = np.asarray(db_vecs, dtype=np.float32)
+        return eng.scores(q.reshape(1, -1), db)[0].cpu().numpy()
+
+    def retrieve_topk(self, query_vec: np.ndarray, db_vecs: np.ndarray, db_labels: List[str], top_k: int,
+                      db_ids: Optional[List[str]] = None) -> Tuple[List[str], List[float], List[str]]:
+        """Top-k labels / scores / ids of one query (utils/cv_evaluator.py:114-130)."""
+        eng = get_engine()
+        q = eng.normalize_fuse(np.asarray(query_vec).reshape(1, -1), flags=0)
+        db = eng.normalize_fuse(np.asarray(db_vecs), flags=0)
+        k = max(1, min(int(top_k), db.n))
+        keys = eng.topk_search(q, db, k, "fp32")
+        from ..engine import unpack_keys
+        scores, idx = unpack_keys(keys)
+        order = [int(j) for j in idx[0] if j >= 0]
+        top_labels = [db_labels[j] for j in order]
+        top_scores = [float(s) for s in scores[0][:len(order)]]
+        top_ids = [db_ids[j] for j in order] if db_ids else [f"neighbor_{j}" for j in order]
+        return top_labels, top_scores, top_ids
+
+    def compute_vote_accuracy(self, top_labels: List[List[str]], top_scores: List[List[float]],
+                              true_labels: List[str], weighted: bool = False) -> float:
+        """Majority (Counter.most_common) or weighted (score-sum) vote accuracy over given
+        Top-K lists (utils/cv_evaluator.py:132-155) -- K4 on synthetic keys: slot (i, j)
+        becomes database row i*K + j carrying label top_labels[i][j]."""
+        eng = get_engine()
+        n = len(true_labels)
+        if n == 0:
+            raise ZeroDivisionError("division by zero")
+        k = max((len(r) for r in top_labels), default=0)
+        classes = sorted(set(true_labels) | {l for row in top_labels for l in row})
+        lut = {c: i for i, c in enumerate(classes)}
+        truth = np.fromiter((lut[l] for l in true_labels), dtype=np.int32, count=n)
+        slot_labels = np.full((n, max(k, 1)), -1, dtype=np.int32)
+        keys = np.zeros((n, max(k, 1)), dtype=np.uint64)
+        for i, (labs, scs) in enumerate(zip(top_labels, top_scores)):
+            m = min(len(labs), len(scs))
+            slot_labels[i, :m] = [lut[l] for l in labs[:m]]
+            s = np.asarray(scs[:m], dtype=np.float32).view(np.uint32).astype(np.uint64)
+            o = np.where(s & np.uint64(0x80000000), (~s) & np.uint64(0xFFFFFFFF), s ^ np.uint64(0x80000000))
+            keys[i, :m] = (o << np.uint64(32)) | (np.uint64(0xFFFFFFFF) - (np.uint64(i * max(k, 1)) + np.arange(m, dtype=np.uint64)))
+        import torch
+        res = eng.vote_metrics(torch.from_numpy(keys.view(np.int64)).to(eng.device), slot_labels.reshape(-1), truth,
+                               len(classes), k_list=[], wacc_f32=False, per_query=False, want_lists=False)
+        good = int(res["vote_counts"][0, 2 if weighted else 1].item())
+        return good / n
+
+    # ------------------------------------------------------------------ fold
+    def evaluate_fold(
+        self,
+        train_img: Optional[np.ndarray],
+        train_txt: Optional[np.ndarray],
+        test_img: Optional[np.ndarray],
+        test_txt: Optional[np.ndarray],
+        train_labels: List[str],
+        test_labels: List[str],
+        test_ids: List[str],
+        fusion: str = "concat",
+        top_k_list: Optional[List[int]] = None,
+        w_text: float = 0.5,
+        train_ids: Optional[List[str]] = None,
+    ) -> Dict:
+        """One CV fold; result keys as in utils/cv_evaluator.py:157-334."""
+        if top_k_list is None:
+            top_k_list = [1, 3, 5, self.top_k]
+        tr_img = te_img = tr_txt = te_txt = None
+        if train_img is not None and test_img is not None:
+            tr_img, te_img = self.process_embeddings(train_img, test_img)
+        if train_txt is not None and test_txt is not None:
+            tr_txt, te_txt = self.process_embeddings(train_txt, test_txt)
+        return self.evaluate_processed_fold(tr_img, tr_txt, te_img, te_txt, train_labels, test_labels, test_ids,
+                                            fusion, top_k_list, w_text, train_ids)
+
+    def evaluate_processed_fold(self, tr_img, tr_txt, te_img, te_txt, train_labels, test_labels, test_ids,
+                                fusion="concat", top_k_list=None, w_text=0.5, train_ids=None) -> Dict:
+        """The GPU part of ``evaluate_fold``: from processed (unit-row) arrays onward
+        (utils/cv_evaluator.py:186-334)."""
+        if top_k_list is None:
+            top_k_list = [1, 3, 5, self.top_k]
+        eng = get_engine()
+        flags_fused = native.NF_ROWNORM
+        if fusion == "image_only":
+            if tr_img is None or te_img is None:
+                raise ValueError("image_only fusion requires image embeddings")
+            db_segs, q_segs, qw, flags = (tr_img,), (te_img,), (1.0, 1.0), 0
+        elif fusion == "text_only":
+            if tr_txt is None or te_txt is None:
+                raise ValueError("text_only fusion requires text embeddings")
+            db_segs, q_segs, qw, flags = (tr_txt,), (te_txt,), (1.0, 1.0), 0
+        elif fusion == "concat":
+            if tr_img is None or te_img is None or tr_txt is None or te_txt is None:
+                raise ValueError("concat fusion requires both image and text embeddings")
+            db_segs, q_segs, qw, flags = (tr_img, tr_txt), (te_img, te_txt), (1.0, 1.0), flags_fused
+        elif fusion == "late":
+            if tr_img is None or te_img is None or tr_txt is None or te_txt is None:
+                raise ValueError("late fusion requires both image and text embeddings")
+            # w*<Tq,Td> + (1-w)*<Iq,Id> == <[(1-w) Iq ; w Tq], [Id ; Td]>: weights folded into the query rows
+            db_segs, q_segs = (tr_img, tr_txt), (te_img, te_txt)
+            qw, flags = (np.float32(1 - w_text), np.float32(w_text)), 0
+        else:
+            raise ValueError(f"Unknown fusion type: {fusion}")
+
+        classes, (db_codes, q_codes) = encode(train_labels, test_labels)
+        n_cls = len(classes)
+        n_db, n_q = len(train_labels), len(test_labels)
+        k_eff = max(1, min(int(self.top_k), n_db))
+        out = eng.search_and_vote(db_segs, q_segs, db_codes, q_codes, n_cls, k_eff,
+                                  db_weights=(1.0, 1.0), q_weights=qw, db_flags=flags, q_flags=flags,
+                                  k_list=[int(k) for k in top_k_list], wacc_f32=False)
+
+        results: Dict = {}
+        hits = out["hit_counts"][0].cpu().numpy()
+        for j, k in enumerate(top_k_list):
+            results[f"top{k}"] = np.float64(hits[j]) / np.float64(n_q)
+        votes = out["vote_counts"][0].cpu().numpy()
+        results["vote_acc"] = int(votes[1]) / n_q
+        results["weighted_vote_acc"] = int(votes[2]) / n_q
+
+        conf = out["confusion"][0].cpu().numpy()
+        prf = prf_from_confusion(conf[1], classes)           # macro metrics are over the MAJORITY vote
+        results["macro_precision"] = np.mean([v["precision"] for v in prf.values()])
+        results["macro_recall"] = np.mean([v["recall"] for v in prf.values()])
+        results["macro_f1"] = np.mean([v["f1"] for v in prf.values()])
+        results["confusion_matrix_top1"] = confusion_dict(conf[0], classes)
+        results["confusion_matrix_vote"] = confusion_dict(conf[1], classes)
+
+        idx = out["top_idx"].cpu().numpy()
+        valid = (idx >= 0).sum(axis=1)
+        results["all_top_labels"] = gather_lists(train_labels, idx, valid)
+        results["all_top_scores"] = score_lists(out["top_scores"].cpu().numpy(), valid)
+        if train_ids:
+            results["all_top_patient_ids"] = gather_lists(train_ids, idx, valid)
+        else:
+            results["all_top_patient_ids"] = [[f"neighbor_{j}" for j in row[:v]] for row, v in zip(idx, valid)]
+        results["test_patient_ids"] = test_ids
+        return results
+
+    # ------------------------------------------------------------------- CV
+    def run_cv(self, patient_ids: List[str], labels: List[str], embeddings: Dict[str, Dict[str, np.ndarray]],
+               fusion: str = "concat", top_k_list: Optional[List[int]] = None, w_text: float = 0.5) -> Dict:
+        """Fold loop + summary (utils/cv_evaluator.py:336-389)."""
+        splits = self.stratified_split(patient_ids, labels)
+        label_of = dict(zip(patient_ids, labels))
+        fold_results = []
+        for fold, (train_ids, test_ids) in enumerate(splits):
+            logger.info(f"Processing fold {fold + 1}/{self.cv_folds}")
+            logger.info(f"Train: {len(train_ids)}, Test: {len(test_ids)}")
+            train_labels = [label_of[p] for p in train_ids]
+            test_labels = [label_of[p] for p in test_ids]
+            counts: Dict[str, int] = {}
+            for lab in train_labels:
+                counts[lab] = counts.get(lab, 0) + 1
+            logger.info(f"Train label distribution: {counts}")
+
+            def stack(ids, modality):
+                return np.stack([embeddings[p][modality] for p in ids])
+
+            tr_img = te_img = tr_txt = te_txt = None
+            if fusion in {"concat", "image_only", "late"}:
+                tr_img, te_img = stack(train_ids, "image"), stack(test_ids, "image")
+            if fusion in {"concat", "text_only", "late"}:
+                tr_txt, te_txt = stack(train_ids, "text"), stack(test_ids, "text")
+            res = self.evaluate_fold(tr_img, tr_txt, te_img, te_txt, train_labels, test_labels, test_ids,
+                                     fusion, top_k_list, w_text, train_ids)
+            res["fold"] = fold + 1
+            res["train_ids"] = train_ids
+            fold_results.append(res)
+            logger.info(f"Fold {fold + 1} results: Top1={res['top1']:.4f}, "
+                        f"Vote Acc={res['vote_acc']:.4f}, "
+                        f"Weighted Acc={res['weighted_vote_acc']:.4f}")
+        return {"fold_results": fold_results, "summary": self._compute_summary(fold_results)}
+
+    def _compute_summary(self, all_results: List[Dict]) -> Dict:
+        """mean / std / min / max over folds of the 8 fixed metrics (utils/cv_evaluator.py:391-405)."""
+        summary = {}
+        for name in _SUMMARY_METRICS:
+            vals = [r[name] for r in all_results]
+            summary[name] = {"mean": float(np.mean(vals)), "std": float(np.std(vals)),
+                             "min": float(np.min(vals)), "max": float(np.max(vals))}
+        return summary
+
+    # ---------------------------------------------------------------- output
+    def save_results(self, results: Dict, output_dir: Path, experiment_id: str, config: Dict):
+        """config.json, fold_k/metrics.json, summary.csv, confusion_matrices.png
+        (utils/cv_evaluator.py:407-441)."""
+        exp_dir = Path(output_dir) / f"exp_{experiment_id}"
+        exp_dir.mkdir(parents=True, exist_ok=True)
+        with (exp_dir / "config.json").open("w", encoding="utf-8") as fh:
+            json.dump(config, fh, ensure_ascii=False, indent=2)
+        for fold_result in results["fold_results"]:
+            fold_dir = exp_dir / f"fold_{fold_result['fold']}"
+            fold_dir.mkdir(exist_ok=True)
+            with (fold_dir / "metrics.json").open("w", encoding="utf-8") as fh:
+                json.dump(self._make_serializable(fold_result), fh, ensure_ascii=False, indent=2)
+        self._save_summary_csv(results["summary"], exp_dir / "summary.csv")
+        if "vlm_review" in results:
+            with (exp_dir / "vlm_review_summary.json").open("w", encoding="utf-8") as fh:
+                json.dump(results["vlm_review"], fh, ensure_ascii=False, indent=2)
+        self._plot_confusion_matrices(results, exp_dir)
+        logger.info(f"Results saved to {exp_dir}")
+
+    def _save_summary_csv(self, summary: Dict, output_path: Path):
+        with Path(output_path).open("w", newline="", encoding="utf-8") as fh:
+            w = csv.writer(fh)
+            w.writerow(["Metric", "Mean", "Std", "Min", "Max"])
+            for name, st in summary.items():
+                w.writerow([name] + [f"{st[key]:.4f}" for key in ("mean", "std", "min", "max")])
+
+    def _plot_confusion_matrices(self, results: Dict, output_dir: Path):
+        """Fold-averaged confusion heat maps (utils/cv_evaluator.py:459-499).  matplotlib and
+        seaborn are optional here: without them the PNG is skipped with a warning."""
+        try:
+            import matplotlib
+            matplotlib.use("Agg")
+            import matplotlib.pyplot as plt
+            import seaborn as sns
+        except Exception as exc:                                     # pragma: no cover - plotting only
+            logger.warning(f"confusion_matrices.png skipped (plotting libraries unavailable: {exc})")
+            return
+        names = sorted({k for r in results["fold_results"] for k in r["confusion_matrix_top1"].keys()})
+        folds = results["fold_results"]
+
+        def mean_matrix(key):
+            return sum(np.array([[r[key][t][p] for p in names] for t in names], dtype=float) for r in folds) / len(folds)
+
+        fig, axes = plt.subplots(1, 2, figsize=(12, 5))
+        for ax, key, title in ((axes[0], "confusion_matrix_top1", "Confusion Matrix (Top1)"),
+                               (axes[1], "confusion_matrix_vote", "Confusion Matrix (Vote)")):
+            sns.heatmap(mean_matrix(key), annot=True, fmt=".1f", cmap="Blues", xticklabels=names, yticklabels=names, ax=ax)
+            ax.set_title(title)
+            ax.set_xlabel("Predicted")
+            ax.set_ylabel("True")
+        plt.tight_layout()
+        plt.savefig(Path(output_dir) / "confusion_matrices.png", dpi=150, bbox_inches="tight")
+        plt.close()
+        logger.info(f"Confusion matrices saved to {Path(output_dir) / 'confusion_matrices.png'}")

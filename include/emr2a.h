@@ -1,0 +1,199 @@
+/*
+ * emr2a.h -- C-ABI of libemr2a.so: the B200 (sm_100a) retrieval hot path of EMR2A.
+ *
+ * The reference (Ali-Xiyao/emr2a-evidence-grounded-multimodal-retrieval) has no
+ * FFI of its own: the path sits behind plain Python modules.  These entry
+ * points are what the same-named Python modules shipped in this repository
+ * (emr2a_b200/retrieval, emr2a_b200/utils) bind with ctypes; each one cites the
+ * reference code it replaces.  Plain pointers and sizes only -- no torch types.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     all work is stream-ordered, no call synchronises the device or allocates;
+ *   - scratch memory is passed in (`workspace`), its size comes from the matching
+ *     *_workspace_bytes query;
+ *   - return value: EMR2A_OK or an error code; emr2a_last_error() gives the text
+ *     (thread-local);
+ *   - leading dimensions (`ld*`) are in ELEMENTS of the array they describe.
+ *
+ * Packed Top-K key (uint64), larger == better:
+ *      bits 63..32  order-preserving image of the fp32 score
+ *                   (b ^ 0x80000000 for b >= 0, ~b for negative floats)
+ *      bits 31..0   0xFFFFFFFF - global database row index
+ *   so sorting keys descending gives (score descending, index ascending): the
+ *   deterministic tie rule that replaces np.argsort's unspecified order
+ *   (utils/cv_evaluator.py:123).  Key 0 means "empty slot".
+ */
+#ifndef EMR2A_H
+#define EMR2A_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMR2A_ABI_VERSION 3
+
+enum emr2a_status {
+  EMR2A_OK = 0,
+  EMR2A_ERR_INVALID = 1,      /* bad argument (maps to ValueError in the Python layer) */
+  EMR2A_ERR_CUDA = 2,         /* a CUDA runtime / driver call failed */
+  EMR2A_ERR_UNSUPPORTED = 3,  /* shape / mode not supported by the requested precision path */
+  EMR2A_ERR_WORKSPACE = 4     /* workspace too small */
+};
+
+enum emr2a_dtype { EMR2A_F32 = 0, EMR2A_BF16 = 1 };
+
+/* flags of emr2a_normalize_fuse */
+enum emr2a_nf_flags {
+  EMR2A_NF_SEGNORM = 1,     /* first scale each segment to unit length: x / (||x|| + 1e-8) */
+  EMR2A_NF_ROWNORM = 2,     /* after weighting + concatenation divide the row by (||row|| + 1e-8) */
+  EMR2A_NF_ZERO_GUARD = 4   /* ROWNORM without epsilon, zero rows stay zero (utils/common.py:4-8) */
+};
+
+/* arithmetic of emr2a_topk_search */
+enum emr2a_precision {
+  EMR2A_PREC_FP32 = 0,      /* fp32 FMA on CUDA cores: exact-order reference arithmetic, any shape */
+  EMR2A_PREC_BF16X3 = 1,    /* tcgen05 bf16 tensor cores, 2-way split (hi*hi + hi*lo + lo*hi), fp32 accumulate: |err| ~ 1e-6 */
+  EMR2A_PREC_BF16X1 = 2     /* tcgen05 bf16 tensor cores, hi plane only (bf16-input variant), fp32 accumulate */
+};
+
+/* score normalisation modes of emr2a_late_fuse_scores (retrieval/fusion.py:31-42) */
+enum emr2a_score_mode { EMR2A_SCORE_NONE = 0, EMR2A_SCORE_ZSCORE = 1, EMR2A_SCORE_MINMAX = 2 };
+
+int emr2a_abi_version(void);
+const char* emr2a_last_error(void);
+
+/* Number of SMs etc. of the current device; returns EMR2A_ERR_CUDA when no
+ * sm_100 device is current (the product path never falls back to the CPU). */
+int emr2a_device_check(int* sm_count, int* cc_major, int* cc_minor);
+
+/*
+ * K1 -- fused normalise + weight + concatenate (+ bf16 hi/lo split).
+ * Replaces, in one pass over HBM:
+ *   _normalize_rows            utils/cv_evaluator.py:95-97, retrieval/evaluator.py:75-77
+ *   concat_fusion              utils/cv_evaluator.py:99-105   (seg0 = image, seg1 = text)
+ *   early_fusion               retrieval/fusion.py:17-28      (seg0 = text,  seg1 = image)
+ *   the per-call database re-normalisation of compute_cosine_similarity
+ *                              retrieval/similarity.py:5-6
+ *   l2_normalize / concat_embeddings  utils/common.py:4-22    (n = 1, ZERO_GUARD)
+ *
+ *   v_s   = seg_s                       (or seg_s / (||seg_s|| + 1e-8) with SEGNORM)
+ *   row   = [w0 * v_0 ; w1 * v_1]
+ *   out   = row                         (or row / (||row|| + 1e-8) with ROWNORM)
+ *
+ * seg1 may be NULL with d1 = 0.  Outputs are optional (NULL to skip):
+ *   out_f32  [n, ld_f32]   fp32 rows (what the Python API returns)
+ *   out_hi / out_lo [n, ld_bf16]  bf16 planes for the tensor-core search:
+ *            hi = bf16(out), lo = bf16(out - hi); columns [d0+d1, ld_bf16) are zero-filled
+ *   inv_norm_out [n]       1 / (||row|| + 1e-8) of the final division (1.0 without ROWNORM)
+ */
+int emr2a_normalize_fuse(const void* seg0, const void* seg1, int64_t n, int d0, int d1,
+                         int64_t ld0, int64_t ld1, float w0, float w1, int flags, int in_dtype,
+                         float* out_f32, int64_t ld_f32,
+                         uint16_t* out_hi, uint16_t* out_lo, int64_t ld_bf16,
+                         float* inv_norm_out, void* stream);
+
+/*
+ * Full score matrix out[q, j] = <q_q, db_j> in fp32 (CUDA cores), for the API
+ * surfaces that must return every score: compute_cosine_similarity
+ * (retrieval/similarity.py:4-7 after K1, utils/cv_evaluator.py:107-112).
+ */
+int emr2a_scores(const float* q, const float* db, int64_t Q, int64_t N, int D,
+                 int64_t ldq, int64_t lddb, float* out, int64_t ld_out, void* stream);
+
+/* 1 - ||db_j - q|| / max_j ||db_j - q||   (retrieval/similarity.py:10-15).
+ * workspace: emr2a_euclid_workspace_bytes(N). */
+size_t emr2a_euclid_workspace_bytes(int64_t N);
+int emr2a_euclid_scores(const float* q, const float* db, int64_t N, int D, int64_t lddb,
+                        float* out, void* workspace, size_t ws_bytes, void* stream);
+
+/*
+ * Row-wise late fusion of two score matrices:
+ *   out = w * norm(text) + (1 - w) * norm(image),  norm in {none, zscore, minmax}
+ * (retrieval/fusion.py:4-14, 31-42).  `one_minus_w` is passed separately because
+ * the reference forms it in float64 before the fp32 multiply.
+ */
+int emr2a_late_fuse_scores(const float* text_scores, const float* image_scores, int64_t Q, int64_t N,
+                           int64_t ld, float w_text, float one_minus_w, int mode,
+                           float* out, int64_t ld_out, void* stream);
+
+/*
+ * K2 -- similarity + Top-K without materialising the score matrix.
+ * Replaces np.dot + np.argsort(...)[-k:][::-1] per query
+ * (utils/cv_evaluator.py:112,123,233-237; retrieval/evaluator.py:188-189,219-220).
+ *
+ * Operands are the rows K1 produced (weights and inverse norms already folded
+ * in, so score = plain dot product):
+ *   EMR2A_PREC_FP32   : q_f32 [Q, ldq], db_f32 [N, lddb]
+ *   EMR2A_PREC_BF16X3 : q_hi,q_lo [Q, ldq] and db_hi,db_lo [N, lddb] (bf16 bits; ld % 64 == 0, zero padded)
+ *   EMR2A_PREC_BF16X1 : q_hi, db_hi only
+ * q_fold / db_fold (uint8, nullable together): a pair with equal fold ids is
+ * excluded -- the CV rule that a case is never retrieved from its own fold
+ * (utils/cv_evaluator.py:349-376).  `fold_sorted` != 0 promises both fold
+ * vectors are non-decreasing so whole tiles of a single fold can be skipped.
+ * idx_base is added to the local row number (row-sharded databases).
+ * out_keys [Q, K]: packed keys, best first; slots beyond the number of
+ * admissible rows are 0.
+ */
+size_t emr2a_topk_search_workspace_bytes(int64_t Q, int64_t N, int D, int K, int precision);
+int emr2a_topk_search(const float* q_f32, const uint16_t* q_hi, const uint16_t* q_lo,
+                      const float* db_f32, const uint16_t* db_hi, const uint16_t* db_lo,
+                      int64_t Q, int64_t N, int D, int64_t ldq, int64_t lddb,
+                      const uint8_t* q_fold, const uint8_t* db_fold, int fold_sorted,
+                      int64_t idx_base, int K, int precision,
+                      uint64_t* out_keys, void* workspace, size_t ws_bytes, void* stream);
+
+/*
+ * K3 -- merge `parts` sorted partial Top-K lists per query into one.
+ *   keys_in[(p * part_stride) + q * q_stride + j], j < K_in   ->  keys_out[q * K_out + j]
+ * Used for the per-CTA partial lists of K2 and for the lists gathered from the
+ * other GPUs (row-sharded database; NCCL all-gather).
+ */
+int emr2a_topk_merge(const uint64_t* keys_in, int parts, int64_t Q, int K_in,
+                     int64_t part_stride, int64_t q_stride, int K_out,
+                     uint64_t* keys_out, void* stream);
+
+/*
+ * K4 -- unpack Top-K, gather labels, vote and count.
+ * Replaces the per-query python of evaluate_fold (utils/cv_evaluator.py:232-310):
+ * top-1 prediction, Counter majority vote (ties -> label seen first), weighted
+ * vote (score sums in rank order; wacc_f32 = 0: float64 sums as in
+ * utils/cv_evaluator.py:255-260, wacc_f32 = 1: float32 sums as in
+ * retrieval/evaluator.py:224-230), hit@k for each k in k_list_host (a HOST array, nk <= 16)
+ * (true label in top_labels[:k]), and the two confusion matrices
+ * (utils/metrics.py:56-75).
+ *
+ *   db_labels [>= max index + 1 - label_base]  int32 class code per database row
+ *   q_labels  [Q] int32 true class codes;  q_group [Q] uint8 (nullable): counters are
+ *             kept per group (the fold) -- n_groups >= 1
+ * Per-query outputs (each nullable): top_idx int64 [Q,K] (-1 = empty), top_scores f32 [Q,K],
+ *   top_labels int32 [Q,K] (-1 = empty), pred_top1 / pred_vote / pred_weighted int32 [Q].
+ * Counters (must be zeroed by the caller, accumulated with atomics):
+ *   hit_counts  uint64 [n_groups, nk]
+ *   vote_counts uint64 [n_groups, 3]   (#top1 correct, #majority correct, #weighted correct)
+ *   confusion   uint64 [n_groups, 2, C, C]   ([.,0]=top-1, [.,1]=majority; index [true][pred])
+ *   group_sizes uint64 [n_groups]
+ */
+int emr2a_vote_metrics(const uint64_t* keys, int64_t Q, int K,
+                       const int32_t* db_labels, int64_t label_base,
+                       const int32_t* q_labels, const uint8_t* q_group, int n_groups, int C,
+                       const int32_t* k_list_host, int nk, int wacc_f32,
+                       int64_t* top_idx, float* top_scores, int32_t* top_labels,
+                       int32_t* pred_top1, int32_t* pred_vote, int32_t* pred_weighted,
+                       unsigned long long* hit_counts, unsigned long long* vote_counts,
+                       unsigned long long* confusion, unsigned long long* group_sizes,
+                       void* stream);
+
+/* Top-K of a given score matrix (the *_from_scores helpers and get_all_top_labels,
+ * retrieval/evaluator.py:195-208, 235-275): keys out [Q, K]. */
+int emr2a_topk_from_scores(const float* scores, int64_t Q, int64_t N, int64_t ld, int K,
+                           uint64_t* out_keys, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMR2A_H */

@@ -219,6 +219,13 @@ def main():
     ho["fs_top3"] = rev._compute_top_k_accuracy_from_scores(sc, trl, tel, 3)
     ho["fs_weighted"] = rev._compute_weighted_accuracy_from_scores(sc, trl, tel)
     ho["fs_top5_labels"] = np.array([[code_of(x) for x in row] for row in rev.get_all_top_labels(sc, trl, tel, 5)])
+    # python-random stratified hold-out split (host logic; RNG stream must match)
+    split_labels = names(np.random.default_rng(31).integers(0, 4, size=97), 4) + ["solo"]
+    rs = retrieval.RetrievalEvaluator(test_ratio=0.2, seed=42)
+    tr_i, te_i = rs.stratified_split(split_labels)
+    tr_j, te_j = rs.stratified_split(split_labels)        # second call continues the RNG stream
+    ho["ss_labels"] = np.array([4 if x == "solo" else code_of(x) for x in split_labels])
+    ho["ss_train1"], ho["ss_test1"], ho["ss_train2"], ho["ss_test2"] = map(np.array, (tr_i, te_i, tr_j, te_j))
     np.savez_compressed(os.path.join(HERE, "holdout_small.npz"), **ho)
 
     import sklearn

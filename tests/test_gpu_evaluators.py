@@ -1,0 +1,208 @@
+"""Evaluator-level parity: the drop-in classes against outputs of the reference classes
+(golden fixtures made by tests/golden/make_golden.py) and against the oracle at C1 size."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL = 1e-5
+
+
+def _names(codes):
+    return [f"class_{int(c)}" for c in codes]
+
+
+def _cm(d, n):
+    cls = [f"class_{c}" for c in range(n)]
+    return np.array([[d[a][b] for b in cls] for a in cls])
+
+
+def test_cv_fold_from_processed_arrays_matches_reference(golden):
+    from emr2a_b200.utils.cv_evaluator import CVRetrievalEvaluator
+    g = golden("cv_small.npz")
+    n, d_img, d_txt, n_cls, pca_dim, top_k = [int(x) for x in g["meta"]]
+    ev = CVRetrievalEvaluator(cv_folds=5, pca_dim=pca_dim, top_k=top_k, seed=42)
+    labels = _names(g["labels"])
+    for f in range(5):
+        tr, te = g[f"f{f}_train_idx"], g[f"f{f}_test_idx"]
+        tr_ids, te_ids = [f"p{j:07d}" for j in tr], [f"p{j:07d}" for j in te]
+        for fusion, w in (("concat", 0.5), ("late", 0.3), ("image_only", 0.5), ("text_only", 0.5)):
+            r = ev.evaluate_processed_fold(g[f"f{f}_img_tr"], g[f"f{f}_txt_tr"], g[f"f{f}_img_te"], g[f"f{f}_txt_te"],
+                                           [labels[j] for j in tr], [labels[j] for j in te], te_ids,
+                                           fusion=fusion, top_k_list=[1, 3, 5, 5], w_text=w, train_ids=tr_ids)
+            key = f"f{f}_{fusion}"
+            pos = {p: j for j, p in enumerate(tr_ids)}
+            got_idx = np.array([[pos[p] for p in row] for row in r["all_top_patient_ids"]])
+            want_sc = g[key + "_top_scores"]
+            got_sc = np.array(r["all_top_scores"])
+            assert np.max(np.abs(got_sc - want_sc)) < TOL, key
+            # rows whose reference scores are separated by more than the tolerance must agree index for index
+            safe = np.abs(np.diff(want_sc, axis=1)).min(axis=1) > 2 * TOL
+            assert safe.mean() > 0.9
+            assert np.array_equal(got_idx[safe], g[key + "_top_idx"][safe]), key
+            got_lab = np.array([[int(x.split("_")[1]) for x in row] for row in r["all_top_labels"]])
+            assert np.array_equal(got_lab[safe], g[key + "_top_labels"][safe])
+            if safe.all():
+                got = np.array([r["top1"], r["top3"], r["top5"], r["vote_acc"], r["weighted_vote_acc"],
+                                r["macro_precision"], r["macro_recall"], r["macro_f1"]], dtype=np.float64)
+                np.testing.assert_allclose(got, g[key + "_metrics"], atol=1e-12)
+                assert np.array_equal(_cm(r["confusion_matrix_top1"], n_cls), g[key + "_cm_top1"])
+                assert np.array_equal(_cm(r["confusion_matrix_vote"], n_cls), g[key + "_cm_vote"])
+            assert r["test_patient_ids"] == te_ids
+    with open(os.path.join(REPO, "tests", "golden", "cv_result_keys.json")) as fh:
+        keys = json.load(fh)
+    assert sorted(list(r.keys()) + ["fold", "train_ids"]) == keys["fold_keys"]
+
+
+@pytest.mark.parametrize("fusion,w", [("concat", 0.5), ("late", 0.25)])
+def test_run_cv_end_to_end_matches_reference(golden, fusion, w):
+    """Whole run_cv (sklearn split + scaler + PCA on the host, the rest on the GPU) with the same
+    numpy seed the golden run used."""
+    from emr2a_b200 import synth
+    from emr2a_b200.utils.cv_evaluator import CVRetrievalEvaluator
+    g = golden("cv_small.npz")
+    n, d_img, d_txt, n_cls, pca_dim, top_k = [int(x) for x in g["meta"]]
+    ids = synth.patient_ids(n)
+    labels = _names(g["labels"])
+    emb = {pid: {"image": g["image"][j], "text": g["text"][j]} for j, pid in enumerate(ids)}
+    np.random.seed(77)
+    ev = CVRetrievalEvaluator(cv_folds=5, pca_dim=pca_dim, top_k=top_k, seed=42)
+    res = ev.run_cv(ids, labels, emb, fusion=fusion, top_k_list=[1, 3, 5, 5], w_text=w)
+    f0 = res["fold_results"][0]
+    assert np.max(np.abs(np.array(f0["all_top_scores"]) - g[f"runcv_{fusion}_f0_scores"])) < TOL
+    pid_idx = {p: j for j, p in enumerate(ids)}
+    got_ids = np.array([[pid_idx[p] for p in row] for row in f0["all_top_patient_ids"]])
+    safe = np.abs(np.diff(g[f"runcv_{fusion}_f0_scores"], axis=1)).min(axis=1) > 2 * TOL
+    assert np.array_equal(got_ids[safe], g[f"runcv_{fusion}_f0_ids"][safe])
+    np.testing.assert_allclose([r["top1"] for r in res["fold_results"]], g[f"runcv_{fusion}_fold_top1"], atol=1.5 / 60)
+    got = np.array([[res["summary"][m][s] for s in ("mean", "std", "min", "max")]
+                    for m in ("top1", "top3", "top5", "vote_acc", "weighted_vote_acc",
+                              "macro_precision", "macro_recall", "macro_f1")])
+    np.testing.assert_allclose(got, g[f"runcv_{fusion}_summary"], atol=0.02)
+    assert f0["fold"] == 1 and len(f0["train_ids"]) == 240
+
+
+def test_cv_save_results_formats(tmp_path, golden):
+    from emr2a_b200 import synth
+    from emr2a_b200.utils.cv_evaluator import CVRetrievalEvaluator
+    g = golden("cv_small.npz")
+    n = int(g["meta"][0])
+    ids = synth.patient_ids(n)
+    emb = {pid: {"image": g["image"][j], "text": g["text"][j]} for j, pid in enumerate(ids)}
+    ev = CVRetrievalEvaluator(cv_folds=5, pca_dim=16, top_k=3, seed=42)
+    res = ev.run_cv(ids, _names(g["labels"]), emb, fusion="image_only")
+    assert res["fold_results"][0]["top5"] == res["fold_results"][0]["top3"]       # hit@k saturates at top_k (App. A.1)
+    ev.save_results(res, tmp_path, "t1", {"a": 1})
+    exp = tmp_path / "exp_t1"
+    assert json.load(open(exp / "config.json")) == {"a": 1}
+    m = json.load(open(exp / "fold_2" / "metrics.json"))
+    for key in ("all_top_labels", "all_top_scores", "all_top_patient_ids", "test_patient_ids", "train_ids", "fold",
+                "confusion_matrix_top1", "confusion_matrix_vote", "top1", "vote_acc"):
+        assert key in m
+    assert len(m["all_top_labels"][0]) == 3 and isinstance(m["all_top_scores"][0][0], float)
+    rows = open(exp / "summary.csv").read().strip().splitlines()
+    assert rows[0] == "Metric,Mean,Std,Min,Max" and len(rows) == 9
+
+
+def test_cv_errors_match_reference():
+    from emr2a_b200.utils.cv_evaluator import CVRetrievalEvaluator
+    ev = CVRetrievalEvaluator()
+    x = np.random.default_rng(0).standard_normal((20, 8)).astype(np.float32)
+    lab = ["a", "b"] * 10
+    with pytest.raises(ValueError, match="concat fusion requires both"):
+        ev.evaluate_fold(x, None, x, None, lab, lab, lab, fusion="concat")
+    with pytest.raises(ValueError, match="Unknown fusion type"):
+        ev.evaluate_fold(x, x, x, x, lab, lab, lab, fusion="bogus")
+    with pytest.raises(ValueError, match="text_only fusion requires text"):
+        ev.evaluate_fold(x, None, x, None, lab, lab, lab, fusion="text_only")
+
+
+def test_holdout_evaluator_matches_reference(golden):
+    from emr2a_b200.retrieval import RetrievalEvaluator
+    g = golden("holdout_small.npz")
+    trl, tel = _names(g["tr_labels"]), _names(g["te_labels"])
+    ev = RetrievalEvaluator()
+    runs = {
+        "early": dict(fusion_type="early", text_weight=0.4),
+        "late_none": dict(fusion_type="late", text_weight=0.4, score_mode="none"),
+        "late_zscore": dict(fusion_type="late", text_weight=0.3, score_mode="zscore"),
+        "late_minmax": dict(fusion_type="late", text_weight=0.6, score_mode="minmax"),
+    }
+    n_q = len(tel)
+    for name, kw in runs.items():
+        r = ev.evaluate_retrieval(g["tr_txt"], g["te_txt"], g["tr_img"], g["te_img"], trl, tel, top_k_list=[1, 3, 5, 7], **kw)
+        scalars = {k: v for k, v in r.items() if not isinstance(v, list)}
+        assert sorted(scalars) == [str(k) for k in g[name + "_keys"]], name
+        for k, v in zip(g[name + "_keys"], g[name + "_vals"]):
+            # a rank flip between near-equal scores may move at most one query
+            assert abs(scalars[str(k)] - v) <= 1.0 / n_q + 1e-12, (name, k, scalars[str(k)], v)
+        if name + "_top5" in g:
+            got = np.array([[int(x.split("_")[1]) for x in row] for row in r["all_top_labels_top5"]])
+            assert (got == g[name + "_top5"]).mean() > 0.98
+    r = ev.evaluate_retrieval(None, None, g["tr_img"], g["te_img"], trl, tel, fusion_type="none", top_k_list=[1, 3, 5, 5])
+    assert sorted(r) == [str(k) for k in g["imgonly_keys"]]
+    for k, v in zip(g["imgonly_keys"], g["imgonly_vals"]):
+        assert abs(r[str(k)] - v) <= 1.0 / n_q + 1e-12
+    with pytest.raises(ValueError, match="Early fusion requires both"):
+        ev.evaluate_retrieval(None, None, g["tr_img"], g["te_img"], trl, tel, fusion_type="early")
+    sc = g["fs_scores"]
+    assert ev._compute_top_k_accuracy_from_scores(sc, trl, tel, 3) == float(g["fs_top3"])
+    assert ev._compute_weighted_accuracy_from_scores(sc, trl, tel) == float(g["fs_weighted"])
+    got = np.array([[int(x.split("_")[1]) for x in row] for row in ev.get_all_top_labels(sc, trl, tel, 5)])
+    assert np.array_equal(got, g["fs_top5_labels"])
+
+
+def test_c1_full_size_against_oracle(oracle):
+    """BASELINE config C1 (2000 cases, 512+512, 3 classes, K=5) from processed arrays: every
+    fold against the oracle's per-query loop."""
+    from sklearn.model_selection import StratifiedKFold
+    from emr2a_b200 import synth
+    from emr2a_b200.utils.cv_evaluator import CVRetrievalEvaluator
+    data = synth.two_modal(2000, 512, 512, 3, seed=7)
+    img, txt, codes = oracle.unit_rows(data["image"]), oracle.unit_rows(data["text"]), data["labels"]
+    labels = _names(codes)
+    ids = synth.patient_ids(2000)
+    ev = CVRetrievalEvaluator(top_k=5)
+    skf = StratifiedKFold(5, shuffle=True, random_state=42)
+    for f, (tr, te) in enumerate(skf.split(ids, labels)):
+        if f not in (0, 3):
+            continue
+        for fusion, w in (("concat", 0.5), ("late", 0.25)):
+            r = ev.evaluate_processed_fold(img[tr], txt[tr], img[te], txt[te], [labels[j] for j in tr],
+                                           [labels[j] for j in te], [ids[j] for j in te], fusion=fusion,
+                                           top_k_list=[1, 3, 5, 5], w_text=w, train_ids=[ids[j] for j in tr])
+            o = oracle.cv_fold_eval(img[tr], txt[tr], img[te], txt[te], codes[tr], codes[te], 3, fusion=fusion,
+                                    top_k=5, top_k_list=(1, 3, 5, 5), w_text=w)
+            got_sc = np.array(r["all_top_scores"])
+            assert np.max(np.abs(got_sc - o["top_scores"])) < TOL
+            safe = np.abs(np.diff(o["top_scores"], axis=1)).min(axis=1) > 2 * TOL
+            pos = {ids[j]: i for i, j in enumerate(tr)}
+            got_idx = np.array([[pos[p] for p in row] for row in r["all_top_patient_ids"]])
+            assert np.array_equal(got_idx[safe], o["top_idx"][safe])
+            if safe.all():
+                for k in ("top1", "top3", "top5", "vote_acc", "weighted_vote_acc", "macro_precision", "macro_recall", "macro_f1"):
+                    assert abs(float(r[k]) - o[k]) < 1e-12, (fusion, k)
+                assert np.array_equal(_cm(r["confusion_matrix_vote"], 3), o["confusion_vote"])
+
+
+def test_dropin_packages_resolve_to_b200_implementation():
+    """With <repo>/emr2a_b200/dropin first on PYTHONPATH, the reference's import statements
+    (`from retrieval import RetrievalEvaluator`, `from utils.cv_evaluator import CVRetrievalEvaluator`)
+    pick up this implementation."""
+    code = ("from retrieval import RetrievalEvaluator, compute_cosine_similarity; "
+            "from utils.cv_evaluator import CVRetrievalEvaluator; from utils import l2_normalize; "
+            "import numpy as np; "
+            "print(RetrievalEvaluator.__module__, CVRetrievalEvaluator.__module__); "
+            "print(float(compute_cosine_similarity(np.ones(4, np.float32), np.ones((2, 4), np.float32))[0]))")
+    env = dict(os.environ, PYTHONPATH=os.path.join(REPO, "emr2a_b200", "dropin"))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd="/tmp")
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    assert lines[-2] == "emr2a_b200.retrieval.evaluator emr2a_b200.utils.cv_evaluator"
+    assert abs(float(lines[-1]) - 1.0) < 1e-6

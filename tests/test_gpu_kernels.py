@@ -1,0 +1,296 @@
+"""Kernel-level parity: every libemr2a.so entry point against the CPU oracle / the golden
+vectors produced by the reference.  Needs a B200 (``-m gpu``); all calls go through the
+C-ABI (ctypes) via emr2a_b200.engine."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SCORE_TOL = 1e-5          # north_star: fp32-accumulated cosine scores within 1e-5
+F32_TOL = 2e-6            # fp32 arms repeat the reference arithmetic; only summation order differs
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from emr2a_b200.engine import get_engine
+    return get_engine()
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _bf16_to_f32(t):
+    return (_np(t).view(np.uint16).astype(np.uint32) << 16).view(np.float32)
+
+
+# ------------------------------------------------------------------ K1
+@pytest.mark.parametrize("n,d0,d1", [(33, 24, 40), (1000, 512, 512), (7, 25, 0), (64, 1024, 0), (19, 4096, 1024),
+                                     (5, 3, 5), (300, 96, 160)])
+def test_normalize_fuse_modes(eng, oracle, n, d0, d1):
+    from emr2a_b200 import native
+    rng = np.random.default_rng(n + d0)
+    a = (rng.standard_normal((n, d0)) * rng.uniform(0.1, 5, (n, 1))).astype(np.float32)
+    b = (rng.standard_normal((n, d1)) * 2).astype(np.float32) if d1 else None
+    if n > 4:
+        a[3] = 0
+        if b is not None:
+            b[3] = 0                                                   # all-zero row: epsilon path
+    if b is None:
+        got = eng.normalize_fuse(a, flags=native.NF_ROWNORM, want_planes=True, want_inv_norm=True)
+        ref = oracle.unit_rows(a)
+    else:
+        got = eng.normalize_fuse(a, b, flags=native.NF_ROWNORM, want_planes=True, want_inv_norm=True)
+        ref = oracle.unit_rows(np.concatenate([a, b], axis=1))
+    np.testing.assert_allclose(_np(got.f32), ref, atol=F32_TOL, rtol=0)
+    # bf16 hi+lo planes reconstruct the fp32 rows to ~2^-17 relative, pad columns are zero
+    d = d0 + d1
+    hi, lo = _bf16_to_f32(got.hi), _bf16_to_f32(got.lo)
+    assert hi.shape[1] % 64 == 0 and np.all(hi[:, d:] == 0) and np.all(lo[:, d:] == 0)
+    np.testing.assert_allclose(hi[:, :d] + lo[:, :d], _np(got.f32), atol=1e-6 * max(1e-3, float(np.abs(ref).max())) * 16, rtol=2e-5)
+    if b is not None:
+        # weighted early fusion (text first) and the CV chain normalise-each -> concat -> normalise
+        w = eng.normalize_fuse(a, b, np.float32(0.4), np.float32(0.6), native.NF_ROWNORM)
+        np.testing.assert_allclose(_np(w.f32), oracle.fuse_early(a, b, 0.4, 0.6), atol=F32_TOL, rtol=0)
+        c = eng.normalize_fuse(a, b, flags=native.NF_SEGNORM | native.NF_ROWNORM)
+        np.testing.assert_allclose(_np(c.f32), oracle.fuse_concat_cv(oracle.unit_rows(a), oracle.unit_rows(b)),
+                                   atol=F32_TOL, rtol=0)
+
+
+def test_normalize_fuse_bf16_input_and_strides(eng, oracle):
+    import torch
+    from emr2a_b200 import native
+    rng = np.random.default_rng(5)
+    x = torch.from_numpy(rng.standard_normal((50, 128)).astype(np.float32)).cuda().to(torch.bfloat16)
+    got = eng.normalize_fuse(x, flags=native.NF_ROWNORM)
+    ref = oracle.unit_rows(x.float().cpu().numpy())
+    np.testing.assert_allclose(_np(got.f32), ref, atol=F32_TOL, rtol=0)
+    # zero guard (utils/common.py): zero vector stays zero, no epsilon
+    z = eng.normalize_fuse(np.zeros((1, 7), np.float32), flags=native.NF_ZERO_GUARD)
+    assert np.all(_np(z.f32) == 0)
+    v = rng.standard_normal((1, 7)).astype(np.float32)
+    np.testing.assert_allclose(_np(eng.normalize_fuse(v, flags=native.NF_ZERO_GUARD).f32)[0], oracle.unit_vector(v[0]),
+                               atol=F32_TOL)
+
+
+def test_golden_primitives_through_python_api(golden):
+    """The reference's primitive functions, same names/signatures, against reference outputs."""
+    from emr2a_b200.retrieval import compute_cosine_similarity, compute_euclidean_similarity, late_fusion, early_fusion
+    from emr2a_b200.retrieval.fusion import normalize_scores
+    from emr2a_b200.utils import l2_normalize, concat_embeddings
+    from emr2a_b200.utils.cv_evaluator import CVRetrievalEvaluator
+    g = golden("primitives.npz")
+    np.testing.assert_allclose(compute_cosine_similarity(g["cos_q"], g["cos_db"]), g["cos_out"], atol=F32_TOL)
+    np.testing.assert_allclose(compute_euclidean_similarity(g["cos_q"], g["cos_db"]), g["euc_out"], atol=F32_TOL)
+    np.testing.assert_allclose(early_fusion(g["ef_text"], g["ef_image"]), g["ef_out_11"], atol=F32_TOL)
+    np.testing.assert_allclose(early_fusion(g["ef_text"], g["ef_image"], 0.4, 0.6), g["ef_out_w"], atol=F32_TOL)
+    for mode in ("none", "zscore", "minmax"):
+        np.testing.assert_allclose(late_fusion(g["lf_ts"], g["lf_is"], 0.4, mode), g[f"lf_out_{mode}"], atol=1e-5, rtol=1e-5)
+        np.testing.assert_allclose(normalize_scores(g["lf_ts"], mode), g[f"ns_out_{mode}"], atol=1e-5, rtol=1e-5)
+    np.testing.assert_allclose(late_fusion(g["lf_ts"], g["lf_is"], 0.7), g["lf_out_w07"], atol=F32_TOL)
+    ev = CVRetrievalEvaluator()
+    np.testing.assert_allclose(ev._normalize_rows(g["ef_image"]), g["nr_out"], atol=F32_TOL)
+    np.testing.assert_allclose(ev.concat_fusion(g["cf_img"], g["cf_txt"]), g["cf_out"], atol=F32_TOL)
+    np.testing.assert_allclose(ev.compute_cosine_similarity(g["cf_out"][2], g["cf_out"]), g["dot_out"], atol=F32_TOL)
+    np.testing.assert_allclose(l2_normalize(g["cos_q"]), g["l2_out"], atol=F32_TOL)
+    assert np.array_equal(l2_normalize(np.zeros(7, np.float32)), g["l2_zero_out"])
+    np.testing.assert_allclose(concat_embeddings(g["ef_text"][0], g["ef_image"][0], 0.3, 0.9), g["ce_out"], atol=F32_TOL)
+    labels = [f"class_{c}" for c in g["rt_labels"]]
+    tl, ts, tid = ev.retrieve_topk(g["cf_out"][2], g["cf_out"], labels, 5)
+    assert [int(x.split("_")[1]) for x in tid] == list(g["rt_top_idx"])
+    assert [int(x.split("_")[1]) for x in tl] == list(g["rt_top_labels"])
+    np.testing.assert_allclose(ts, g["rt_top_scores"], atol=F32_TOL)
+    # votes on given lists
+    vl = [[f"class_{c}" for c in r] for r in g["v_labels"]]
+    vs = [[float(x) for x in r] for r in g["v_scores"]]
+    true = [f"class_{c}" for c in g["v_true"]]
+    assert ev.compute_vote_accuracy(vl, vs, true, weighted=False) == float(g["v_acc_major"])
+    assert ev.compute_vote_accuracy(vl, vs, true, weighted=True) == float(g["v_acc_weight"])
+
+
+# ------------------------------------------------------------------ K2 (fp32 arm)
+def _check_topk(oracle, keys, qs, db, k, q_fold=None, db_fold=None, tol=SCORE_TOL, idx_base=0):
+    from emr2a_b200.engine import unpack_keys
+    sc, idx = unpack_keys(keys)
+    o_idx, o_sc = oracle.search_topk_batched(qs, db, k, q_fold=q_fold, db_fold=db_fold)
+    valid = o_idx >= 0
+    assert np.array_equal(idx >= 0, valid)
+    assert np.max(np.abs(np.where(valid, sc - o_sc, 0))) <= tol
+    # index sets bit-exact wherever adjacent gaps (including the gap to the first loser) exceed 2*tol
+    full = qs.astype(np.float64) @ db.astype(np.float64).T
+    if q_fold is not None:
+        full = np.where(q_fold[:, None] == db_fold[None, :], -np.inf, full)
+    srt = -np.sort(-full, axis=1)[:, :k + 1]
+    gaps = np.abs(np.diff(srt, axis=1))
+    gaps = np.where(np.isfinite(gaps), gaps, np.inf)
+    safe = gaps.min(axis=1) > 2 * tol if gaps.shape[1] else np.ones(len(qs), bool)
+    assert safe.mean() > 0.5
+    assert np.array_equal(np.where(valid, idx - idx_base, -1)[safe], o_idx[safe])
+    return safe
+
+
+@pytest.mark.parametrize("Q,N,D,K", [(1, 1, 8, 1), (70, 300, 33, 5), (130, 1000, 256, 10), (64, 129, 64, 40),
+                                     (5, 3, 16, 5), (257, 4097, 100, 3)])
+def test_topk_search_fp32(eng, oracle, Q, N, D, K):
+    rng = np.random.default_rng(Q * 7 + N)
+    db = oracle.unit_rows(rng.standard_normal((N, D)).astype(np.float32))
+    qs = oracle.unit_rows(rng.standard_normal((Q, D)).astype(np.float32))
+    if N > 20:
+        db[7] = db[11]                                   # exact duplicate rows: tie -> lower index first
+        qs[0] = db[7]
+    keys = eng.topk_search(eng.prepare(qs, flags=0), eng.prepare(db, flags=0), K, "fp32")
+    _check_topk(oracle, keys, qs, db, K)
+    if N > 20:
+        from emr2a_b200.engine import unpack_keys
+        _, idx = unpack_keys(keys)
+        assert list(idx[0][:2]) == [7, 11]
+
+
+def test_topk_search_fp32_fold_mask_and_base(eng, oracle):
+    rng = np.random.default_rng(1)
+    N, Q, D, K = 2000, 200, 64, 5
+    db = oracle.unit_rows(rng.standard_normal((N, D)).astype(np.float32))
+    fold = rng.integers(0, 5, N).astype(np.uint8)
+    qs, qf = db[:Q].copy(), fold[:Q].copy()            # queries ARE database rows, as in the CV loop
+    import torch
+    keys = eng.topk_search(eng.prepare(qs, flags=0), eng.prepare(db, flags=0), K, "fp32",
+                           q_fold=torch.from_numpy(qf), db_fold=torch.from_numpy(fold), idx_base=1000)
+    _check_topk(oracle, keys, qs, db, K, q_fold=qf, db_fold=fold, idx_base=1000)
+
+
+# ------------------------------------------------------------------ K2 (tcgen05 arms)
+@pytest.mark.parametrize("prec,tol", [("bf16x3", SCORE_TOL)])
+@pytest.mark.parametrize("Q,N,D,K", [(128, 256, 64, 5), (100, 1000, 128, 5), (300, 5000, 200, 10),
+                                     (257, 3333, 96, 20), (1000, 40000, 1024, 10), (2, 70, 8, 3)])
+def test_topk_search_tensor_core(eng, oracle, prec, tol, Q, N, D, K):
+    rng = np.random.default_rng(Q + N + D)
+    db = oracle.unit_rows(rng.standard_normal((N, D)).astype(np.float32))
+    qs = oracle.unit_rows(rng.standard_normal((Q, D)).astype(np.float32))
+    db[5] = db[9]
+    qs[1] = db[5]
+    keys = eng.topk_search(eng.prepare(qs, flags=0, precision=prec), eng.prepare(db, flags=0, precision=prec), K, prec)
+    _check_topk(oracle, keys, qs, db, K, tol=tol)
+    from emr2a_b200.engine import unpack_keys
+    _, idx = unpack_keys(keys)
+    assert list(idx[1][:2]) == [5, 9]                   # identical rows give identical scores: index order decides
+
+
+def test_topk_search_bf16x1_matches_bf16_math(eng, oracle):
+    """bf16-input variant: products of bf16 values are exact, accumulation is fp32 -- compare with the
+    same bf16-rounded operands evaluated in float64 (tolerance 1e-5), NOT with the unrounded fp32 inputs."""
+    rng = np.random.default_rng(17)
+    Q, N, D, K = 200, 6000, 320, 5
+    db = oracle.unit_rows(rng.standard_normal((N, D)).astype(np.float32))
+    qs = oracle.unit_rows(rng.standard_normal((Q, D)).astype(np.float32))
+    qo, do = eng.prepare(qs, flags=0, precision="bf16x1"), eng.prepare(db, flags=0, precision="bf16x1")
+    keys = eng.topk_search(qo, do, K, "bf16x1")
+    qh, dh = _bf16_to_f32(qo.hi)[:, :D], _bf16_to_f32(do.hi)[:, :D]
+    _check_topk(oracle, keys, qh, dh, K, tol=SCORE_TOL)
+
+
+def test_topk_search_tensor_core_fold_mask(eng, oracle):
+    import torch
+    rng = np.random.default_rng(23)
+    N, Q, D, K = 6000, 300, 192, 5
+    db = oracle.unit_rows(rng.standard_normal((N, D)).astype(np.float32))
+    fold = np.sort(rng.integers(0, 5, N)).astype(np.uint8)
+    pick = rng.choice(N, Q, replace=False)
+    qs, qf = db[pick].copy(), fold[pick].copy()
+    keys = eng.topk_search(eng.prepare(qs, flags=0, precision="bf16x3"), eng.prepare(db, flags=0, precision="bf16x3"),
+                           K, "bf16x3", q_fold=torch.from_numpy(qf), db_fold=torch.from_numpy(fold))
+    _check_topk(oracle, keys, qs, db, K, q_fold=qf, db_fold=fold)
+
+
+def test_tensor_core_equals_fp32_arm_large(eng):
+    """Property at a size the CPU oracle would take minutes for: both arms agree on the index
+    sets (where the fp32 arm's gaps are clear) and on scores to 1e-5."""
+    import torch
+    from emr2a_b200 import synth, native
+    from emr2a_b200.engine import unpack_keys
+    data = synth.two_modal(200_000 + 2048, 256, 256, 3, seed=11)
+    db = (data["image"][:200_000], data["text"][:200_000])
+    qs = (data["image"][200_000:], data["text"][200_000:])
+    flags = native.NF_SEGNORM | native.NF_ROWNORM
+    res = {}
+    for prec in ("fp32", "bf16x3"):
+        res[prec] = unpack_keys(eng.topk_search(eng.prepare(qs[0], qs[1], flags=flags, precision=prec),
+                                                eng.prepare(db[0], db[1], flags=flags, precision=prec), 10, prec))
+    (s32, i32), (s3, i3) = res["fp32"], res["bf16x3"]
+    assert np.max(np.abs(s32 - s3)) < SCORE_TOL
+    safe = np.abs(np.diff(s32, axis=1)).min(axis=1) > 2 * SCORE_TOL
+    assert safe.mean() > 0.8
+    assert np.array_equal(i32[safe][:, :9], i3[safe][:, :9])
+
+
+# ------------------------------------------------------------------ K3 / K4
+def test_topk_merge(eng):
+    import torch
+    rng = np.random.default_rng(2)
+    for parts, Q, K_in, K_out in [(2, 100, 5, 5), (8, 37, 10, 10), (13, 50, 16, 7), (40, 9, 32, 32), (3, 5, 4, 9)]:
+        raw = rng.integers(1, 2**62, size=(parts, Q, K_in), dtype=np.int64)
+        raw = -np.sort(-raw, axis=2)
+        raw[0, 0, K_in - 1] = 0                              # an empty slot
+        got = _np(eng.topk_merge(torch.from_numpy(raw).cuda(), K_out))
+        flat = np.transpose(raw, (1, 0, 2)).reshape(Q, -1)
+        want = -np.sort(-flat, axis=1)[:, :K_out]
+        if K_out > flat.shape[1]:
+            want = np.concatenate([want, np.zeros((Q, K_out - flat.shape[1]), np.int64)], axis=1)
+        assert np.array_equal(got, want)
+
+
+def test_vote_metrics_against_oracle(eng, oracle):
+    import torch
+    rng = np.random.default_rng(4)
+    Q, K, C, N = 500, 5, 3, 1000
+    db_labels = rng.integers(0, C, N).astype(np.int32)
+    q_labels = rng.integers(0, C, Q).astype(np.int32)
+    groups = rng.integers(0, 5, Q).astype(np.uint8)
+    idx = np.stack([rng.choice(N, K, replace=False) for _ in range(Q)])
+    sc = -np.sort(-rng.random((Q, K)).astype(np.float32), axis=1)
+    sc[::9, 1] = sc[::9, 0]                                   # equal scores
+    sc[::11, 2:] = sc[::11, 1:2]                              # equal sums are likely -> first-label rule
+    bits = sc.view(np.uint32).astype(np.uint64) ^ np.uint64(0x80000000)
+    keys = (bits << np.uint64(32)) | (np.uint64(0xFFFFFFFF) - idx.astype(np.uint64))
+    for wacc in (False, True):
+        r = eng.vote_metrics(torch.from_numpy(keys.view(np.int64)).cuda(), db_labels, q_labels, C, k_list=[1, 3, 5, 5],
+                             wacc_f32=wacc, q_group=torch.from_numpy(groups), n_groups=5)
+        labs = db_labels[idx]
+        maj = np.array([oracle.vote_majority([int(x) for x in row]) for row in labs])
+        wv = np.array([oracle.vote_weighted([int(x) for x in row], list(s), "f32" if wacc else "f64")
+                       for row, s in zip(labs, sc)])
+        assert np.array_equal(_np(r["pred_top1"]), labs[:, 0])
+        assert np.array_equal(_np(r["pred_vote"]), maj)
+        assert np.array_equal(_np(r["pred_weighted"]), wv)
+        assert np.array_equal(_np(r["top_idx"]), idx) and np.array_equal(_np(r["top_labels"]), labs)
+        assert np.array_equal(_np(r["top_scores"]), sc)
+        for g in range(5):
+            m = groups == g
+            assert int(r["group_sizes"][g]) == int(m.sum())
+            for j, k in enumerate([1, 3, 5, 5]):
+                assert int(r["hit_counts"][g, j]) == int(sum(q_labels[i] in labs[i, :k] for i in np.nonzero(m)[0]))
+            assert int(r["vote_counts"][g, 1]) == int((maj[m] == q_labels[m]).sum())
+            assert int(r["vote_counts"][g, 2]) == int((wv[m] == q_labels[m]).sum())
+            assert np.array_equal(_np(r["confusion"][g, 0]), oracle.confusion_counts(labs[m, 0], q_labels[m], C))
+            assert np.array_equal(_np(r["confusion"][g, 1]), oracle.confusion_counts(maj[m], q_labels[m], C))
+
+
+def test_topk_from_scores(eng, oracle):
+    rng = np.random.default_rng(8)
+    s = rng.standard_normal((40, 333)).astype(np.float32)
+    s[:, 10] = s[:, 20]
+    from emr2a_b200.engine import unpack_keys
+    sc, idx = unpack_keys(eng.topk_from_scores(s, 7))
+    for i in range(40):
+        assert np.array_equal(idx[i], oracle.topk_desc(s[i], 7))
+    sc, idx = unpack_keys(eng.topk_from_scores(s[:, :3], 5))         # K > N
+    assert np.all(idx[:, 3:] == -1) and np.all(idx[:, :3] >= 0)
+
+
+def test_errors_are_loud(eng):
+    from emr2a_b200 import native
+    with pytest.raises(ValueError):
+        eng.normalize_fuse(np.zeros((3, 4), np.float32), np.zeros((2, 4), np.float32))
+    with pytest.raises(ValueError):
+        eng.topk_search(eng.prepare(np.ones((2, 8), np.float32)), eng.prepare(np.ones((2, 16), np.float32)), 1)
+    rc = eng.lib.emr2a_scores(None, None, 1, 1, 4, 4, 4, None, 1, None)
+    assert rc == native.ERR_INVALID and "scores" in native.last_error()

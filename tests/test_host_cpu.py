@@ -1,0 +1,157 @@
+"""CPU-only checks: the C-ABI library builds, loads and exports every symbol the header
+declares; host-side logic (label coding, metrics, splits, result materialisation)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from emr2a_b200 import build, native
+    build.build()
+    return native.load()
+
+
+def test_library_exports_every_header_symbol(lib):
+    from emr2a_b200 import native
+    header = open(os.path.join(REPO, "include", "emr2a.h")).read()
+    declared = set(re.findall(r"\b(emr2a_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/emr2a.h but not exported"
+        assert name in native.symbols(), f"{name} has no ctypes signature"
+    assert lib.emr2a_abi_version() == native.ABI_VERSION
+    m = re.search(r"#define EMR2A_ABI_VERSION (\d+)", header)
+    assert int(m.group(1)) == native.ABI_VERSION
+
+
+def test_header_enums_match_binding():
+    from emr2a_b200 import native
+    header = open(os.path.join(REPO, "include", "emr2a.h")).read()
+    for name, val in (("EMR2A_PREC_FP32", native.PREC_FP32), ("EMR2A_PREC_BF16X3", native.PREC_BF16X3),
+                      ("EMR2A_PREC_BF16X1", native.PREC_BF16X1), ("EMR2A_NF_SEGNORM", native.NF_SEGNORM),
+                      ("EMR2A_NF_ROWNORM", native.NF_ROWNORM), ("EMR2A_NF_ZERO_GUARD", native.NF_ZERO_GUARD),
+                      ("EMR2A_SCORE_ZSCORE", native.SCORE_ZSCORE), ("EMR2A_SCORE_MINMAX", native.SCORE_MINMAX),
+                      ("EMR2A_BF16", native.BF16), ("EMR2A_ERR_WORKSPACE", native.ERR_WORKSPACE)):
+        m = re.search(name + r"\s*=\s*(\d+)", header)
+        assert m and int(m.group(1)) == val, name
+
+
+def test_product_path_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from emr2a_b200.engine import get_engine
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        get_engine()
+    from emr2a_b200.retrieval import compute_cosine_similarity
+    with pytest.raises(RuntimeError):
+        compute_cosine_similarity(np.ones(4, np.float32), np.ones((2, 4), np.float32))
+
+
+def test_product_never_imports_the_oracle():
+    for root, _, files in os.walk(os.path.join(REPO, "emr2a_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(root, f)).read()
+                assert "emr2a_oracle" not in src and "import oracle" not in src, f
+
+
+def test_metrics_against_reference_golden(golden):
+    from emr2a_b200.utils import (compute_accuracy, compute_confusion_matrix, compute_precision_recall_f1,
+                                  compute_top_k_accuracy)
+    g = golden("primitives.npz")
+    names = lambda codes: [f"class_{int(c)}" for c in codes]      # noqa: E731
+    labs = [f"class_{c}" for c in range(4)]
+    pred, truth = names(g["m_pred"]), names(g["m_truth"])
+    prf = compute_precision_recall_f1(pred, truth, labs)
+    got = np.array([[prf[l]["precision"], prf[l]["recall"], prf[l]["f1"], prf[l]["support"]] for l in labs])
+    np.testing.assert_allclose(got, g["m_prf"], atol=1e-15)
+    cm = compute_confusion_matrix(pred, truth, labs)
+    assert np.array_equal(np.array([[cm[a][b] for b in labs] for a in labs]), g["m_cm"])
+    assert isinstance(cm["class_0"]["class_1"], int)
+    assert compute_accuracy(pred, truth) == float(g["m_acc"])
+    pl = [names(r) for r in g["m_predlists"]]
+    assert compute_top_k_accuracy(pl, truth, 3) == float(g["m_top3"])
+    with pytest.raises(ValueError, match="same length"):
+        compute_accuracy(["a"], ["a", "b"])
+    # labels outside the list are ignored by the confusion matrix, counted by P/R/F1
+    cm = compute_confusion_matrix(["x", "a"], ["a", "a"], ["a"])
+    assert cm == {"a": {"a": 1}}
+    assert compute_precision_recall_f1(["x", "a"], ["a", "a"], ["a"])["a"]["recall"] == 0.5
+    # prf_from_confusion == compute_precision_recall_f1 when every label is known
+    from emr2a_b200.utils.metrics import prf_from_confusion
+    p2 = prf_from_confusion(g["m_cm"], labs)
+    for l in labs:
+        for k in ("precision", "recall", "f1", "support"):
+            assert p2[l][k] == prf[l][k]
+
+
+def test_cv_stratified_split_matches_reference(golden):
+    from emr2a_b200 import synth
+    from emr2a_b200.utils.cv_evaluator import CVRetrievalEvaluator
+    g = golden("cv_small.npz")
+    n = int(g["meta"][0])
+    ids = synth.patient_ids(n)
+    labels = [f"class_{int(c)}" for c in g["labels"]]
+    splits = CVRetrievalEvaluator(cv_folds=5, seed=42).stratified_split(ids, labels)
+    assert len(splits) == 5
+    for f, (tr, te) in enumerate(splits):
+        assert tr == [ids[j] for j in g[f"f{f}_train_idx"]]
+        assert te == [ids[j] for j in g[f"f{f}_test_idx"]]
+        assert isinstance(tr, list) and isinstance(tr[0], str)
+
+
+def test_holdout_stratified_split_matches_reference(golden):
+    from emr2a_b200.retrieval import RetrievalEvaluator
+    g = golden("holdout_small.npz")
+    labels = ["solo" if c == 4 else f"class_{int(c)}" for c in g["ss_labels"]]
+    ev = RetrievalEvaluator(test_ratio=0.2, seed=42)
+    tr, te = ev.stratified_split(labels)
+    assert tr == list(g["ss_train1"]) and te == list(g["ss_test1"])
+    tr, te = ev.stratified_split(labels)
+    assert tr == list(g["ss_train2"]) and te == list(g["ss_test2"])
+
+
+def test_label_helpers():
+    from emr2a_b200.labels import encode, gather_lists, score_lists
+    classes, (a, b) = encode(["b", "a", "c"], ["c", "c"])
+    assert classes == ["a", "b", "c"] and list(a) == [1, 0, 2] and list(b) == [2, 2] and a.dtype == np.int32
+    idx = np.array([[2, 0], [1, -1]])
+    valid = np.array([2, 1])
+    assert gather_lists(["x", "y", "z"], idx, valid) == [["z", "x"], ["y"]]
+    assert gather_lists(["x", "y", "z"], np.array([[2, 0], [1, 1]]), np.array([2, 2])) == [["z", "x"], ["y", "y"]]
+    sl = score_lists(np.array([[0.5, 0.25], [0.125, 0.0]], dtype=np.float32), valid)
+    assert sl == [[0.5, 0.25], [0.125]] and isinstance(sl[0][0], float)
+
+
+def test_summary_and_serialisation_host_logic(tmp_path):
+    from emr2a_b200.utils.cv_evaluator import CVRetrievalEvaluator
+    ev = CVRetrievalEvaluator()
+    folds = [{m: np.float64(0.1 * (i + 1)) for m in ("top1", "top3", "top5", "vote_acc", "weighted_vote_acc",
+                                                     "macro_precision", "macro_recall", "macro_f1")} for i in range(5)]
+    s = ev._compute_summary(folds)
+    assert list(s) == ["top1", "top3", "top5", "vote_acc", "weighted_vote_acc", "macro_precision", "macro_recall", "macro_f1"]
+    assert abs(s["top1"]["mean"] - 0.3) < 1e-12 and abs(s["top1"]["std"] - np.std([.1, .2, .3, .4, .5])) < 1e-12
+    assert isinstance(s["top1"]["max"], float)
+    out = ev._make_serializable({"a": np.float32(1.5), "b": [np.int64(2), np.bool_(True)], "c": np.arange(2)})
+    assert out == {"a": 1.5, "b": [2, True], "c": [0, 1]} and type(out["b"][0]) is int
+    ev._save_summary_csv(s, tmp_path / "s.csv")
+    rows = open(tmp_path / "s.csv").read().strip().splitlines()
+    assert rows[0] == "Metric,Mean,Std,Min,Max" and rows[1] == "top1,0.3000,0.1414,0.1000,0.5000"
+
+
+def test_dropin_shims_exist_for_every_reference_module():
+    base = os.path.join(REPO, "emr2a_b200", "dropin")
+    assert os.path.exists(os.path.join(base, "retrieval", "__init__.py"))
+    assert os.path.exists(os.path.join(base, "utils", "__init__.py"))
+    import emr2a_b200.retrieval as r
+    import emr2a_b200.utils as u
+    assert r.__all__ == ["compute_cosine_similarity", "compute_euclidean_similarity", "late_fusion", "early_fusion",
+                         "RetrievalEvaluator"]
+    assert u.__all__ == ["l2_normalize", "concat_embeddings", "compute_accuracy", "compute_top_k_accuracy",
+                         "compute_precision_recall_f1", "compute_confusion_matrix"]
