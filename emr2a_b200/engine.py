@@ -28,6 +28,11 @@ def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+def _ld(t: torch.Tensor) -> int:
+    """Leading dimension in elements (a 1-row tensor may carry an arbitrary row stride)."""
+    return int(t.stride(0)) if t.shape[0] > 1 else int(t.shape[1])
+
+
 @dataclass
 class Operand:
     """Rows prepared by K1 for K2: fp32 rows and/or bf16 hi/lo planes."""
@@ -118,7 +123,7 @@ class Engine:
             return out
         with torch.cuda.device(self.device):
             native.check(self.lib.emr2a_normalize_fuse(
-                a.data_ptr(), native.ptr(b), n, d0, d1, a.stride(0), b.stride(0) if b is not None else 0,
+                a.data_ptr(), native.ptr(b), n, d0, d1, _ld(a), _ld(b) if b is not None else 0,
                 float(w0), float(w1), int(flags), code,
                 native.ptr(out.f32), dim, native.ptr(out.hi), native.ptr(out.lo), ld_planes,
                 native.ptr(out.inv_norm), self._stream()))
@@ -139,7 +144,7 @@ class Engine:
         out = torch.empty((Q, N), dtype=torch.float32, device=self.device)
         if Q and N:
             with torch.cuda.device(self.device):
-                native.check(self.lib.emr2a_scores(q.data_ptr(), db.data_ptr(), Q, N, D, q.stride(0), db.stride(0),
+                native.check(self.lib.emr2a_scores(q.data_ptr(), db.data_ptr(), Q, N, D, _ld(q), _ld(db),
                                                    out.data_ptr(), N, self._stream()))
             self.launches += 1
         return out
@@ -152,7 +157,7 @@ class Engine:
         ws = torch.empty((16,), dtype=torch.uint8, device=self.device)
         if N:
             with torch.cuda.device(self.device):
-                native.check(self.lib.emr2a_euclid_scores(q.data_ptr(), db.data_ptr(), N, D, db.stride(0),
+                native.check(self.lib.emr2a_euclid_scores(q.data_ptr(), db.data_ptr(), N, D, _ld(db),
                                                           out.data_ptr(), ws.data_ptr(), 16, self._stream()))
             self.launches += 2
         return out
@@ -167,7 +172,7 @@ class Engine:
         out = torch.empty((Q, N), dtype=torch.float32, device=self.device)
         if Q and N:
             with torch.cuda.device(self.device):
-                native.check(self.lib.emr2a_late_fuse_scores(ts.data_ptr(), im.data_ptr(), Q, N, ts.stride(0),
+                native.check(self.lib.emr2a_late_fuse_scores(ts.data_ptr(), im.data_ptr(), Q, N, _ld(ts),
                                                              float(np.float32(w_text)), float(np.float32(1 - w_text)),
                                                              mode, out.data_ptr(), N, self._stream()))
             self.launches += 1
@@ -181,7 +186,7 @@ class Engine:
         keys = torch.zeros((Q, k), dtype=torch.int64, device=self.device)
         if Q and N:
             with torch.cuda.device(self.device):
-                native.check(self.lib.emr2a_topk_from_scores(s.data_ptr(), Q, N, s.stride(0), k, keys.data_ptr(),
+                native.check(self.lib.emr2a_topk_from_scores(s.data_ptr(), Q, N, _ld(s), k, keys.data_ptr(),
                                                              self._stream()))
             self.launches += 1
         return keys
@@ -221,11 +226,11 @@ class Engine:
         if prec == native.PREC_FP32:
             if q.f32 is None or db.f32 is None:
                 raise ValueError("topk_search(fp32) needs fp32 operands")
-            ldq, lddb = q.f32.stride(0), db.f32.stride(0)
+            ldq, lddb = _ld(q.f32), _ld(db.f32)
         else:
             if q.hi is None or db.hi is None or (prec == native.PREC_BF16X3 and (q.lo is None or db.lo is None)):
                 raise ValueError("topk_search(bf16) needs bf16 operand planes")
-            ldq, lddb = q.hi.stride(0), db.hi.stride(0)
+            ldq, lddb = _ld(q.hi), _ld(db.hi)
         if q_fold is not None:
             q_fold = self.to_device(q_fold, torch.uint8)
             db_fold = self.to_device(db_fold, torch.uint8)
@@ -263,9 +268,10 @@ class Engine:
             q_group = self.to_device(q_group, torch.uint8)
         nk = len(k_list)
         dev = self.device
-        counters = torch.zeros((n_groups * (nk + 3 + 1 + 2 * n_classes * n_classes),), dtype=torch.int64, device=dev)
+        nk_alloc = max(nk, 1)                   # keep the hit-counter pointer non-null when k_list is empty
+        counters = torch.zeros((n_groups * (nk_alloc + 3 + 1 + 2 * n_classes * n_classes),), dtype=torch.int64, device=dev)
         o = 0
-        hit = counters[o:o + n_groups * nk]; o += n_groups * nk
+        hit = counters[o:o + n_groups * nk_alloc]; o += n_groups * nk_alloc
         votes = counters[o:o + n_groups * 3]; o += n_groups * 3
         sizes = counters[o:o + n_groups]; o += n_groups
         conf = counters[o:]
@@ -287,7 +293,7 @@ class Engine:
                     native.ptr(res.get("pred_top1")), native.ptr(res.get("pred_vote")), native.ptr(res.get("pred_weighted")),
                     hit.data_ptr(), votes.data_ptr(), conf.data_ptr(), sizes.data_ptr(), self._stream()))
             self.launches += 1
-        res["hit_counts"] = hit.view(n_groups, nk)
+        res["hit_counts"] = hit.view(n_groups, nk_alloc)[:, :nk]
         res["vote_counts"] = votes.view(n_groups, 3)
         res["group_sizes"] = sizes
         res["confusion"] = conf.view(n_groups, 2, n_classes, n_classes)
