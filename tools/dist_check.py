@@ -1,0 +1,33 @@
+"""Run under torchrun: sharded search at world_size W must give bit-identical keys to a
+single-GPU search of the whole database (global-index tie rule)."""
+import os, sys
+import torch, torch.distributed as dist
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+from emr2a_b200 import native, synth
+from emr2a_b200.dist import shard_range, sharded_search_and_vote
+from emr2a_b200.engine import get_engine
+
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr); dev = torch.device("cuda", lr)
+dist.init_process_group("nccl", device_id=dev)
+eng = get_engine(dev)
+n, d, q, k, c = 300_000, 256, 3000, 10, 3
+flags = native.NF_SEGNORM | native.NF_ROWNORM
+labels = synth.device_labels(0, n, c, 11, dev)
+qi, ql = synth.device_block(50_003_968, q, d, c, 11, dev, label_seed=11)
+qt, _ = synth.device_block(50_003_968, q, d, c, 12, dev, label_seed=11)
+ok = True
+for prec in ("bf16x3", "fp32"):
+    lo, hi = shard_range(n, rank, world)
+    di, _ = synth.device_block(lo, hi - lo, d, c, 11, dev, label_seed=11)
+    dt, _ = synth.device_block(lo, hi - lo, d, c, 12, dev, label_seed=11)
+    r = sharded_search_and_vote(eng, (di, dt), (qi, qt), labels, ql, c, k, lo, flags, flags, precision=prec)
+    fi, _ = synth.device_block(0, n, d, c, 11, dev, label_seed=11)
+    ft, _ = synth.device_block(0, n, d, c, 12, dev, label_seed=11)
+    full = eng.search_and_vote((fi, ft), (qi, qt), labels, ql, c, k, db_flags=flags, q_flags=flags, precision=prec)
+    same = torch.equal(r["keys"], full["keys"]) and torch.equal(r["pred_vote"], full["pred_vote"]) and torch.equal(r["confusion"], full["confusion"])
+    print(f"rank {rank}/{world} {prec}: sharded == single-GPU: {same}", flush=True)
+    ok = ok and same
+dist.barrier(); dist.destroy_process_group()
+sys.exit(0 if ok else 1)
