@@ -38,10 +38,25 @@ int simt_topk_search(const float* q, const float* db, int64_t Q, int64_t N, int 
                      const uint8_t* q_fold, const uint8_t* db_fold, int64_t idx_base, int K, uint64_t* out_keys,
                      void* workspace, size_t ws_bytes, cudaStream_t st);
 size_t tc_topk_workspace_bytes(int64_t Q, int64_t N, int K);
+struct TcPartials {
+  const uint64_t* parts;
+  int splits;
+  const uint32_t* tau;
+};
 int tc_topk_search(const uint16_t* q_hi, const uint16_t* q_lo, const uint16_t* db_hi, const uint16_t* db_lo,
                    int64_t Q, int64_t N, int D, int64_t ldq, int64_t lddb, const uint8_t* q_fold,
                    const uint8_t* db_fold, int64_t idx_base, int K, int passes, uint64_t* out_keys,
-                   void* workspace, size_t ws_bytes, float* debug_scores, cudaStream_t st);
+                   void* workspace, size_t ws_bytes, float* debug_scores, cudaStream_t st, TcPartials* partials);
+
+size_t rescore_workspace_bytes(int64_t Q, int K);
+int rescore_pipeline(const uint64_t* approx, int KP, const uint32_t* tau, const float* q, int64_t ldq, const float* db,
+                     int64_t lddb, int64_t Q, int64_t N, int D, int64_t idx_base, int K, const float* q_stats,
+                     const float* db_stats, const uint8_t* q_fold, const uint8_t* db_fold, uint64_t* out_keys,
+                     int* status, void* workspace, size_t ws_bytes, cudaStream_t st);
+
+constexpr int RESCORE_KP = 32;    // candidates kept per (query, database split) by the filter; 16 leaves too little slack (measured)
+constexpr int RESCORE_KPM = 64;   // candidates per query re-scored after merging the splits
+static inline size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
 __global__ void zero_keys_kernel(uint64_t* k, int64_t n) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -73,14 +88,19 @@ extern "C" size_t emr2a_topk_search_workspace_bytes(int64_t Q, int64_t N, int D,
   (void)D;
   if (Q <= 0 || N <= 0 || K <= 0) return 256;
   if (precision == EMR2A_PREC_FP32) return simt_topk_workspace_bytes(Q, N, K) + 256;
+  if (precision == EMR2A_PREC_BF16_RESCORE) {
+    return align256(sizeof(uint64_t) * static_cast<size_t>(Q) * RESCORE_KPM) +
+           align256(tc_topk_workspace_bytes(Q, N, RESCORE_KP)) + align256(rescore_workspace_bytes(Q, K));
+  }
   return tc_topk_workspace_bytes(Q, N, K);
 }
 
-static int topk_search_impl(const float* q_f32, const uint16_t* q_hi, const uint16_t* q_lo, const float* db_f32,
-                            const uint16_t* db_hi, const uint16_t* db_lo, int64_t Q, int64_t N, int D, int64_t ldq,
-                            int64_t lddb, const uint8_t* q_fold, const uint8_t* db_fold, int fold_sorted,
-                            int64_t idx_base, int K, int precision, uint64_t* out_keys, void* workspace,
-                            size_t ws_bytes, float* debug_scores, void* stream) {
+static int topk_search_impl(const float* q_f32, int64_t ldq_f32, const uint16_t* q_hi, const uint16_t* q_lo,
+                            int64_t ldq_bf16, const float* db_f32, int64_t lddb_f32, const uint16_t* db_hi,
+                            const uint16_t* db_lo, int64_t lddb_bf16, int64_t Q, int64_t N, int D,
+                            const uint8_t* q_fold, const uint8_t* db_fold, int fold_sorted, int64_t idx_base, int K,
+                            int precision, const float* q_stats, const float* db_stats, uint64_t* out_keys,
+                            int32_t* status, void* workspace, size_t ws_bytes, float* debug_scores, void* stream) {
   (void)fold_sorted;   // tile skipping for sorted folds is a scheduling optimisation; results never depend on it
   if (Q < 0 || N < 0 || D <= 0 || K <= 0 || !out_keys) return fail(EMR2A_ERR_INVALID, "topk_search: bad arguments (Q=%lld N=%lld D=%d K=%d)", (long long)Q, (long long)N, D, K);
   if ((q_fold == nullptr) != (db_fold == nullptr)) return fail(EMR2A_ERR_INVALID, "topk_search: q_fold and db_fold must be given together");
@@ -96,24 +116,55 @@ static int topk_search_impl(const float* q_f32, const uint16_t* q_hi, const uint
   switch (precision) {
     case EMR2A_PREC_FP32:
       if (!q_f32 || !db_f32) return fail(EMR2A_ERR_INVALID, "topk_search(fp32): q_f32/db_f32 required");
-      if (ldq < D || lddb < D) return fail(EMR2A_ERR_INVALID, "topk_search(fp32): leading dimension smaller than D");
-      return simt_topk_search(q_f32, db_f32, Q, N, D, ldq, lddb, q_fold, db_fold, idx_base, K, out_keys, workspace, ws_bytes, st);
+      if (ldq_f32 < D || lddb_f32 < D) return fail(EMR2A_ERR_INVALID, "topk_search(fp32): leading dimension smaller than D");
+      return simt_topk_search(q_f32, db_f32, Q, N, D, ldq_f32, lddb_f32, q_fold, db_fold, idx_base, K, out_keys, workspace, ws_bytes, st);
     case EMR2A_PREC_BF16X3:
-      return tc_topk_search(q_hi, q_lo, db_hi, db_lo, Q, N, D, ldq, lddb, q_fold, db_fold, idx_base, K, 3, out_keys, workspace, ws_bytes, debug_scores, st);
+      return tc_topk_search(q_hi, q_lo, db_hi, db_lo, Q, N, D, ldq_bf16, lddb_bf16, q_fold, db_fold, idx_base, K, 3, out_keys, workspace, ws_bytes, debug_scores, st, nullptr);
     case EMR2A_PREC_BF16X1:
-      return tc_topk_search(q_hi, nullptr, db_hi, nullptr, Q, N, D, ldq, lddb, q_fold, db_fold, idx_base, K, 1, out_keys, workspace, ws_bytes, debug_scores, st);
+      return tc_topk_search(q_hi, nullptr, db_hi, nullptr, Q, N, D, ldq_bf16, lddb_bf16, q_fold, db_fold, idx_base, K, 1, out_keys, workspace, ws_bytes, debug_scores, st, nullptr);
+    case EMR2A_PREC_BF16_RESCORE: {
+      if (K > 10) return fail(EMR2A_ERR_UNSUPPORTED, "topk_search(rescore): K=%d > 10 (use EMR2A_PREC_BF16X3)", K);
+      if (!q_f32 || !db_f32) return fail(EMR2A_ERR_INVALID, "topk_search(rescore): q_f32/db_f32 required");
+      if (ldq_f32 < D || lddb_f32 < D) return fail(EMR2A_ERR_INVALID, "topk_search(rescore): leading dimension smaller than D");
+      if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255)) return fail(EMR2A_ERR_INVALID, "topk_search(rescore): workspace must be 256-byte aligned");
+      const size_t a_bytes = align256(sizeof(uint64_t) * static_cast<size_t>(Q) * RESCORE_KPM);
+      const size_t t_bytes = align256(tc_topk_workspace_bytes(Q, N, RESCORE_KP));
+      const size_t r_bytes = align256(rescore_workspace_bytes(Q, K));
+      if (ws_bytes < a_bytes + t_bytes + r_bytes) return fail(EMR2A_ERR_WORKSPACE, "topk_search(rescore): workspace %zu < %zu", ws_bytes, a_bytes + t_bytes + r_bytes);
+      uint8_t* ws = static_cast<uint8_t*>(workspace);
+      uint64_t* approx = reinterpret_cast<uint64_t*>(ws);
+      TcPartials parts{};
+      int rc = tc_topk_search(q_hi, nullptr, db_hi, nullptr, Q, N, D, ldq_bf16, lddb_bf16, q_fold, db_fold, idx_base,
+                              RESCORE_KP, 1, nullptr, ws + a_bytes, t_bytes, debug_scores, st, &parts);
+      if (rc != EMR2A_OK) return rc;
+      // several splits: re-score the 64 best approximate candidates of the query (rows outside the per-split
+      // lists are bounded by tau); one split: its 32 candidates are all there is
+      int kpm = RESCORE_KP;
+      const uint64_t* cand = parts.parts;
+      if (parts.splits > 1) {
+        kpm = RESCORE_KPM;
+        rc = emr2a_topk_merge(parts.parts, parts.splits, Q, RESCORE_KP, Q * RESCORE_KP, RESCORE_KP, kpm, approx, st);
+        if (rc != EMR2A_OK) return rc;
+        cand = approx;
+      }
+      return rescore_pipeline(cand, kpm, parts.tau, q_f32, ldq_f32, db_f32, lddb_f32, Q, N, D, idx_base, K, q_stats,
+                              db_stats, q_fold, db_fold, out_keys, status, ws + a_bytes + t_bytes, r_bytes, st);
+    }
     default:
       return fail(EMR2A_ERR_INVALID, "topk_search: unknown precision %d", precision);
   }
 }
 
-extern "C" int emr2a_topk_search(const float* q_f32, const uint16_t* q_hi, const uint16_t* q_lo, const float* db_f32,
-                                 const uint16_t* db_hi, const uint16_t* db_lo, int64_t Q, int64_t N, int D,
-                                 int64_t ldq, int64_t lddb, const uint8_t* q_fold, const uint8_t* db_fold,
-                                 int fold_sorted, int64_t idx_base, int K, int precision, uint64_t* out_keys,
-                                 void* workspace, size_t ws_bytes, void* stream) {
-  return topk_search_impl(q_f32, q_hi, q_lo, db_f32, db_hi, db_lo, Q, N, D, ldq, lddb, q_fold, db_fold, fold_sorted,
-                          idx_base, K, precision, out_keys, workspace, ws_bytes, nullptr, stream);
+extern "C" int emr2a_topk_search(const float* q_f32, int64_t ldq_f32, const uint16_t* q_hi, const uint16_t* q_lo,
+                                 int64_t ldq_bf16, const float* db_f32, int64_t lddb_f32, const uint16_t* db_hi,
+                                 const uint16_t* db_lo, int64_t lddb_bf16, int64_t Q, int64_t N, int D,
+                                 const uint8_t* q_fold, const uint8_t* db_fold, int fold_sorted, int64_t idx_base,
+                                 int K, int precision, const float* q_stats, const float* db_stats,
+                                 uint64_t* out_keys, int32_t* status_out, void* workspace, size_t ws_bytes,
+                                 void* stream) {
+  return topk_search_impl(q_f32, ldq_f32, q_hi, q_lo, ldq_bf16, db_f32, lddb_f32, db_hi, db_lo, lddb_bf16, Q, N, D,
+                          q_fold, db_fold, fold_sorted, idx_base, K, precision, q_stats, db_stats, out_keys,
+                          status_out, workspace, ws_bytes, nullptr, stream);
 }
 
 // Diagnostics: same as emr2a_topk_search on the tensor-core arms, additionally dumping every
@@ -125,6 +176,7 @@ extern "C" int emr2a_debug_topk_search_dump(const uint16_t* q_hi, const uint16_t
                                             void* workspace, size_t ws_bytes, float* debug_scores, void* stream) {
   if (precision != EMR2A_PREC_BF16X3 && precision != EMR2A_PREC_BF16X1)
     return fail(EMR2A_ERR_INVALID, "debug dump is for the tensor-core arms only");
-  return topk_search_impl(nullptr, q_hi, q_lo, nullptr, db_hi, db_lo, Q, N, D, ldq, lddb, q_fold, db_fold, 0,
-                          idx_base, K, precision, out_keys, workspace, ws_bytes, debug_scores, stream);
+  return topk_search_impl(nullptr, 0, q_hi, q_lo, ldq, nullptr, 0, db_hi, db_lo, lddb, Q, N, D, q_fold, db_fold, 0,
+                          idx_base, K, precision, nullptr, nullptr, out_keys, nullptr, workspace, ws_bytes,
+                          debug_scores, stream);
 }

@@ -26,7 +26,17 @@ struct NfParams {
   uint16_t* out_lo;
   int64_t ld_bf16;
   float* inv_norm;
+  float* stats;     // [0] = max row norm, [1] = max ||row - bf16(row)||  (atomic max on the float bits)
 };
+
+__device__ __forceinline__ void stats_update(float* stats, float norm2, float res2) {
+  // non-negative floats order like their bit patterns; read first so that the (quickly saturating)
+  // running maxima cost an atomic only when they actually grow
+  unsigned int* u = reinterpret_cast<unsigned int*>(stats);
+  const unsigned int a = __float_as_uint(__fsqrt_ru(norm2)), b = __float_as_uint(__fsqrt_ru(res2));
+  if (a > __ldcg(u)) atomicMax(u, a);
+  if (b > __ldcg(u + 1)) atomicMax(u + 1, b);
+}
 
 template <typename InT> struct Loader;
 template <> struct Loader<float> {
@@ -54,8 +64,26 @@ template <> struct Loader<__nv_bfloat16> {
 };
 
 __device__ __forceinline__ float sq4(const float4& a) { return a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w; }
-__device__ __forceinline__ void div4(float4& a, float d) {
-  a.x = __fdiv_rn(a.x, d); a.y = __fdiv_rn(a.y, d); a.z = __fdiv_rn(a.z, d); a.w = __fdiv_rn(a.w, d);
+// Division of a whole row by one divisor: r = RN(1/d) once per row, then per element
+// q0 = x*r, rem = x - q0*d (exact in an FMA), q = q0 + rem*r -- the correctly rounded quotient
+// x/d (Markstein) without the per-element special-case branches of __fdiv_rn, which made K1
+// ALU-bound (3160 instructions per row).  Inputs are finite and d >= 1e-8.
+struct RowDiv {
+  float d, r;
+  __device__ __forceinline__ float operator()(float x) const {
+    const float q0 = x * r;
+    const float rem = fmaf(-q0, d, x);
+    return fmaf(rem, r, q0);
+  }
+};
+__device__ __forceinline__ RowDiv row_div(float d) {
+  RowDiv v;
+  v.d = d;
+  v.r = __frcp_rn(d);
+  return v;
+}
+__device__ __forceinline__ void div4(float4& a, const RowDiv& dv) {
+  a.x = dv(a.x); a.y = dv(a.y); a.z = dv(a.z); a.w = dv(a.w);
 }
 __device__ __forceinline__ void mul4(float4& a, float w) { a.x *= w; a.y *= w; a.z *= w; a.w *= w; }
 
@@ -86,8 +114,8 @@ __global__ void __launch_bounds__(256) normalize_fuse_vec_kernel(const NfParams 
       }
     }
     if (p.flags & EMR2A_NF_SEGNORM) {
-      const float n0 = __fsqrt_rn(warp_sum(ss0)) + EMR2A_EPS;
-      const float n1 = __fsqrt_rn(warp_sum(ss1)) + EMR2A_EPS;
+      const RowDiv n0 = row_div(__fsqrt_rn(warp_sum(ss0)) + EMR2A_EPS);
+      const RowDiv n1 = row_div(__fsqrt_rn(warp_sum(ss1)) + EMR2A_EPS);
 #pragma unroll
       for (int j = 0; j < MAXC; ++j) {
         const int c = lane + 32 * j;
@@ -110,9 +138,10 @@ __global__ void __launch_bounds__(256) normalize_fuse_vec_kernel(const NfParams 
       const bool guard = (p.flags & EMR2A_NF_ZERO_GUARD) != 0;
       if (!guard) nrm += EMR2A_EPS;
       if (!(guard && nrm == 0.f)) {
+        const RowDiv dv = row_div(nrm);
 #pragma unroll
-        for (int j = 0; j < MAXC; ++j) div4(v[j], nrm);
-        inv = __fdiv_rn(1.0f, nrm);
+        for (int j = 0; j < MAXC; ++j) div4(v[j], dv);
+        inv = dv.r;
       }
     }
     if (p.inv_norm && lane == 0) p.inv_norm[row] = inv;
@@ -124,6 +153,7 @@ __global__ void __launch_bounds__(256) normalize_fuse_vec_kernel(const NfParams 
       }
     }
     if (p.out_hi) {
+      float n2 = 0.f, r2 = 0.f;
 #pragma unroll
       for (int j = 0; j < MAXC; ++j) {
         const int c = lane + 32 * j;
@@ -131,6 +161,14 @@ __global__ void __launch_bounds__(256) normalize_fuse_vec_kernel(const NfParams 
           uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
           split_bf16(v[j].x, h0, l0); split_bf16(v[j].y, h1, l1);
           split_bf16(v[j].z, h2, l2); split_bf16(v[j].w, h3, l3);
+          if (p.stats) {
+            n2 += sq4(v[j]);
+            const float e0 = v[j].x - __uint_as_float(static_cast<uint32_t>(h0) << 16);
+            const float e1 = v[j].y - __uint_as_float(static_cast<uint32_t>(h1) << 16);
+            const float e2 = v[j].z - __uint_as_float(static_cast<uint32_t>(h2) << 16);
+            const float e3 = v[j].w - __uint_as_float(static_cast<uint32_t>(h3) << 16);
+            r2 += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+          }
           uint2 hv = make_uint2(h0 | (static_cast<uint32_t>(h1) << 16), h2 | (static_cast<uint32_t>(h3) << 16));
           *reinterpret_cast<uint2*>(p.out_hi + row * p.ld_bf16 + 4 * c) = hv;
           if (p.out_lo) {
@@ -138,6 +176,10 @@ __global__ void __launch_bounds__(256) normalize_fuse_vec_kernel(const NfParams 
             *reinterpret_cast<uint2*>(p.out_lo + row * p.ld_bf16 + 4 * c) = lv;
           }
         }
+      }
+      if (p.stats) {
+        n2 = warp_sum(n2); r2 = warp_sum(r2);
+        if (lane == 0) stats_update(p.stats, n2, r2);
       }
     }
   }
@@ -186,6 +228,7 @@ __global__ void __launch_bounds__(256) normalize_fuse_scalar_kernel(const NfPara
     }
     if (p.inv_norm && lane == 0) p.inv_norm[row] = inv;
     const int epad = p.out_hi ? static_cast<int>(p.ld_bf16) : dtot;
+    float n2 = 0.f, r2 = 0.f;
     for (int e = lane; e < epad; e += 32) {
       float x = 0.f;
       if (e < dtot) {
@@ -198,7 +241,13 @@ __global__ void __launch_bounds__(256) normalize_fuse_scalar_kernel(const NfPara
         split_bf16(x, h, l);
         p.out_hi[row * p.ld_bf16 + e] = h;
         if (p.out_lo) p.out_lo[row * p.ld_bf16 + e] = l;
+        const float er = x - __uint_as_float(static_cast<uint32_t>(h) << 16);
+        n2 += x * x; r2 += er * er;
       }
+    }
+    if (p.stats && p.out_hi) {
+      n2 = warp_sum(n2); r2 = warp_sum(r2);
+      if (lane == 0) stats_update(p.stats, n2, r2);
     }
   }
 }
@@ -242,17 +291,18 @@ using namespace emr2a;
 extern "C" int emr2a_normalize_fuse(const void* seg0, const void* seg1, int64_t n, int d0, int d1,
                                     int64_t ld0, int64_t ld1, float w0, float w1, int flags, int in_dtype,
                                     float* out_f32, int64_t ld_f32, uint16_t* out_hi, uint16_t* out_lo,
-                                    int64_t ld_bf16, float* inv_norm_out, void* stream) {
+                                    int64_t ld_bf16, float* inv_norm_out, float* stats_out, void* stream) {
   if (n < 0 || d0 <= 0 || d1 < 0) return fail(EMR2A_ERR_INVALID, "normalize_fuse: bad shape n=%lld d0=%d d1=%d", (long long)n, d0, d1);
   if (!seg0 || (d1 > 0 && !seg1)) return fail(EMR2A_ERR_INVALID, "normalize_fuse: null segment pointer");
   if (ld0 < d0 || (d1 > 0 && ld1 < d1)) return fail(EMR2A_ERR_INVALID, "normalize_fuse: leading dimension smaller than row");
   if (in_dtype != EMR2A_F32 && in_dtype != EMR2A_BF16) return fail(EMR2A_ERR_INVALID, "normalize_fuse: unknown dtype %d", in_dtype);
   if (out_lo && !out_hi) return fail(EMR2A_ERR_INVALID, "normalize_fuse: out_lo without out_hi");
+  if (stats_out && !out_hi) return fail(EMR2A_ERR_INVALID, "normalize_fuse: stats_out needs the bf16 planes");
   if (out_f32 && ld_f32 < d0 + d1) return fail(EMR2A_ERR_INVALID, "normalize_fuse: ld_f32 too small");
   if (out_hi && ld_bf16 < d0 + d1) return fail(EMR2A_ERR_INVALID, "normalize_fuse: ld_bf16 too small");
   if (n == 0) return EMR2A_OK;
   NfParams p{seg0, seg1, n, d0, d1, ld0, d1 > 0 ? ld1 : 0, w0, w1, flags,
-             out_f32, ld_f32, out_hi, out_lo, ld_bf16, inv_norm_out};
+             out_f32, ld_f32, out_hi, out_lo, ld_bf16, inv_norm_out, stats_out};
   const size_t in_align = in_dtype == EMR2A_F32 ? 16 : 8;
   auto aligned = [](const void* q, size_t a) { return (reinterpret_cast<uintptr_t>(q) % a) == 0; };
   bool vec_ok = (d0 % 4 == 0) && (d1 % 4 == 0) && (ld0 % 4 == 0) && (d1 == 0 || ld1 % 4 == 0) &&

@@ -1,0 +1,298 @@
+// EMR2A_PREC_BF16_RESCORE: exact re-scoring of the candidates the 1-pass tensor-core filter kept,
+// verified selection, and an exact re-scan for the (rare) queries the bound cannot verify.
+//
+// Filter:   s~(q,d) = <bf16(q), bf16(d)> accumulated in fp32 on the tensor cores; per query the KP = 32
+//           rows with the largest s~ are kept (K <= 10: the slack below the K-th best must hold ~2E of scores).
+// Rescore:  s(q,d) = fp32 dot product of the fp32 rows K1 wrote (the same values the fp32 arm uses).
+// Bound:    |s~ - s| <= E = r_q * n_d + (n_q + r_q) * r_d + 1e-5 * n_q * n_d   for every pair, where
+//           n_* = max row norm and r_* = max ||row - bf16(row)|| over the queries / database rows
+//           (K1 `stats`, Cauchy-Schwarz on the two quantisation residuals; the last term covers
+//           the fp32 accumulation inside the tensor core).
+// Verify:   every row outside the candidate list has s~ <= tau (the KP-th approximate score), hence
+//           s <= tau + E.  If the exact K-th best candidate score exceeds tau + E strictly, no
+//           outside row can enter the Top-K and the selection is exact.  Otherwise the query is
+//           appended to a flag list and re-searched exactly against the whole database
+//           (exact_rescan_kernel, cost proportional to the number of flagged queries).
+// Roofline: HBM-bound gather: Q * KP * D * 4 bytes (C2: 1.3 GB, ~0.3 ms).
+#include "common.cuh"
+
+namespace emr2a {
+
+struct RescoreParams {
+  const uint64_t* approx;   // [Q][KP] approximate keys, best first (KP = 32 or 64)
+  int KP;
+  const uint32_t* tau;      // [Q] bound (order-preserving image) on the filter score of rows outside the per-split lists; may be null
+  const float* q; int64_t ldq;
+  const float* db; int64_t lddb;
+  int64_t Q, N;
+  int D;
+  int64_t idx_base;
+  int K;
+  const float* q_stats;
+  const float* db_stats;
+  uint64_t* out;            // [Q][K]
+  int* status;              // [0] = #unverified queries, [1] = flag list overflow
+  int* flag_list;
+  int cap;
+  // exact re-scan
+  const uint8_t* q_fold;
+  const uint8_t* db_fold;
+  uint64_t* fb_parts;       // [blocks][cap][K]
+};
+
+template <bool VEC>
+__device__ __forceinline__ float lane_dot(const float* __restrict__ a, const float* __restrict__ b, int D, int lane) {
+  float acc = 0.f;
+  if (VEC) {
+    for (int c = lane * 4; c < D; c += 128) {
+      const float4 x = *reinterpret_cast<const float4*>(a + c);
+      const float4 y = __ldg(reinterpret_cast<const float4*>(b + c));
+      acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+    }
+  } else {
+    for (int c = lane; c < D; c += 32) acc = fmaf(a[c], __ldg(b + c), acc);
+  }
+  return acc;
+}
+
+__device__ __forceinline__ float error_bound(const float* qs, const float* ds) {
+  const float nq = qs[0], rq = qs[1], nd = ds[0], rd = ds[1];
+  return rq * nd + (nq + rq) * rd + 1e-5f * nq * nd + 1e-7f;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) rescore_select_kernel(const RescoreParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (q >= p.Q) return;
+  // lane holds candidates lane and lane + 32
+  uint64_t akey[2], ekey[2] = {0ull, 0ull};
+  akey[0] = lane < p.KP ? p.approx[q * p.KP + lane] : 0ull;
+  akey[1] = lane + 32 < p.KP ? p.approx[q * p.KP + lane + 32] : 0ull;
+  const uint64_t last = __shfl_sync(0xffffffffu, p.KP > 32 ? akey[1] : akey[0], (p.KP - 1) & 31);
+  const float* qrow = p.q + q * p.ldq;
+  bool done = false;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    for (int g = 0; g < 32 && !done && h * 32 + g < p.KP; g += 4) {
+      uint64_t kk[4];
+      float acc[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { kk[c] = __shfl_sync(0xffffffffu, akey[h], g + c); acc[c] = 0.f; }
+      if (kk[0] == 0ull) { done = true; break; }      // lists are packed: nothing valid beyond the first empty slot
+      if (VEC) {
+        for (int e = lane * 4; e < p.D; e += 128) {
+          const float4 x = __ldg(reinterpret_cast<const float4*>(qrow + e));
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (kk[c] != 0ull) {
+              const int64_t row = static_cast<int64_t>(key_index(kk[c])) - p.idx_base;
+              const float4 y = __ldg(reinterpret_cast<const float4*>(p.db + row * p.lddb + e));
+              acc[c] = fmaf(x.x, y.x, acc[c]); acc[c] = fmaf(x.y, y.y, acc[c]);
+              acc[c] = fmaf(x.z, y.z, acc[c]); acc[c] = fmaf(x.w, y.w, acc[c]);
+            }
+          }
+        }
+      } else {
+        for (int e = lane; e < p.D; e += 32) {
+          const float x = __ldg(qrow + e);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (kk[c] != 0ull) {
+              const int64_t row = static_cast<int64_t>(key_index(kk[c])) - p.idx_base;
+              acc[c] = fmaf(x, __ldg(p.db + row * p.lddb + e), acc[c]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float s = warp_sum(acc[c]);
+        if (lane == g + c && kk[c] != 0ull) ekey[h] = pack_key(s, key_index(kk[c]));
+      }
+    }
+  }
+  // exact Top-K of the candidates
+  uint64_t mine = 0ull;
+  for (int r = 0; r < p.K; ++r) {
+    const uint64_t loc = ekey[0] > ekey[1] ? ekey[0] : ekey[1];
+    const uint64_t best = warp_max_u64(loc);
+    if (best != 0ull) {
+      if (ekey[0] == best) ekey[0] = 0ull;
+      if (ekey[1] == best) ekey[1] = 0ull;
+    }
+    if (lane == r) mine = best;
+  }
+  if (lane < p.K) p.out[q * p.K + lane] = mine;
+  // Verification.  Rows that are not candidates have a filter score <= tau:
+  //   - rows a split kept but the merge dropped:            <= the last merged candidate's score
+  //   - rows a split did not keep (its list was full, or the shared threshold pruned them):
+  //                                                          <= p.tau[q] = max over the full lists of their last score
+  float tau = -INFINITY;
+  bool bounded = false;
+  if (last != 0ull) { tau = key_score(last); bounded = true; }
+  if (p.tau != nullptr) {
+    const uint32_t t = __ldcg(p.tau + q);
+    if (t != 0u) { tau = fmaxf(tau, unorder_f32(t)); bounded = true; }
+  }
+  if (bounded) {
+    const uint64_t kth = __shfl_sync(0xffffffffu, mine, p.K - 1);
+    const float E = error_bound(p.q_stats, p.db_stats);
+    const bool ok = kth != 0ull && key_score(kth) > tau + E;
+    if (!ok && lane == 0) {
+      const int i = atomicAdd(&p.status[0], 1);
+      if (i < p.cap) p.flag_list[i] = static_cast<int>(q); else p.status[1] = 1;
+    }
+  }
+}
+
+// Exact re-search of the flagged queries against every database row (fp32, CUDA cores).  A block
+// owns a contiguous row range and walks the flagged queries in groups held in shared memory; each
+// warp keeps one sorted list per query of the group.
+constexpr int FB_WARPS = 8;
+constexpr int FB_GMAX = 8;
+
+template <bool VEC>
+__global__ void __launch_bounds__(FB_WARPS * 32) exact_rescan_kernel(const RescoreParams p, int G) {
+  extern __shared__ __align__(16) unsigned char fb_smem[];
+  int n = p.status[0];
+  if (n > p.cap) n = p.cap;
+  if (n <= 0) return;
+  float* qbuf = reinterpret_cast<float*>(fb_smem);                                   // [G][Dp]
+  const int Dp = (p.D + 3) & ~3;
+  uint64_t* lists = reinterpret_cast<uint64_t*>(fb_smem + sizeof(float) * G * Dp);   // [FB_WARPS][G][K]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int K = p.K;
+  const int64_t per = (p.N + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * per;
+  const int64_t r1 = (r0 + per < p.N) ? r0 + per : p.N;
+
+  for (int g0 = 0; g0 < n; g0 += G) {
+    const int gc = (n - g0 < G) ? (n - g0) : G;
+    __syncthreads();
+    for (int e = threadIdx.x; e < gc * Dp; e += blockDim.x) {
+      const int g = e / Dp, c = e - g * Dp;
+      qbuf[e] = c < p.D ? p.q[static_cast<int64_t>(p.flag_list[g0 + g]) * p.ldq + c] : 0.f;
+    }
+    for (int e = threadIdx.x; e < FB_WARPS * G * K; e += blockDim.x) lists[e] = 0ull;
+    __syncthreads();
+    uint64_t kth = 0ull;                             // lane g: K-th best of (this warp, query g)
+    const int my_fold = (p.q_fold && lane < gc) ? p.q_fold[p.flag_list[g0 + lane]] : -1;
+    for (int64_t r = r0 + warp; r < r1; r += FB_WARPS) {
+      const float* drow = p.db + r * p.lddb;
+      const int dfold = p.db_fold ? p.db_fold[r] : -2;
+      for (int g = 0; g < gc; ++g) {
+        const float s = warp_sum(lane_dot<VEC>(qbuf + g * Dp, drow, p.D, lane));
+        if (lane == g && dfold != my_fold) {
+          const uint64_t key = pack_key(s, static_cast<uint32_t>(r + p.idx_base));
+          if (key > kth) {
+            uint64_t* mine = lists + (warp * G + g) * K;
+            int pos = K - 1;
+            while (pos > 0 && mine[pos - 1] < key) { mine[pos] = mine[pos - 1]; --pos; }
+            mine[pos] = key;
+            kth = mine[K - 1];
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // merge the FB_WARPS lists of each query: warp w serves queries w, w+8, ...
+    for (int g = warp; g < gc; g += FB_WARPS) {
+      uint64_t bound = ~0ull;
+      for (int rnk = 0; rnk < K; ++rnk) {
+        uint64_t best = 0ull;
+        for (int t = lane; t < FB_WARPS * K; t += 32) {
+          const int w = t / K, j = t - w * K;
+          const uint64_t key = lists[(w * G + g) * K + j];
+          if (key < bound && key > best) best = key;
+        }
+        best = warp_max_u64(best);
+        bound = best;
+        if (lane == 0) p.fb_parts[(static_cast<int64_t>(blockIdx.x) * p.cap + g0 + g) * K + rnk] = best;
+        if (best == 0ull) {
+          for (int r2 = rnk + 1 + lane; r2 < K; r2 += 32)
+            p.fb_parts[(static_cast<int64_t>(blockIdx.x) * p.cap + g0 + g) * K + r2] = 0ull;
+          break;
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) rescan_merge_kernel(const RescoreParams p, int blocks) {
+  int n = p.status[0];
+  if (n > p.cap) n = p.cap;
+  const int lane = threadIdx.x & 31;
+  const int i = static_cast<int>((static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
+  if (i >= n) return;
+  const int K = p.K;
+  const int64_t qd = p.flag_list[i];
+  uint64_t bound = ~0ull;
+  for (int rnk = 0; rnk < K; ++rnk) {
+    uint64_t best = 0ull;
+    if (bound != 0ull) {
+      for (int t = lane; t < blocks * K; t += 32) {
+        const int b = t / K, j = t - b * K;
+        const uint64_t key = p.fb_parts[(static_cast<int64_t>(b) * p.cap + i) * K + j];
+        if (key < bound && key > best) best = key;
+      }
+      best = warp_max_u64(best);
+    }
+    bound = best;
+    if (lane == 0) p.out[qd * K + rnk] = best;
+  }
+}
+
+int rescore_fallback_blocks() { return 2 * sm_count(); }
+int rescore_cap(int64_t Q) { return static_cast<int>(Q < 1024 ? Q : 1024); }
+
+size_t rescore_workspace_bytes(int64_t Q, int K) {
+  const int cap = rescore_cap(Q);
+  return sizeof(int) * static_cast<size_t>(cap) + 256 +
+         sizeof(uint64_t) * static_cast<size_t>(rescore_fallback_blocks()) * cap * K + 256;
+}
+
+// approx: merged approximate keys [Q][KP]; writes exact keys [Q][K]; status[0..1] must be zeroed by the caller.
+int rescore_pipeline(const uint64_t* approx, int KP, const uint32_t* tau, const float* q, int64_t ldq, const float* db,
+                     int64_t lddb, int64_t Q, int64_t N, int D, int64_t idx_base, int K, const float* q_stats,
+                     const float* db_stats, const uint8_t* q_fold, const uint8_t* db_fold, uint64_t* out_keys,
+                     int* status, void* workspace, size_t ws_bytes, cudaStream_t st) {
+  if (!q_stats || !db_stats) return fail(EMR2A_ERR_INVALID, "topk_search(rescore): q_stats/db_stats (K1 stats) required");
+  if (!status) return fail(EMR2A_ERR_INVALID, "topk_search(rescore): status_out required");
+  if (rescore_workspace_bytes(Q, K) > ws_bytes) return fail(EMR2A_ERR_WORKSPACE, "topk_search(rescore): workspace too small");
+  RescoreParams p{};
+  p.approx = approx; p.KP = KP; p.tau = tau; p.q = q; p.ldq = ldq; p.db = db; p.lddb = lddb; p.Q = Q; p.N = N; p.D = D;
+  p.idx_base = idx_base; p.K = K; p.q_stats = q_stats; p.db_stats = db_stats; p.out = out_keys; p.status = status;
+  p.cap = rescore_cap(Q);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  p.flag_list = reinterpret_cast<int*>(ws);
+  const size_t off = (sizeof(int) * static_cast<size_t>(p.cap) + 255) & ~static_cast<size_t>(255);
+  p.fb_parts = reinterpret_cast<uint64_t*>(ws + off);
+  p.q_fold = q_fold; p.db_fold = db_fold;
+  auto al16 = [](const void* x) { return (reinterpret_cast<uintptr_t>(x) & 15) == 0; };
+  const bool vec = (D % 4 == 0) && (ldq % 4 == 0) && (lddb % 4 == 0) && al16(q) && al16(db);
+  const unsigned blocks = static_cast<unsigned>((Q * 32 + 255) / 256);
+  if (vec) rescore_select_kernel<true><<<blocks, 256, 0, st>>>(p);
+  else rescore_select_kernel<false><<<blocks, 256, 0, st>>>(p);
+  EMR2A_LAUNCH_CHECK("rescore_select_kernel");
+  // exact re-scan of unverified queries; both kernels return at once when status[0] == 0
+  const int Dp = (D + 3) & ~3;
+  int G = static_cast<int>((96 * 1024) / (sizeof(float) * Dp));
+  if (G > FB_GMAX) G = FB_GMAX;
+  if (G < 1) return fail(EMR2A_ERR_UNSUPPORTED, "topk_search(rescore): D=%d too large for the exact re-scan", D);
+  const size_t smem = sizeof(float) * G * Dp + sizeof(uint64_t) * FB_WARPS * G * K;
+  const int fb_blocks = rescore_fallback_blocks();
+  if (vec) {
+    EMR2A_CUDA_TRY(cudaFuncSetAttribute(exact_rescan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    exact_rescan_kernel<true><<<fb_blocks, FB_WARPS * 32, smem, st>>>(p, G);
+  } else {
+    EMR2A_CUDA_TRY(cudaFuncSetAttribute(exact_rescan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    exact_rescan_kernel<false><<<fb_blocks, FB_WARPS * 32, smem, st>>>(p, G);
+  }
+  EMR2A_LAUNCH_CHECK("exact_rescan_kernel");
+  rescan_merge_kernel<<<static_cast<unsigned>((static_cast<int64_t>(p.cap) * 32 + 255) / 256), 256, 0, st>>>(p, fb_blocks);
+  EMR2A_LAUNCH_CHECK("rescan_merge_kernel");
+  return EMR2A_OK;
+}
+
+}  // namespace emr2a

@@ -40,6 +40,7 @@ struct TcParams {
   int64_t idx_base;
   int K;
   uint64_t* keys_out;      // [splits][Q][K]
+  uint32_t* tau;           // [Q] order-preserving image of a lower bound of the query's global KCAP-th best score
   float* debug_scores;     // optional [Q][N] dump of every score (bring-up / tests)
 };
 
@@ -281,7 +282,16 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
       const int64_t t1 = (t0 + p.tiles_per_split < p.n_tiles) ? t0 + p.tiles_per_split : p.n_tiles;
       const uint32_t my_fold = (HAS_FOLD && q < p.Q) ? p.q_fold[q] : 0xFFFFu;
       top.reset();
-      float thr = -INFINITY;
+      // Units of the same query tile that finished earlier published their KCAP-th best score: the global
+      // KCAP-th best is at least that, so rows strictly below it can be skipped here without changing the
+      // merged list (">= bound" is kept, hence the step down by one ulp).  It removes the list warm-up --
+      // a burst of warp-serialised insertions -- from every unit but the first of a query tile.
+      float thr0 = -INFINITY;
+      if (p.tau != nullptr && q < p.Q) {
+        const uint32_t t = __ldcg(p.tau + q);
+        if (t != 0u) thr0 = __uint_as_float(__float_as_uint(unorder_f32(t)) - ((unorder_f32(t) > 0.f) ? 1u : 0u) + ((unorder_f32(t) < 0.f) ? 1u : 0u));
+      }
+      float thr = thr0;
       for (int64_t t = t0; t < t1; ++t) {
         const int64_t n0 = t * T_BN;
         mbar_wait(smem_u32(&bar_tfull[acc]), acc_phase);
@@ -323,7 +333,7 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
               const float val = select32(v, c);
               if (val > thr) {
                 top.insert(val, static_cast<uint32_t>(c0 + c + p.idx_base));
-                thr = top.threshold();
+                thr = fmaxf(top.threshold(), thr0);
               }
             }
           }
@@ -335,6 +345,7 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
       if (q < p.Q) {
+        if (p.tau != nullptr && top.i[KCAP - 1] != 0xFFFFFFFFu) atomicMax(p.tau + q, order_f32(top.s[KCAP - 1]));
         uint64_t* dst = p.keys_out + (split * p.Q + q) * p.K;
 #pragma unroll
         for (int j = 0; j < KCAP; ++j)
@@ -382,11 +393,18 @@ static int make_plane_map(CUtensorMap* map, const uint16_t* base, int64_t rows, 
   return EMR2A_OK;
 }
 
+// When the caller asks for it, the per-split lists are left unmerged and described here.
+struct TcPartials {
+  const uint64_t* parts;   // [splits][Q][K]
+  int splits;
+  const uint32_t* tau;     // [Q] max over splits of the split's K-th (last kept) score, 0 = no list was full; null if splits == 1
+};
+
 struct TcPlan {
   int64_t m_tiles, n_tiles, tiles_per_split;
   int splits;
   int grid;
-  size_t keys_bytes, fold_bytes;
+  size_t keys_bytes, fold_bytes, tau_bytes;
 };
 
 static TcPlan tc_plan(int64_t Q, int64_t N, int K, bool has_fold) {
@@ -415,12 +433,13 @@ static TcPlan tc_plan(int64_t Q, int64_t N, int K, bool has_fold) {
   pl.grid = static_cast<int>(units < sms ? units : sms);
   pl.keys_bytes = sizeof(uint64_t) * static_cast<size_t>(pl.splits) * Q * K;
   pl.fold_bytes = has_fold ? static_cast<size_t>(pl.n_tiles) * T_BN : 0;
+  pl.tau_bytes = (sizeof(uint32_t) * static_cast<size_t>(Q) + 255) & ~static_cast<size_t>(255);
   return pl;
 }
 
 size_t tc_topk_workspace_bytes(int64_t Q, int64_t N, int K) {
   TcPlan pl = tc_plan(Q, N, K, true);
-  return ((pl.keys_bytes + 255) & ~static_cast<size_t>(255)) + pl.fold_bytes + 256;
+  return ((pl.keys_bytes + 255) & ~static_cast<size_t>(255)) + pl.fold_bytes + pl.tau_bytes + 512;
 }
 
 template <int PASSES, int KCAP, bool HAS_FOLD>
@@ -446,7 +465,8 @@ static int tc_launch_fold(bool has_fold, const CUtensorMap& a, const CUtensorMap
 int tc_topk_search(const uint16_t* q_hi, const uint16_t* q_lo, const uint16_t* db_hi, const uint16_t* db_lo,
                    int64_t Q, int64_t N, int D, int64_t ldq, int64_t lddb,
                    const uint8_t* q_fold, const uint8_t* db_fold, int64_t idx_base, int K, int passes,
-                   uint64_t* out_keys, void* workspace, size_t ws_bytes, float* debug_scores, cudaStream_t st) {
+                   uint64_t* out_keys, void* workspace, size_t ws_bytes, float* debug_scores, cudaStream_t st,
+                   TcPartials* partials) {
   if (K > 32) return fail(EMR2A_ERR_UNSUPPORTED, "topk_search(bf16): K=%d > 32 (use EMR2A_PREC_FP32)", K);
   const int64_t Dp = (static_cast<int64_t>(D) + T_BK - 1) / T_BK * T_BK;
   if (ldq < Dp || lddb < Dp || (ldq % 8) || (lddb % 8))
@@ -461,7 +481,8 @@ int tc_topk_search(const uint16_t* q_hi, const uint16_t* q_lo, const uint16_t* d
   TcPlan pl = tc_plan(Q, N, K, has_fold);
   const size_t keys_off = 0;
   const size_t fold_off = (pl.keys_bytes + 255) & ~static_cast<size_t>(255);
-  const size_t need = fold_off + pl.fold_bytes;
+  const size_t tau_off = (fold_off + pl.fold_bytes + 255) & ~static_cast<size_t>(255);
+  const size_t need = tau_off + pl.tau_bytes;
   if (!workspace || ws_bytes < need) return fail(EMR2A_ERR_WORKSPACE, "topk_search(bf16): workspace %zu < %zu", ws_bytes, need);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return fail(EMR2A_ERR_INVALID, "topk_search(bf16): workspace must be 256-byte aligned");
@@ -480,7 +501,11 @@ int tc_topk_search(const uint16_t* q_hi, const uint16_t* q_lo, const uint16_t* d
   p.Q = Q; p.N = N; p.k_chunks = static_cast<int>(Dp / T_BK);
   p.m_tiles = pl.m_tiles; p.n_tiles = pl.n_tiles; p.splits = pl.splits; p.tiles_per_split = pl.tiles_per_split;
   p.idx_base = idx_base; p.K = K; p.debug_scores = debug_scores;
-  p.keys_out = pl.splits > 1 ? reinterpret_cast<uint64_t*>(ws + keys_off) : out_keys;
+  p.keys_out = (pl.splits > 1 || partials) ? reinterpret_cast<uint64_t*>(ws + keys_off) : out_keys;
+  if (pl.splits > 1) {     // sharing only pays (and is only needed) when a query tile is searched by several units
+    p.tau = reinterpret_cast<uint32_t*>(ws + tau_off);
+    EMR2A_CUDA_TRY(cudaMemsetAsync(p.tau, 0, sizeof(uint32_t) * static_cast<size_t>(Q), st));
+  }
   if (has_fold) {
     uint8_t* fpad = ws + fold_off;
     EMR2A_CUDA_TRY(cudaMemsetAsync(fpad, 0xFF, pl.fold_bytes, st));
@@ -498,6 +523,12 @@ int tc_topk_search(const uint16_t* q_hi, const uint16_t* q_lo, const uint16_t* d
     else rc = tc_launch_fold<1, 32>(has_fold, mq_hi, mq_lo, md_hi, md_lo, p, pl.grid, st);
   }
   if (rc != EMR2A_OK) return rc;
+  if (partials) {
+    partials->parts = p.keys_out;
+    partials->splits = pl.splits;
+    partials->tau = p.tau;
+    return EMR2A_OK;
+  }
   if (pl.splits > 1)
     return emr2a_topk_merge(reinterpret_cast<const uint64_t*>(ws + keys_off), pl.splits, Q, K, Q * K, K, K, out_keys, st);
   return EMR2A_OK;

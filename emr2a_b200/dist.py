@@ -55,6 +55,15 @@ def sharded_search_and_vote(eng, db_segs_local: Sequence, q_segs: Sequence, db_l
     keys = eng.topk_search(qs, db, k, prec, q_fold=q_fold, db_fold=db_fold_local, idx_base=row_offset)
     if timers is not None:
         timers["k2_end"].record()
+    if prec == "rescore":
+        unverified, overflow = eng.consume_status()
+        flag = torch.tensor([int(overflow)], device=keys.device, dtype=torch.int32)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if int(flag.item()):          # some rank could not verify within its re-scan capacity: all ranks take the 3-pass arm
+            return sharded_search_and_vote(eng, db_segs_local, q_segs, db_labels_global, q_labels, n_classes, k,
+                                           row_offset, db_flags, q_flags, q_weights, k_list, "bf16x3", q_fold,
+                                           db_fold_local, q_group, n_groups, want_lists, timers)
     if world > 1:
         allk = gather_keys(keys)
         keys = eng.topk_merge(allk, k)
@@ -62,4 +71,6 @@ def sharded_search_and_vote(eng, db_segs_local: Sequence, q_segs: Sequence, db_l
                            n_groups=n_groups, want_lists=want_lists)
     res["keys"] = keys
     res["precision"] = prec
+    if prec == "rescore":
+        res["unverified"] = unverified
     return res

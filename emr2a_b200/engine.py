@@ -19,7 +19,9 @@ import torch
 
 from . import native
 
-_PREC = {"fp32": native.PREC_FP32, "bf16x3": native.PREC_BF16X3, "bf16x1": native.PREC_BF16X1}
+_PREC = {"fp32": native.PREC_FP32, "bf16x3": native.PREC_BF16X3, "bf16x1": native.PREC_BF16X1,
+         "rescore": native.PREC_BF16_RESCORE}
+_RESCORE_MAX_K = 10
 # tensor cores pay off once the contraction is large; below this the exact fp32 arm is used
 _TC_MIN_MACS = float(os.environ.get("EMR2A_TC_MIN_MACS", 2.0e9))
 
@@ -42,6 +44,7 @@ class Operand:
     hi: Optional[torch.Tensor] = None       # [n, ld] bf16 bits (int16 storage)
     lo: Optional[torch.Tensor] = None
     inv_norm: Optional[torch.Tensor] = None
+    stats: Optional[torch.Tensor] = None    # [max row norm, max ||row - bf16(row)||]  (rescore error bound)
 
     @property
     def ld_planes(self) -> int:
@@ -59,6 +62,7 @@ class Engine:
         with torch.cuda.device(self.device):
             self.sm_count, self.cc_major, self.cc_minor = native.device_check()
         self.launches = 0       # kernels of ours launched through this engine (bench reports it)
+        self._status_log: List[torch.Tensor] = []   # status_out of rescore searches not yet checked
 
     # ------------------------------------------------------------------ utils
     def _stream(self) -> int:
@@ -95,7 +99,7 @@ class Engine:
     # --------------------------------------------------------------------- K1
     def normalize_fuse(self, seg0, seg1=None, w0: float = 1.0, w1: float = 1.0, flags: int = native.NF_ROWNORM,
                        want_f32: bool = True, want_planes: bool = False, want_lo: bool = True,
-                       want_inv_norm: bool = False) -> Operand:
+                       want_inv_norm: bool = False, want_stats: bool = False) -> Operand:
         a, code = self._embedding(seg0)
         n, d0 = a.shape
         b = None
@@ -119,6 +123,8 @@ class Engine:
                 out.lo = torch.empty((n, ld_planes), dtype=torch.int16, device=self.device)
         if want_inv_norm:
             out.inv_norm = torch.empty((n,), dtype=torch.float32, device=self.device)
+        if want_stats and want_planes:
+            out.stats = torch.zeros((2,), dtype=torch.float32, device=self.device)
         if n == 0:
             return out
         with torch.cuda.device(self.device):
@@ -126,7 +132,7 @@ class Engine:
                 a.data_ptr(), native.ptr(b), n, d0, d1, _ld(a), _ld(b) if b is not None else 0,
                 float(w0), float(w1), int(flags), code,
                 native.ptr(out.f32), dim, native.ptr(out.hi), native.ptr(out.lo), ld_planes,
-                native.ptr(out.inv_norm), self._stream()))
+                native.ptr(out.inv_norm), native.ptr(out.stats), self._stream()))
         self.launches += 1
         return out
 
@@ -198,14 +204,20 @@ class Engine:
             if req not in _PREC:
                 raise ValueError(f"unknown precision {req!r}")
             return req
-        if K <= 32 and float(Q) * float(N) * float(D) >= _TC_MIN_MACS:
-            return "bf16x3"
+        if float(Q) * float(N) * float(D) >= _TC_MIN_MACS:
+            if K <= _RESCORE_MAX_K:
+                return "rescore"
+            if K <= 32:
+                return "bf16x3"
         return "fp32"
 
     def prepare(self, seg0, seg1=None, w0=1.0, w1=1.0, flags=native.NF_ROWNORM, precision="fp32") -> Operand:
         """K1 with the outputs the chosen K2 arm consumes."""
         if precision == "fp32":
             return self.normalize_fuse(seg0, seg1, w0, w1, flags, want_f32=True, want_planes=False)
+        if precision == "rescore":
+            return self.normalize_fuse(seg0, seg1, w0, w1, flags, want_f32=True, want_planes=True, want_lo=False,
+                                       want_stats=True)
         return self.normalize_fuse(seg0, seg1, w0, w1, flags, want_f32=False, want_planes=True,
                                    want_lo=(precision == "bf16x3"))
 
@@ -223,25 +235,44 @@ class Engine:
         ws_bytes = int(self.lib.emr2a_topk_search_workspace_bytes(Q, N, D, k, prec))
         ws = torch.empty((ws_bytes + 256,), dtype=torch.uint8, device=self.device)
         ws_ptr = _round_up(ws.data_ptr(), 256)
-        if prec == native.PREC_FP32:
-            if q.f32 is None or db.f32 is None:
-                raise ValueError("topk_search(fp32) needs fp32 operands")
-            ldq, lddb = _ld(q.f32), _ld(db.f32)
-        else:
-            if q.hi is None or db.hi is None or (prec == native.PREC_BF16X3 and (q.lo is None or db.lo is None)):
-                raise ValueError("topk_search(bf16) needs bf16 operand planes")
-            ldq, lddb = _ld(q.hi), _ld(db.hi)
+        need_f32 = prec in (native.PREC_FP32, native.PREC_BF16_RESCORE)
+        need_hi = prec != native.PREC_FP32
+        if need_f32 and (q.f32 is None or db.f32 is None):
+            raise ValueError(f"topk_search({precision}) needs fp32 operands")
+        if need_hi and (q.hi is None or db.hi is None or (prec == native.PREC_BF16X3 and (q.lo is None or db.lo is None))):
+            raise ValueError(f"topk_search({precision}) needs bf16 operand planes")
+        status = None
+        if prec == native.PREC_BF16_RESCORE:
+            if q.stats is None or db.stats is None:
+                raise ValueError("topk_search(rescore) needs operands prepared with stats")
+            if k > _RESCORE_MAX_K:
+                raise ValueError(f"topk_search(rescore): K={k} > {_RESCORE_MAX_K}")
+            status = torch.zeros((4,), dtype=torch.int32, device=self.device)
         if q_fold is not None:
             q_fold = self.to_device(q_fold, torch.uint8)
             db_fold = self.to_device(db_fold, torch.uint8)
         with torch.cuda.device(self.device):
             native.check(self.lib.emr2a_topk_search(
-                native.ptr(q.f32), native.ptr(q.hi), native.ptr(q.lo),
-                native.ptr(db.f32), native.ptr(db.hi), native.ptr(db.lo),
-                Q, N, D, ldq, lddb, native.ptr(q_fold), native.ptr(db_fold), int(fold_sorted),
-                int(idx_base), int(k), prec, keys.data_ptr(), ws_ptr, ws_bytes, self._stream()))
-        self.launches += 2
+                native.ptr(q.f32), _ld(q.f32) if q.f32 is not None else 0,
+                native.ptr(q.hi), native.ptr(q.lo), _ld(q.hi) if q.hi is not None else 0,
+                native.ptr(db.f32), _ld(db.f32) if db.f32 is not None else 0,
+                native.ptr(db.hi), native.ptr(db.lo), _ld(db.hi) if db.hi is not None else 0,
+                Q, N, D, native.ptr(q_fold), native.ptr(db_fold), int(fold_sorted),
+                int(idx_base), int(k), prec, native.ptr(q.stats), native.ptr(db.stats),
+                keys.data_ptr(), native.ptr(status), ws_ptr, ws_bytes, self._stream()))
+        self.launches += 2 if status is None else 6
+        if status is not None:
+            self._status_log.append(status)
         return keys
+
+    def consume_status(self) -> Tuple[int, bool]:
+        """(number of queries the rescore bound could not verify -- they were re-searched exactly --,
+        overflow of the re-scan list) over all rescore searches since the last call.  Synchronises."""
+        if not self._status_log:
+            return 0, False
+        st = torch.stack(self._status_log).cpu().numpy()
+        self._status_log = []
+        return int(st[:, 0].sum()), bool(st[:, 1].any())
 
     # --------------------------------------------------------------------- K3
     def topk_merge(self, parts: torch.Tensor, k_out: int) -> torch.Tensor:
@@ -315,6 +346,13 @@ class Engine:
         keys = self.topk_search(qs, db, k, prec, q_fold=q_fold, db_fold=db_fold)
         res = self.vote_metrics(keys, db_labels, q_labels, n_classes, k_list=k_list, wacc_f32=wacc_f32,
                                 q_group=q_group, n_groups=n_groups, want_lists=want_lists)
+        if prec == "rescore":
+            unverified, overflow = self.consume_status()
+            if overflow:      # more unverifiable queries than the exact re-scan list holds: take the 3-pass arm
+                return self.search_and_vote(db_segs, q_segs, db_labels, q_labels, n_classes, k, db_weights, q_weights,
+                                            db_flags, q_flags, k_list, "bf16x3", wacc_f32, q_fold, db_fold, q_group,
+                                            n_groups, want_lists)
+            res["unverified"] = unverified
         res["keys"] = keys
         res["precision"] = prec
         return res
@@ -374,6 +412,11 @@ class Engine:
             freed[sl].record(compute)
             n_chunks += 1
         keys = parts[0] if n_chunks == 1 else self.topk_merge(torch.stack(parts), k)
+        if prec == "rescore":
+            _, overflow = self.consume_status()
+            if overflow:
+                return self.search_and_vote_host(db_segs_host, q_segs_host, db_labels, q_labels, n_classes, k, db_flags,
+                                                 q_flags, q_weights, k_list, "bf16x3", chunk_rows, row_offset, reduce_fn)
         if reduce_fn is not None:
             keys = reduce_fn(keys)
         db_labels = as_host(db_labels)

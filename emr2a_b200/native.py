@@ -16,9 +16,9 @@ LIB_PATH = os.path.join(PKG, "libemr2a.so")
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_WORKSPACE = 0, 1, 2, 3, 4
 F32, BF16 = 0, 1
 NF_SEGNORM, NF_ROWNORM, NF_ZERO_GUARD = 1, 2, 4
-PREC_FP32, PREC_BF16X3, PREC_BF16X1 = 0, 1, 2
+PREC_FP32, PREC_BF16X3, PREC_BF16X1, PREC_BF16_RESCORE = 0, 1, 2, 3
 SCORE_NONE, SCORE_ZSCORE, SCORE_MINMAX = 0, 1, 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _p = C.c_void_p
 _i64 = C.c_int64
@@ -31,14 +31,14 @@ _SIGNATURES = {
     "emr2a_last_error": (C.c_char_p, []),
     "emr2a_device_check": (_int, [C.POINTER(_int), C.POINTER(_int), C.POINTER(_int)]),
     "emr2a_normalize_fuse": (_int, [_p, _p, _i64, _int, _int, _i64, _i64, _f, _f, _int, _int,
-                                    _p, _i64, _p, _p, _i64, _p, _p]),
+                                    _p, _i64, _p, _p, _i64, _p, _p, _p]),
     "emr2a_scores": (_int, [_p, _p, _i64, _i64, _int, _i64, _i64, _p, _i64, _p]),
     "emr2a_euclid_workspace_bytes": (_sz, [_i64]),
     "emr2a_euclid_scores": (_int, [_p, _p, _i64, _int, _i64, _p, _p, _sz, _p]),
     "emr2a_late_fuse_scores": (_int, [_p, _p, _i64, _i64, _i64, _f, _f, _int, _p, _i64, _p]),
     "emr2a_topk_search_workspace_bytes": (_sz, [_i64, _i64, _int, _int, _int]),
-    "emr2a_topk_search": (_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _int, _i64, _i64, _p, _p, _int,
-                                 _i64, _int, _int, _p, _p, _sz, _p]),
+    "emr2a_topk_search": (_int, [_p, _i64, _p, _p, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _int, _p, _p, _int,
+                                 _i64, _int, _int, _p, _p, _p, _p, _p, _sz, _p]),
     "emr2a_topk_merge": (_int, [_p, _int, _i64, _int, _i64, _i64, _int, _p, _p]),
     "emr2a_vote_metrics": (_int, [_p, _i64, _int, _p, _i64, _p, _p, _int, _int, C.POINTER(C.c_int32), _int, _int,
                                   _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
@@ -67,6 +67,13 @@ def load(check_device: bool = False) -> C.CDLL:
     ``python -m emr2a_b200.build``).  Raises if it is absent -- never falls back."""
     global _lib
     if _lib is None:
+        if os.environ.get("EMR2A_NO_AUTOBUILD") != "1":
+            try:            # rebuild when a CUDA source changed since the library was linked (no-op otherwise)
+                from . import build as _build
+                _build.build()
+            except Exception as exc:  # pragma: no cover - nvcc missing: use what is there, or fail below
+                if not os.path.exists(LIB_PATH):
+                    raise ImportError(f"libemr2a.so is missing and could not be built: {exc}") from exc
         if not os.path.exists(LIB_PATH):
             raise ImportError(
                 f"{LIB_PATH} not found: build it with `python -m emr2a_b200.build` "

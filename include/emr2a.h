@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define EMR2A_ABI_VERSION 3
+#define EMR2A_ABI_VERSION 4
 
 enum emr2a_status {
   EMR2A_OK = 0,
@@ -58,7 +58,11 @@ enum emr2a_nf_flags {
 enum emr2a_precision {
   EMR2A_PREC_FP32 = 0,      /* fp32 FMA on CUDA cores: exact-order reference arithmetic, any shape */
   EMR2A_PREC_BF16X3 = 1,    /* tcgen05 bf16 tensor cores, 2-way split (hi*hi + hi*lo + lo*hi), fp32 accumulate: |err| ~ 1e-6 */
-  EMR2A_PREC_BF16X1 = 2     /* tcgen05 bf16 tensor cores, hi plane only (bf16-input variant), fp32 accumulate */
+  EMR2A_PREC_BF16X1 = 2,    /* tcgen05 bf16 tensor cores, hi plane only (bf16-input variant), fp32 accumulate */
+  EMR2A_PREC_BF16_RESCORE = 3 /* 1-pass bf16 tensor-core FILTER keeping K' = 32 candidates per query, exact fp32
+                                 re-scoring of the candidates from the fp32 rows, selection verified against a rigorous
+                                 error bound; unverifiable queries are re-searched exactly (fp32).  K <= 10.
+                                 Scores are fp32 dot products (|err| ~ 1e-7), about 2.4x faster than BF16X3. */
 };
 
 /* score normalisation modes of emr2a_late_fuse_scores (retrieval/fusion.py:31-42) */
@@ -90,12 +94,15 @@ int emr2a_device_check(int* sm_count, int* cc_major, int* cc_minor);
  *   out_hi / out_lo [n, ld_bf16]  bf16 planes for the tensor-core search:
  *            hi = bf16(out), lo = bf16(out - hi); columns [d0+d1, ld_bf16) are zero-filled
  *   inv_norm_out [n]       1 / (||row|| + 1e-8) of the final division (1.0 without ROWNORM)
+ *   stats_out [2]          running maxima over the rows (atomic max; zero it before the first call):
+ *                          [0] = max ||out row||, [1] = max ||out row - bf16(out row)||; needs out_hi.
+ *                          Input of the EMR2A_PREC_BF16_RESCORE error bound.
  */
 int emr2a_normalize_fuse(const void* seg0, const void* seg1, int64_t n, int d0, int d1,
                          int64_t ld0, int64_t ld1, float w0, float w1, int flags, int in_dtype,
                          float* out_f32, int64_t ld_f32,
                          uint16_t* out_hi, uint16_t* out_lo, int64_t ld_bf16,
-                         float* inv_norm_out, void* stream);
+                         float* inv_norm_out, float* stats_out, void* stream);
 
 /*
  * Full score matrix out[q, j] = <q_q, db_j> in fp32 (CUDA cores), for the API
@@ -128,24 +135,35 @@ int emr2a_late_fuse_scores(const float* text_scores, const float* image_scores, 
  *
  * Operands are the rows K1 produced (weights and inverse norms already folded
  * in, so score = plain dot product):
- *   EMR2A_PREC_FP32   : q_f32 [Q, ldq], db_f32 [N, lddb]
- *   EMR2A_PREC_BF16X3 : q_hi,q_lo [Q, ldq] and db_hi,db_lo [N, lddb] (bf16 bits; ld % 64 == 0, zero padded)
- *   EMR2A_PREC_BF16X1 : q_hi, db_hi only
- * q_fold / db_fold (uint8, nullable together): a pair with equal fold ids is
+ *   EMR2A_PREC_FP32         : q_f32 [Q, ldq_f32], db_f32 [N, lddb_f32]
+ *   EMR2A_PREC_BF16X3       : q_hi,q_lo [Q, ldq_bf16] and db_hi,db_lo [N, lddb_bf16]
+ *                             (bf16 bits; ld >= round_up(D,64), ld % 8 == 0, zero padded, 16-byte aligned)
+ *   EMR2A_PREC_BF16X1       : q_hi, db_hi only
+ *   EMR2A_PREC_BF16_RESCORE : q_hi, db_hi AND q_f32, db_f32, plus q_stats / db_stats (the float[2] K1
+ *                             wrote for each side) and status_out
+ * q_fold / db_fold (uint8 0..254, nullable together): a pair with equal fold ids is
  * excluded -- the CV rule that a case is never retrieved from its own fold
  * (utils/cv_evaluator.py:349-376).  `fold_sorted` != 0 promises both fold
  * vectors are non-decreasing so whole tiles of a single fold can be skipped.
  * idx_base is added to the local row number (row-sharded databases).
  * out_keys [Q, K]: packed keys, best first; slots beyond the number of
  * admissible rows are 0.
+ * status_out (int32[4], nullable except for BF16_RESCORE; zero it before the call):
+ *   [0] number of queries whose selection the error bound could not verify (they were re-searched
+ *       exactly), [1] != 0: more such queries than the re-scan list holds (min(Q,1024)) -- the caller
+ *       must repeat the call with EMR2A_PREC_BF16X3 or EMR2A_PREC_FP32.
  */
 size_t emr2a_topk_search_workspace_bytes(int64_t Q, int64_t N, int D, int K, int precision);
-int emr2a_topk_search(const float* q_f32, const uint16_t* q_hi, const uint16_t* q_lo,
-                      const float* db_f32, const uint16_t* db_hi, const uint16_t* db_lo,
-                      int64_t Q, int64_t N, int D, int64_t ldq, int64_t lddb,
+int emr2a_topk_search(const float* q_f32, int64_t ldq_f32,
+                      const uint16_t* q_hi, const uint16_t* q_lo, int64_t ldq_bf16,
+                      const float* db_f32, int64_t lddb_f32,
+                      const uint16_t* db_hi, const uint16_t* db_lo, int64_t lddb_bf16,
+                      int64_t Q, int64_t N, int D,
                       const uint8_t* q_fold, const uint8_t* db_fold, int fold_sorted,
                       int64_t idx_base, int K, int precision,
-                      uint64_t* out_keys, void* workspace, size_t ws_bytes, void* stream);
+                      const float* q_stats, const float* db_stats,
+                      uint64_t* out_keys, int32_t* status_out,
+                      void* workspace, size_t ws_bytes, void* stream);
 
 /*
  * K3 -- merge `parts` sorted partial Top-K lists per query into one.

@@ -10,7 +10,7 @@ def main():
     eng = get_engine()
     dev = eng.device
     cfgs = [tuple(x) for x in json.loads(os.environ.get("SWEEP", '[[1000000,1024,10000]]'))]
-    arms = os.environ.get("ARMS", "bf16x3:10,bf16x1:10,bf16x1:32,bf16x1:5").split(",")
+    arms = os.environ.get("ARMS", "bf16x3:10,rescore:10,rescore:5,bf16x1:10").split(",")
     for (n, d, q) in cfgs:
         db, _ = synth.device_block(0, n, d, 3, 11, dev)
         qs, _ = synth.device_block(50_003_968, q, d, 3, 11, dev)
