@@ -46,7 +46,8 @@ struct TcPartials {
 int tc_topk_search(const uint16_t* q_hi, const uint16_t* q_lo, const uint16_t* db_hi, const uint16_t* db_lo,
                    int64_t Q, int64_t N, int D, int64_t ldq, int64_t lddb, const uint8_t* q_fold,
                    const uint8_t* db_fold, int64_t idx_base, int K, int passes, uint64_t* out_keys,
-                   void* workspace, size_t ws_bytes, float* debug_scores, cudaStream_t st, TcPartials* partials);
+                   void* workspace, size_t ws_bytes, float* debug_scores, cudaStream_t st, TcPartials* partials,
+                   int fold_sorted);
 
 size_t rescore_workspace_bytes(int64_t Q, int K);
 int rescore_pipeline(const uint64_t* approx, int KP, const uint32_t* tau, const float* q, int64_t ldq, const float* db,
@@ -101,7 +102,6 @@ static int topk_search_impl(const float* q_f32, int64_t ldq_f32, const uint16_t*
                             const uint8_t* q_fold, const uint8_t* db_fold, int fold_sorted, int64_t idx_base, int K,
                             int precision, const float* q_stats, const float* db_stats, uint64_t* out_keys,
                             int32_t* status, void* workspace, size_t ws_bytes, float* debug_scores, void* stream) {
-  (void)fold_sorted;   // tile skipping for sorted folds is a scheduling optimisation; results never depend on it
   if (Q < 0 || N < 0 || D <= 0 || K <= 0 || !out_keys) return fail(EMR2A_ERR_INVALID, "topk_search: bad arguments (Q=%lld N=%lld D=%d K=%d)", (long long)Q, (long long)N, D, K);
   if ((q_fold == nullptr) != (db_fold == nullptr)) return fail(EMR2A_ERR_INVALID, "topk_search: q_fold and db_fold must be given together");
   if (idx_base < 0) return fail(EMR2A_ERR_INVALID, "topk_search: negative idx_base");
@@ -119,9 +119,9 @@ static int topk_search_impl(const float* q_f32, int64_t ldq_f32, const uint16_t*
       if (ldq_f32 < D || lddb_f32 < D) return fail(EMR2A_ERR_INVALID, "topk_search(fp32): leading dimension smaller than D");
       return simt_topk_search(q_f32, db_f32, Q, N, D, ldq_f32, lddb_f32, q_fold, db_fold, idx_base, K, out_keys, workspace, ws_bytes, st);
     case EMR2A_PREC_BF16X3:
-      return tc_topk_search(q_hi, q_lo, db_hi, db_lo, Q, N, D, ldq_bf16, lddb_bf16, q_fold, db_fold, idx_base, K, 3, out_keys, workspace, ws_bytes, debug_scores, st, nullptr);
+      return tc_topk_search(q_hi, q_lo, db_hi, db_lo, Q, N, D, ldq_bf16, lddb_bf16, q_fold, db_fold, idx_base, K, 3, out_keys, workspace, ws_bytes, debug_scores, st, nullptr, fold_sorted);
     case EMR2A_PREC_BF16X1:
-      return tc_topk_search(q_hi, nullptr, db_hi, nullptr, Q, N, D, ldq_bf16, lddb_bf16, q_fold, db_fold, idx_base, K, 1, out_keys, workspace, ws_bytes, debug_scores, st, nullptr);
+      return tc_topk_search(q_hi, nullptr, db_hi, nullptr, Q, N, D, ldq_bf16, lddb_bf16, q_fold, db_fold, idx_base, K, 1, out_keys, workspace, ws_bytes, debug_scores, st, nullptr, fold_sorted);
     case EMR2A_PREC_BF16_RESCORE: {
       if (K > 10) return fail(EMR2A_ERR_UNSUPPORTED, "topk_search(rescore): K=%d > 10 (use EMR2A_PREC_BF16X3)", K);
       if (!q_f32 || !db_f32) return fail(EMR2A_ERR_INVALID, "topk_search(rescore): q_f32/db_f32 required");
@@ -135,7 +135,7 @@ static int topk_search_impl(const float* q_f32, int64_t ldq_f32, const uint16_t*
       uint64_t* approx = reinterpret_cast<uint64_t*>(ws);
       TcPartials parts{};
       int rc = tc_topk_search(q_hi, nullptr, db_hi, nullptr, Q, N, D, ldq_bf16, lddb_bf16, q_fold, db_fold, idx_base,
-                              RESCORE_KP, 1, nullptr, ws + a_bytes, t_bytes, debug_scores, st, &parts);
+                              RESCORE_KP, 1, nullptr, ws + a_bytes, t_bytes, debug_scores, st, &parts, fold_sorted);
       if (rc != EMR2A_OK) return rc;
       // several splits: re-score the 64 best approximate candidates of the query (rows outside the per-split
       // lists are bounded by tau); one split: its 32 candidates are all there is

@@ -37,6 +37,7 @@ struct TcParams {
   int64_t tiles_per_split;
   const uint8_t* q_fold;
   const uint8_t* db_fold;  // padded to n_tiles * 256 bytes
+  int fold_sorted;         // both fold vectors are non-decreasing: single-fold tiles of the query's own fold are skipped
   int64_t idx_base;
   int K;
   uint64_t* keys_out;      // [splits][Q][K]
@@ -157,6 +158,21 @@ __device__ __forceinline__ float select32(const float (&v)[32], int idx) {
   return (idx & 16) ? d1 : d0;
 }
 
+// CV rule at tile granularity (fold-sorted inputs): if every query of the tile is in fold f and every
+// database row of the tile is in fold f, all 128 x 256 pairs are inadmissible -- no TMA, no MMA, no epilogue.
+// The three warp roles evaluate the same predicate from the same global bytes.
+__device__ __forceinline__ int unit_fold(const TcParams& p, int64_t mt) {
+  if (!p.fold_sorted || p.q_fold == nullptr) return -1;
+  const int64_t a = mt * T_BM, b = (a + T_BM - 1 < p.Q) ? a + T_BM - 1 : p.Q - 1;
+  const int lo = __ldg(p.q_fold + a), hi = __ldg(p.q_fold + b);
+  return lo == hi ? lo : -1;
+}
+__device__ __forceinline__ bool tile_skipped(const TcParams& p, int ufold, int64_t t) {
+  if (ufold < 0) return false;
+  const int64_t a = t * T_BN, b = (a + T_BN - 1 < p.N) ? a + T_BN - 1 : p.N - 1;
+  return __ldg(p.db_fold + a) == ufold && __ldg(p.db_fold + b) == ufold;
+}
+
 template <int PASSES, int KCAP, bool HAS_FOLD>
 __global__ void __launch_bounds__(T_THREADS, 1)
 tc_topk_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo,
@@ -210,7 +226,9 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
         const int m0 = static_cast<int>(mt * T_BM);
         const int64_t t0 = split * p.tiles_per_split;
         const int64_t t1 = (t0 + p.tiles_per_split < p.n_tiles) ? t0 + p.tiles_per_split : p.n_tiles;
+        const int ufold = HAS_FOLD ? unit_fold(p, mt) : -1;
         for (int64_t t = t0; t < t1; ++t) {
+          if (HAS_FOLD && tile_skipped(p, ufold, t)) continue;
           const int n0 = static_cast<int>(t * T_BN);
           for (int kc = 0; kc < p.k_chunks; ++kc) {
             mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
@@ -237,7 +255,9 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
         const int64_t split = u / p.m_tiles;
         const int64_t t0 = split * p.tiles_per_split;
         const int64_t t1 = (t0 + p.tiles_per_split < p.n_tiles) ? t0 + p.tiles_per_split : p.n_tiles;
+        const int ufold = HAS_FOLD ? unit_fold(p, u - split * p.m_tiles) : -1;
         for (int64_t t = t0; t < t1; ++t) {
+          if (HAS_FOLD && tile_skipped(p, ufold, t)) continue;
           mbar_wait(smem_u32(&bar_tempty[acc]), acc_phase ^ 1u);
           tcgen05_fence_after();
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * T_BN);
@@ -292,7 +312,9 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
         if (t != 0u) thr0 = __uint_as_float(__float_as_uint(unorder_f32(t)) - ((unorder_f32(t) > 0.f) ? 1u : 0u) + ((unorder_f32(t) < 0.f) ? 1u : 0u));
       }
       float thr = thr0;
+      const int ufold = HAS_FOLD ? unit_fold(p, mt) : -1;
       for (int64_t t = t0; t < t1; ++t) {
+        if (HAS_FOLD && tile_skipped(p, ufold, t)) continue;
         const int64_t n0 = t * T_BN;
         mbar_wait(smem_u32(&bar_tfull[acc]), acc_phase);
         tcgen05_fence_after();
@@ -466,7 +488,7 @@ int tc_topk_search(const uint16_t* q_hi, const uint16_t* q_lo, const uint16_t* d
                    int64_t Q, int64_t N, int D, int64_t ldq, int64_t lddb,
                    const uint8_t* q_fold, const uint8_t* db_fold, int64_t idx_base, int K, int passes,
                    uint64_t* out_keys, void* workspace, size_t ws_bytes, float* debug_scores, cudaStream_t st,
-                   TcPartials* partials) {
+                   TcPartials* partials, int fold_sorted) {
   if (K > 32) return fail(EMR2A_ERR_UNSUPPORTED, "topk_search(bf16): K=%d > 32 (use EMR2A_PREC_FP32)", K);
   const int64_t Dp = (static_cast<int64_t>(D) + T_BK - 1) / T_BK * T_BK;
   if (ldq < Dp || lddb < Dp || (ldq % 8) || (lddb % 8))
@@ -510,7 +532,7 @@ int tc_topk_search(const uint16_t* q_hi, const uint16_t* q_lo, const uint16_t* d
     uint8_t* fpad = ws + fold_off;
     EMR2A_CUDA_TRY(cudaMemsetAsync(fpad, 0xFF, pl.fold_bytes, st));
     EMR2A_CUDA_TRY(cudaMemcpyAsync(fpad, db_fold, static_cast<size_t>(N), cudaMemcpyDeviceToDevice, st));
-    p.q_fold = q_fold; p.db_fold = fpad;
+    p.q_fold = q_fold; p.db_fold = fpad; p.fold_sorted = fold_sorted;
   }
   const int kcap = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
   if (passes == 3) {

@@ -55,22 +55,28 @@ def sharded_search_and_vote(eng, db_segs_local: Sequence, q_segs: Sequence, db_l
     keys = eng.topk_search(qs, db, k, prec, q_fold=q_fold, db_fold=db_fold_local, idx_base=row_offset)
     if timers is not None:
         timers["k2_end"].record()
-    if prec == "rescore":
-        unverified, overflow = eng.consume_status()
-        flag = torch.tensor([int(overflow)], device=keys.device, dtype=torch.int32)
-        if world > 1:
-            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-        if int(flag.item()):          # some rank could not verify within its re-scan capacity: all ranks take the 3-pass arm
-            return sharded_search_and_vote(eng, db_segs_local, q_segs, db_labels_global, q_labels, n_classes, k,
-                                           row_offset, db_flags, q_flags, q_weights, k_list, "bf16x3", q_fold,
-                                           db_fold_local, q_group, n_groups, want_lists, timers)
+    # optimistic execution: the rescore status (did any rank overflow its exact re-scan list?) travels
+    # with the keys in the same all-gather and is only looked at after the vote, so the step has a
+    # single host synchronisation at its very end
+    status = eng.pop_status_tensor() if prec == "rescore" else None
     if world > 1:
-        allk = gather_keys(keys)
+        payload = keys.reshape(-1)
+        if status is not None:
+            payload = torch.cat([payload, status.to(torch.int64)])
+        allp = gather_keys(payload.unsqueeze(0)).squeeze(1)              # [world, Q*K (+4)]
+        allk = allp[:, :keys.numel()].reshape(world, *keys.shape)
+        if status is not None:
+            status = allp[:, keys.numel():].to(torch.int32).max(dim=0).values
         keys = eng.topk_merge(allk, k)
     res = eng.vote_metrics(keys, db_labels_global, q_labels, n_classes, k_list=k_list, q_group=q_group,
                            n_groups=n_groups, want_lists=want_lists)
     res["keys"] = keys
     res["precision"] = prec
-    if prec == "rescore":
-        res["unverified"] = unverified
+    if status is not None:
+        st = status.cpu()
+        if int(st[1]):            # some rank could not verify within its re-scan capacity: redo with the 3-pass arm
+            return sharded_search_and_vote(eng, db_segs_local, q_segs, db_labels_global, q_labels, n_classes, k,
+                                           row_offset, db_flags, q_flags, q_weights, k_list, "bf16x3", q_fold,
+                                           db_fold_local, q_group, n_groups, want_lists, timers)
+        res["unverified"] = int(st[0])
     return res

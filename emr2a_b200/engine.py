@@ -265,6 +265,15 @@ class Engine:
             self._status_log.append(status)
         return keys
 
+    def pop_status_tensor(self) -> Optional[torch.Tensor]:
+        """Device-side status (int32[4], element-wise max over the pending rescore searches) without a
+        host synchronisation; the caller decides when to look at it."""
+        if not self._status_log:
+            return None
+        st = torch.stack(self._status_log)
+        self._status_log = []
+        return torch.stack([st[:, 0].sum(), st[:, 1].max(), st[:, 2].max(), st[:, 3].max()]).to(torch.int32)
+
     def consume_status(self) -> Tuple[int, bool]:
         """(number of queries the rescore bound could not verify -- they were re-searched exactly --,
         overflow of the re-scan list) over all rescore searches since the last call.  Synchronises."""
@@ -347,7 +356,7 @@ class Engine:
         res = self.vote_metrics(keys, db_labels, q_labels, n_classes, k_list=k_list, wacc_f32=wacc_f32,
                                 q_group=q_group, n_groups=n_groups, want_lists=want_lists)
         if prec == "rescore":
-            unverified, overflow = self.consume_status()
+            unverified, overflow = self.consume_status()      # the step's only host sync, after all work is queued
             if overflow:      # more unverifiable queries than the exact re-scan list holds: take the 3-pass arm
                 return self.search_and_vote(db_segs, q_segs, db_labels, q_labels, n_classes, k, db_weights, q_weights,
                                             db_flags, q_flags, k_list, "bf16x3", wacc_f32, q_fold, db_fold, q_group,
@@ -357,6 +366,83 @@ class Engine:
         res["precision"] = prec
         return res
 
+
+    # ------------------------------------------------- all folds at once (CV)
+    @staticmethod
+    def _rows(op: "Operand", lo: int, hi: int) -> "Operand":
+        """View of rows [lo, hi) of a prepared operand (no copy)."""
+        cut = lambda t: None if t is None else t[lo:hi]          # noqa: E731
+        return Operand(n=hi - lo, dim=op.dim, f32=cut(op.f32), hi=cut(op.hi), lo=cut(op.lo),
+                       inv_norm=cut(op.inv_norm), stats=op.stats)
+
+    def cv_search_and_vote(self, segs: Sequence, labels, folds, n_classes: int, k: int,
+                           flags: int = native.NF_ROWNORM, q_weights=(1.0, 1.0),
+                           k_list: Sequence[int] = (1, 3, 5), precision: str = "auto",
+                           n_folds: Optional[int] = None, q_block: int = 1 << 20,
+                           want_lists: bool = True) -> Dict[str, torch.Tensor]:
+        """The whole CV loop in one pass: every row is a query against the rows of the OTHER folds
+        (utils/cv_evaluator.py:349-376 builds exactly these train/test pairs, one fold at a time).
+        Rows are brought into fold order so the search can skip whole tiles of the query's own fold;
+        indices and per-query outputs are mapped back to the caller's row order.  Counters are
+        per fold (``hit_counts[f]``, ``vote_counts[f]``, ``confusion[f]``, ``group_sizes[f]``).
+        Equals the reference's per-fold evaluation whenever the preprocessing does not depend on
+        the fold (the rows passed in are the processed embeddings)."""
+        folds_t = self.to_device(folds, torch.uint8)
+        n = int(folds_t.shape[0])
+        if n_folds is None:
+            n_folds = int(folds_t.max().item()) + 1 if n else 1
+        labels_t = self.to_device(labels, torch.int32)
+        mats = [self._embedding(x)[0] for x in segs if x is not None]
+        in_order = bool((folds_t[1:] >= folds_t[:-1]).all().item()) if n > 1 else True
+        perm = None
+        if not in_order:
+            perm = torch.argsort(folds_t.to(torch.int16), stable=True)
+            mats = [m.index_select(0, perm) for m in mats]
+            labels_t = labels_t.index_select(0, perm)
+            folds_t = folds_t.index_select(0, perm)
+        dim = sum(int(m.shape[1]) for m in mats)
+        prec = self.pick_precision(n, n, dim, k, precision)
+        seg1 = mats[1] if len(mats) > 1 else None
+        db = self.prepare(mats[0], seg1, 1.0, 1.0, flags, prec)
+        same_q = float(q_weights[0]) == 1.0 and float(q_weights[1]) == 1.0
+        qs_all = db if same_q else self.prepare(mats[0], seg1, q_weights[0], q_weights[1], flags, prec)
+        outs: List[Dict[str, torch.Tensor]] = []
+        unverified = 0
+        for lo in range(0, n, q_block):
+            hi = min(lo + q_block, n)
+            keys = self.topk_search(self._rows(qs_all, lo, hi), db, k, prec, q_fold=folds_t[lo:hi], db_fold=folds_t,
+                                    fold_sorted=True)
+            r = self.vote_metrics(keys, labels_t, labels_t[lo:hi], n_classes, k_list=k_list, q_group=folds_t[lo:hi],
+                                  n_groups=n_folds, want_lists=want_lists)
+            r["keys"] = keys
+            outs.append(r)
+            if prec == "rescore":
+                u, overflow = self.consume_status()
+                if overflow:
+                    return self.cv_search_and_vote(segs, labels, folds, n_classes, k, flags, q_weights, k_list,
+                                                   "bf16x3", n_folds, q_block, want_lists)
+                unverified += u
+        res: Dict[str, torch.Tensor] = {}
+        for name in ("hit_counts", "vote_counts", "confusion", "group_sizes"):
+            res[name] = torch.stack([o[name] for o in outs]).sum(dim=0)
+        per_query = [nm for nm in ("keys", "top_idx", "top_scores", "top_labels", "pred_top1", "pred_vote", "pred_weighted")
+                     if nm in outs[0]]
+        for name in per_query:
+            res[name] = torch.cat([o[name] for o in outs])
+        if perm is not None:                                   # back to the caller's row order / row numbers
+            if "top_idx" in res:
+                ti = res["top_idx"]
+                res["top_idx"] = torch.where(ti >= 0, perm[ti.clamp(min=0)], ti)
+            for name in per_query:
+                if name == "keys":
+                    continue
+                out = torch.empty_like(res[name])
+                out[perm] = res[name]
+                res[name] = out
+            res.pop("keys", None)                              # packed keys carry fold-order indices: not exported
+        res["precision"] = prec
+        res["unverified"] = unverified
+        return res
 
     # ----------------------------------------------- host-buffer (end-to-end) path
     def search_and_vote_host(self, db_segs_host: Sequence, q_segs_host: Sequence, db_labels, q_labels,

@@ -265,6 +265,80 @@ class CVRetrievalEvaluator:
                         f"Weighted Acc={res['weighted_vote_acc']:.4f}")
         return {"fold_results": fold_results, "summary": self._compute_summary(fold_results)}
 
+    def run_cv_processed(self, patient_ids: List[str], labels: List[str], image: Optional[np.ndarray],
+                         text: Optional[np.ndarray], fusion: str = "concat", top_k_list: Optional[List[int]] = None,
+                         w_text: float = 0.5, lists: bool = True) -> Dict:
+        """Array fast path of ``run_cv`` for embeddings that are ALREADY processed (unit rows; no per-fold
+        scaler/PCA): the same StratifiedKFold split, then all folds in ONE fold-masked GPU pass
+        (``Engine.cv_search_and_vote``) instead of one database upload + search per fold.  Returns the
+        same ``{"fold_results": [...], "summary": {...}}`` structure; with ``lists=False`` the per-sample
+        python lists (``all_top_*``) are left out (at 10M cases they dwarf the GPU time)."""
+        if top_k_list is None:
+            top_k_list = [1, 3, 5, self.top_k]
+        if fusion == "image_only":
+            if image is None:
+                raise ValueError("image_only fusion requires image embeddings")
+            segs, qw, flags = (image,), (1.0, 1.0), 0
+        elif fusion == "text_only":
+            if text is None:
+                raise ValueError("text_only fusion requires text embeddings")
+            segs, qw, flags = (text,), (1.0, 1.0), 0
+        elif fusion == "concat":
+            if image is None or text is None:
+                raise ValueError("concat fusion requires both image and text embeddings")
+            segs, qw, flags = (image, text), (1.0, 1.0), native.NF_ROWNORM
+        elif fusion == "late":
+            if image is None or text is None:
+                raise ValueError("late fusion requires both image and text embeddings")
+            segs, qw, flags = (image, text), (np.float32(1 - w_text), np.float32(w_text)), 0
+        else:
+            raise ValueError(f"Unknown fusion type: {fusion}")
+        n = len(labels)
+        folds = np.zeros(n, dtype=np.uint8)
+        skf = StratifiedKFold(n_splits=self.cv_folds, shuffle=True, random_state=self.seed)
+        members = []
+        for f, (_, te) in enumerate(skf.split(patient_ids, labels)):
+            folds[te] = f
+            members.append(te)
+        classes, (codes,) = encode(labels)
+        n_cls = len(classes)
+        eng = get_engine()
+        k_eff = max(1, min(int(self.top_k), n - max(len(m) for m in members)))
+        out = eng.cv_search_and_vote(segs, codes, folds, n_cls, k_eff, flags=flags, q_weights=qw,
+                                     k_list=[int(k) for k in top_k_list], n_folds=self.cv_folds, want_lists=lists)
+        hits = out["hit_counts"].cpu().numpy()
+        votes = out["vote_counts"].cpu().numpy()
+        conf = out["confusion"].cpu().numpy()
+        if lists:
+            idx_all = out["top_idx"].cpu().numpy()
+            sc_all = out["top_scores"].cpu().numpy()
+        ids_arr = np.asarray(patient_ids, dtype=object)
+        fold_results = []
+        for f, te in enumerate(members):
+            n_q = len(te)
+            r: Dict = {}
+            for j, k in enumerate(top_k_list):
+                r[f"top{k}"] = np.float64(hits[f, j]) / np.float64(n_q)
+            r["vote_acc"] = int(votes[f, 1]) / n_q
+            r["weighted_vote_acc"] = int(votes[f, 2]) / n_q
+            prf = prf_from_confusion(conf[f, 1], classes)
+            r["macro_precision"] = np.mean([v["precision"] for v in prf.values()])
+            r["macro_recall"] = np.mean([v["recall"] for v in prf.values()])
+            r["macro_f1"] = np.mean([v["f1"] for v in prf.values()])
+            r["confusion_matrix_top1"] = confusion_dict(conf[f, 0], classes)
+            r["confusion_matrix_vote"] = confusion_dict(conf[f, 1], classes)
+            if lists:
+                idx = idx_all[te]
+                valid = (idx >= 0).sum(axis=1)
+                r["all_top_labels"] = gather_lists(labels, idx, valid)
+                r["all_top_scores"] = score_lists(sc_all[te], valid)
+                r["all_top_patient_ids"] = gather_lists(patient_ids, idx, valid)
+            r["test_patient_ids"] = ids_arr[te].tolist()
+            r["fold"] = f + 1
+            r["train_ids"] = ids_arr[np.setdiff1d(np.arange(n), te)].tolist() if lists else []
+            fold_results.append(r)
+        return {"fold_results": fold_results, "summary": self._compute_summary(fold_results)}
+
     def _compute_summary(self, all_results: List[Dict]) -> Dict:
         """mean / std / min / max over folds of the 8 fixed metrics (utils/cv_evaluator.py:391-405)."""
         summary = {}

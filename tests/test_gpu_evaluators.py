@@ -206,3 +206,35 @@ def test_dropin_packages_resolve_to_b200_implementation():
     lines = out.stdout.strip().splitlines()
     assert lines[-2] == "emr2a_b200.retrieval.evaluator emr2a_b200.utils.cv_evaluator"
     assert abs(float(lines[-1]) - 1.0) < 1e-6
+
+
+def test_run_cv_processed_equals_fold_by_fold(oracle):
+    """The one-pass, fold-masked CV (run_cv_processed) against the reference-shaped fold loop
+    (evaluate_processed_fold on each StratifiedKFold split) and the oracle for one fold."""
+    from sklearn.model_selection import StratifiedKFold
+    from emr2a_b200 import synth
+    from emr2a_b200.utils.cv_evaluator import CVRetrievalEvaluator
+    data = synth.two_modal(2000, 64, 48, 3, seed=5, sep=0.3)
+    img, txt = oracle.unit_rows(data["image"]), oracle.unit_rows(data["text"])
+    labels = _names(data["labels"])
+    ids = synth.patient_ids(2000)
+    ev = CVRetrievalEvaluator(top_k=5)
+    for fusion, w in (("concat", 0.5), ("late", 0.3), ("image_only", 0.5)):
+        fast = ev.run_cv_processed(ids, labels, img, txt, fusion=fusion, top_k_list=[1, 3, 5, 5], w_text=w)
+        skf = StratifiedKFold(5, shuffle=True, random_state=42)
+        for f, (tr, te) in enumerate(skf.split(ids, labels)):
+            slow = ev.evaluate_processed_fold(img[tr], txt[tr], img[te], txt[te], [labels[j] for j in tr],
+                                              [labels[j] for j in te], [ids[j] for j in te], fusion=fusion,
+                                              top_k_list=[1, 3, 5, 5], w_text=w, train_ids=[ids[j] for j in tr])
+            fr = fast["fold_results"][f]
+            assert fr["test_patient_ids"] == slow["test_patient_ids"] and fr["fold"] == f + 1
+            assert np.max(np.abs(np.array(fr["all_top_scores"]) - np.array(slow["all_top_scores"]))) < 2e-6
+            gaps = np.abs(np.diff(np.array(slow["all_top_scores"]), axis=1)).min(axis=1) > 4e-6
+            same = np.array([a == b for a, b in zip(fr["all_top_patient_ids"], slow["all_top_patient_ids"])])
+            assert same[gaps].all()
+            if same.all():
+                for key in ("top1", "top3", "top5", "vote_acc", "weighted_vote_acc", "macro_precision", "macro_recall",
+                            "macro_f1", "confusion_matrix_top1", "confusion_matrix_vote"):
+                    assert fr[key] == slow[key], (fusion, f, key)
+        assert set(fast["summary"]) == {"top1", "top3", "top5", "vote_acc", "weighted_vote_acc", "macro_precision",
+                                        "macro_recall", "macro_f1"}

@@ -351,3 +351,103 @@ def test_errors_are_loud(eng):
         eng.topk_search(eng.prepare(np.ones((2, 8), np.float32)), eng.prepare(np.ones((2, 16), np.float32)), 1)
     rc = eng.lib.emr2a_scores(None, None, 1, 1, 4, 4, 4, None, 1, None)
     assert rc == native.ERR_INVALID and "scores" in native.last_error()
+
+
+# ------------------------------------------------------------------ CV rule at scale / other BASELINE configs
+@pytest.mark.parametrize("prec", ["bf16x3", "rescore", "fp32"])
+def test_fold_sorted_tile_skipping(eng, oracle, prec):
+    """Every row a query, rows in fold order, fold_sorted=1: whole 128x256 tiles of the query's own fold
+    are skipped in the tcgen05 kernel -- results must equal the element-masked search."""
+    import torch
+    rng = np.random.default_rng(31)
+    N, D, K = 6400, 128, 5
+    db = oracle.unit_rows(rng.standard_normal((N, D)).astype(np.float32))
+    fold = np.sort(rng.integers(0, 5, N)).astype(np.uint8)
+    op = eng.prepare(db, flags=0, precision=prec)
+    f = torch.from_numpy(fold)
+    keys = eng.topk_search(op, op, K, prec, q_fold=f, db_fold=f, fold_sorted=True)
+    eng.consume_status()
+    _check_topk(oracle, keys, db, db, K, q_fold=fold, db_fold=fold, tol=SCORE_TOL if prec == "bf16x3" else F32_TOL)
+    keys2 = eng.topk_search(op, op, K, prec, q_fold=f, db_fold=f, fold_sorted=False)
+    eng.consume_status()
+    assert torch.equal(keys, keys2)
+
+
+@pytest.mark.parametrize("prec", ["rescore", "bf16x3"])
+def test_cv_all_folds_engine_path(eng, oracle, prec):
+    """Engine.cv_search_and_vote with UNSORTED folds: rows are permuted into fold order internally and
+    everything is mapped back; compare with the oracle's masked search + votes, per fold counters."""
+    rng = np.random.default_rng(77)
+    N, D, K, C = 5000, 96, 5, 3
+    img = oracle.unit_rows(rng.standard_normal((N, D)).astype(np.float32))
+    txt = oracle.unit_rows(rng.standard_normal((N, D)).astype(np.float32))
+    labels = rng.integers(0, C, N).astype(np.int32)
+    fold = rng.integers(0, 5, N).astype(np.uint8)
+    from emr2a_b200 import native
+    r = eng.cv_search_and_vote((img, txt), labels, fold, C, K, flags=native.NF_ROWNORM, k_list=[1, 3, 5],
+                               precision=prec, n_folds=5, q_block=2048)
+    fused = oracle.fuse_concat_cv(img, txt)
+    o_idx, o_sc = oracle.search_topk_batched(fused, fused, K, q_fold=fold, db_fold=fold)
+    got_idx, got_sc = _np(r["top_idx"]), _np(r["top_scores"])
+    tol = SCORE_TOL if prec == "bf16x3" else F32_TOL
+    assert np.max(np.abs(got_sc - o_sc)) < tol
+    safe = np.abs(np.diff(o_sc, axis=1)).min(axis=1) > 2 * tol
+    assert safe.mean() > 0.9 and np.array_equal(got_idx[safe], o_idx[safe])
+    assert np.all(fold[got_idx] != fold[:, None])                       # never retrieved from the own fold
+    maj = np.array([oracle.vote_majority([int(x) for x in labels[row]]) for row in o_idx])
+    assert np.array_equal(_np(r["pred_vote"])[safe], maj[safe])
+    for f in range(5):
+        m = fold == f
+        assert int(r["group_sizes"][f]) == int(m.sum())
+        if safe[m].all():
+            assert int(r["vote_counts"][f, 1]) == int((maj[m] == labels[m]).sum())
+            assert int(r["hit_counts"][f, 0]) == int((labels[o_idx[m, 0]] == labels[m]).sum())
+
+
+def test_c3_late_fusion_merge_then_topk(eng, oracle):
+    """BASELINE config C3 shape (512-d image + 512-d text, late fusion): the reference merges the two
+    score vectors of ALL rows and then ranks (utils/cv_evaluator.py:233-237); here the weights are
+    folded into the query rows and one contraction does both."""
+    rng = np.random.default_rng(13)
+    N, Q, D, K = 50_000, 512, 512, 10
+    for w in (0.25, 0.5):
+        di = oracle.unit_rows(rng.standard_normal((N, D)).astype(np.float32))
+        dt = oracle.unit_rows(rng.standard_normal((N, D)).astype(np.float32))
+        qi = oracle.unit_rows(rng.standard_normal((Q, D)).astype(np.float32))
+        qt = oracle.unit_rows(rng.standard_normal((Q, D)).astype(np.float32))
+        ref = w * (qt.astype(np.float64) @ dt.T.astype(np.float64)) + (1 - w) * (qi.astype(np.float64) @ di.T.astype(np.float64))
+        o_idx = np.argsort(-ref, axis=1, kind="stable")[:, :K]
+        o_sc = np.take_along_axis(ref, o_idx, axis=1)
+        from emr2a_b200.engine import unpack_keys
+        for prec in ("rescore", "bf16x3"):
+            db = eng.prepare(di, dt, 1.0, 1.0, 0, prec)
+            qs = eng.prepare(qi, qt, np.float32(1 - w), np.float32(w), 0, prec)
+            sc, idx = unpack_keys(eng.topk_search(qs, db, K, prec))
+            assert eng.consume_status() == (0, False)
+            tol = SCORE_TOL if prec == "bf16x3" else F32_TOL
+            assert np.max(np.abs(sc - o_sc)) < tol
+            safe = np.abs(np.diff(np.sort(-ref, axis=1)[:, :K + 1], axis=1)).min(axis=1) > 2 * tol
+            assert safe.mean() > 0.7 and np.array_equal(idx[safe], o_idx[safe])
+
+
+def test_c4_bf16_inputs_wide_rows(eng, oracle):
+    """BASELINE config C4 shape: 4096-d image + 1024-d text, bf16 INPUTS, fp32 accumulation.  The oracle
+    consumes the bf16 values up-cast to fp32."""
+    import torch
+    from emr2a_b200 import native
+    from emr2a_b200.engine import unpack_keys
+    rng = np.random.default_rng(17)
+    N, Q, K = 12_000, 200, 5
+    to_bf16 = lambda a: torch.from_numpy(a).to(torch.bfloat16)                      # noqa: E731
+    di, dt = to_bf16(rng.standard_normal((N, 4096)).astype(np.float32)), to_bf16(rng.standard_normal((N, 1024)).astype(np.float32))
+    qi, qt = to_bf16(rng.standard_normal((Q, 4096)).astype(np.float32)), to_bf16(rng.standard_normal((Q, 1024)).astype(np.float32))
+    up = lambda t: t.float().numpy()                                                 # noqa: E731
+    odb = oracle.fuse_concat_cv(oracle.unit_rows(up(di)), oracle.unit_rows(up(dt)))
+    oq = oracle.fuse_concat_cv(oracle.unit_rows(up(qi)), oracle.unit_rows(up(qt)))
+    flags = native.NF_SEGNORM | native.NF_ROWNORM
+    for prec, tol in (("rescore", F32_TOL), ("bf16x3", SCORE_TOL), ("fp32", F32_TOL)):
+        db = eng.prepare(di.cuda(), dt.cuda(), 1.0, 1.0, flags, prec)
+        qs = eng.prepare(qi.cuda(), qt.cuda(), 1.0, 1.0, flags, prec)
+        keys = eng.topk_search(qs, db, K, prec)
+        eng.consume_status()
+        _check_topk(oracle, keys, oq, odb, K, tol=tol)
