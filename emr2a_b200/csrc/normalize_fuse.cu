@@ -29,13 +29,11 @@ struct NfParams {
   float* stats;     // [0] = max row norm, [1] = max ||row - bf16(row)||  (atomic max on the float bits)
 };
 
-__device__ __forceinline__ void stats_update(float* stats, float norm2, float res2) {
-  // non-negative floats order like their bit patterns; read first so that the (quickly saturating)
-  // running maxima cost an atomic only when they actually grow
+__device__ __forceinline__ void stats_flush(float* stats, float max_norm2, float max_res2) {
+  // one atomic pair per warp at the end of the kernel; non-negative floats order like their bit patterns
   unsigned int* u = reinterpret_cast<unsigned int*>(stats);
-  const unsigned int a = __float_as_uint(__fsqrt_ru(norm2)), b = __float_as_uint(__fsqrt_ru(res2));
-  if (a > __ldcg(u)) atomicMax(u, a);
-  if (b > __ldcg(u + 1)) atomicMax(u + 1, b);
+  atomicMax(u, __float_as_uint(__fsqrt_ru(max_norm2)));
+  atomicMax(u + 1, __float_as_uint(__fsqrt_ru(max_res2)));
 }
 
 template <typename InT> struct Loader;
@@ -89,28 +87,45 @@ __device__ __forceinline__ void mul4(float4& a, float w) { a.x *= w; a.y *= w; a
 
 // Register-cached path: every lane keeps MAXC chunks of 4 elements.
 template <typename InT, int MAXC>
-__global__ void __launch_bounds__(256) normalize_fuse_vec_kernel(const NfParams p) {
+__device__ __forceinline__ void load_row(const NfParams& p, int64_t row, int lane, int c0, int ctot, float4 (&v)[MAXC]) {
+#pragma unroll
+  for (int j = 0; j < MAXC; ++j) {
+    const int c = lane + 32 * j;
+    if (c < c0) v[j] = Loader<InT>::load4(p.seg0, row * p.ld0 + 4 * c);
+    else if (c < ctot) v[j] = Loader<InT>::load4(p.seg1, row * p.ld1 + 4 * (c - c0));
+    else v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+template <typename InT, int MAXC, bool WANT_LO, bool STATS>
+__global__ void __launch_bounds__(256, (MAXC <= 8 ? 2 : 1)) normalize_fuse_vec_kernel(const NfParams p) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   const int c0 = p.d0 >> 2;
   const int ctot = (p.d0 + p.d1) >> 2;
   const int cpad = p.out_hi ? static_cast<int>(p.ld_bf16 >> 2) : ctot;
+  constexpr bool PREFETCH = MAXC <= 8;      // next row's loads are in flight while this row is processed
+  float max_n2 = 0.f, max_r2 = 0.f;
+
+  float4 nxt[PREFETCH ? MAXC : 1];
+  if (PREFETCH && warp0 < p.n) load_row<InT, MAXC>(p, warp0, lane, c0, ctot, reinterpret_cast<float4 (&)[MAXC]>(nxt));
 
   for (int64_t row = warp0; row < p.n; row += nwarps) {
     float4 v[MAXC];
-    float ss0 = 0.f, ss1 = 0.f;
+    if (PREFETCH) {
 #pragma unroll
-    for (int j = 0; j < MAXC; ++j) {
-      const int c = lane + 32 * j;
-      if (c < c0) {
-        v[j] = Loader<InT>::load4(p.seg0, row * p.ld0 + 4 * c);
-        ss0 += sq4(v[j]);
-      } else if (c < ctot) {
-        v[j] = Loader<InT>::load4(p.seg1, row * p.ld1 + 4 * (c - c0));
-        ss1 += sq4(v[j]);
-      } else {
-        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < MAXC; ++j) v[j] = nxt[PREFETCH ? j : 0];
+      if (row + nwarps < p.n) load_row<InT, MAXC>(p, row + nwarps, lane, c0, ctot, reinterpret_cast<float4 (&)[MAXC]>(nxt));
+    } else {
+      load_row<InT, MAXC>(p, row, lane, c0, ctot, v);
+    }
+    float ss0 = 0.f, ss1 = 0.f;
+    if (p.flags & EMR2A_NF_SEGNORM) {
+#pragma unroll
+      for (int j = 0; j < MAXC; ++j) {
+        const int c = lane + 32 * j;
+        if (c < c0) ss0 += sq4(v[j]); else ss1 += sq4(v[j]);
       }
     }
     if (p.flags & EMR2A_NF_SEGNORM) {
@@ -158,31 +173,37 @@ __global__ void __launch_bounds__(256) normalize_fuse_vec_kernel(const NfParams 
       for (int j = 0; j < MAXC; ++j) {
         const int c = lane + 32 * j;
         if (c < cpad) {
-          uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
-          split_bf16(v[j].x, h0, l0); split_bf16(v[j].y, h1, l1);
-          split_bf16(v[j].z, h2, l2); split_bf16(v[j].w, h3, l3);
-          if (p.stats) {
-            n2 += sq4(v[j]);
-            const float e0 = v[j].x - __uint_as_float(static_cast<uint32_t>(h0) << 16);
-            const float e1 = v[j].y - __uint_as_float(static_cast<uint32_t>(h1) << 16);
-            const float e2 = v[j].z - __uint_as_float(static_cast<uint32_t>(h2) << 16);
-            const float e3 = v[j].w - __uint_as_float(static_cast<uint32_t>(h3) << 16);
-            r2 += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
-          }
-          uint2 hv = make_uint2(h0 | (static_cast<uint32_t>(h1) << 16), h2 | (static_cast<uint32_t>(h3) << 16));
-          *reinterpret_cast<uint2*>(p.out_hi + row * p.ld_bf16 + 4 * c) = hv;
-          if (p.out_lo) {
-            uint2 lv = make_uint2(l0 | (static_cast<uint32_t>(l1) << 16), l2 | (static_cast<uint32_t>(l3) << 16));
-            *reinterpret_cast<uint2*>(p.out_lo + row * p.ld_bf16 + 4 * c) = lv;
+          // packed conversion: one cvt.rn.bf16x2.f32 per pair
+          const __nv_bfloat162 h01 = __floats2bfloat162_rn(v[j].x, v[j].y);
+          const __nv_bfloat162 h23 = __floats2bfloat162_rn(v[j].z, v[j].w);
+          const uint32_t u01 = *reinterpret_cast<const uint32_t*>(&h01);
+          const uint32_t u23 = *reinterpret_cast<const uint32_t*>(&h23);
+          *reinterpret_cast<uint2*>(p.out_hi + row * p.ld_bf16 + 4 * c) = make_uint2(u01, u23);
+          if (WANT_LO || STATS) {
+            const float e0 = v[j].x - __uint_as_float(u01 << 16);
+            const float e1 = v[j].y - __uint_as_float(u01 & 0xFFFF0000u);
+            const float e2 = v[j].z - __uint_as_float(u23 << 16);
+            const float e3 = v[j].w - __uint_as_float(u23 & 0xFFFF0000u);
+            if (STATS) {
+              n2 += sq4(v[j]);
+              r2 += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+            }
+            if (WANT_LO) {
+              const __nv_bfloat162 l01 = __floats2bfloat162_rn(e0, e1);
+              const __nv_bfloat162 l23 = __floats2bfloat162_rn(e2, e3);
+              *reinterpret_cast<uint2*>(p.out_lo + row * p.ld_bf16 + 4 * c) =
+                  make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+            }
           }
         }
       }
-      if (p.stats) {
-        n2 = warp_sum(n2); r2 = warp_sum(r2);
-        if (lane == 0) stats_update(p.stats, n2, r2);
+      if (STATS) {
+        max_n2 = fmaxf(max_n2, warp_sum(n2));
+        max_r2 = fmaxf(max_r2, warp_sum(r2));
       }
     }
   }
+  if (STATS && lane == 0 && warp0 < p.n) stats_flush(p.stats, max_n2, max_r2);
 }
 
 // Generic path (any d0/d1/alignment): scalar loads, the row is re-read through L1/L2.
@@ -193,6 +214,7 @@ __global__ void __launch_bounds__(256) normalize_fuse_scalar_kernel(const NfPara
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   const int dtot = p.d0 + p.d1;
   const bool segnorm = (p.flags & EMR2A_NF_SEGNORM) != 0;
+  float max_n2 = 0.f, max_r2 = 0.f;
   for (int64_t row = warp0; row < p.n; row += nwarps) {
     float n0 = 1.f, n1 = 1.f;
     if (segnorm) {
@@ -246,10 +268,20 @@ __global__ void __launch_bounds__(256) normalize_fuse_scalar_kernel(const NfPara
       }
     }
     if (p.stats && p.out_hi) {
-      n2 = warp_sum(n2); r2 = warp_sum(r2);
-      if (lane == 0) stats_update(p.stats, n2, r2);
+      max_n2 = fmaxf(max_n2, warp_sum(n2));
+      max_r2 = fmaxf(max_r2, warp_sum(r2));
     }
   }
+  if (p.stats && p.out_hi && lane == 0 && warp0 < p.n) stats_flush(p.stats, max_n2, max_r2);
+}
+
+template <typename InT, int MAXC>
+static void launch_vec(const NfParams& p, unsigned blocks, int threads, cudaStream_t st) {
+  const bool lo = p.out_lo != nullptr, stats = p.stats != nullptr;
+  if (lo && stats) normalize_fuse_vec_kernel<InT, MAXC, true, true><<<blocks, threads, 0, st>>>(p);
+  else if (lo) normalize_fuse_vec_kernel<InT, MAXC, true, false><<<blocks, threads, 0, st>>>(p);
+  else if (stats) normalize_fuse_vec_kernel<InT, MAXC, false, true><<<blocks, threads, 0, st>>>(p);
+  else normalize_fuse_vec_kernel<InT, MAXC, false, false><<<blocks, threads, 0, st>>>(p);
 }
 
 template <typename InT>
@@ -262,20 +294,15 @@ static int launch_nf(const NfParams& p, bool vec_ok, cudaStream_t st) {
   const int cmax = cpad > ctot ? cpad : ctot;
   int64_t blocks = (warps_needed + 7) / 8;
   if (vec_ok && cmax <= 32 * 48) {
-    // grid: a multiple of the SM count; resident CTAs per SM depend on the register footprint
-    if (cmax <= 32 * 4) {
-      int64_t cap = static_cast<int64_t>(sms) * 8; if (blocks > cap) blocks = cap;
-      normalize_fuse_vec_kernel<InT, 4><<<static_cast<unsigned>(blocks), threads, 0, st>>>(p);
-    } else if (cmax <= 32 * 8) {
-      int64_t cap = static_cast<int64_t>(sms) * 6; if (blocks > cap) blocks = cap;
-      normalize_fuse_vec_kernel<InT, 8><<<static_cast<unsigned>(blocks), threads, 0, st>>>(p);
-    } else if (cmax <= 32 * 16) {
-      int64_t cap = static_cast<int64_t>(sms) * 3; if (blocks > cap) blocks = cap;
-      normalize_fuse_vec_kernel<InT, 16><<<static_cast<unsigned>(blocks), threads, 0, st>>>(p);
-    } else {
-      int64_t cap = static_cast<int64_t>(sms) * 1; if (blocks > cap) blocks = cap;
-      normalize_fuse_vec_kernel<InT, 48><<<static_cast<unsigned>(blocks), threads, 0, st>>>(p);
-    }
+    // persistent grid-stride grid: a multiple of the SM count (resident CTAs per SM follow the register footprint)
+    int per_sm = cmax <= 32 * 8 ? 2 : 1;
+    const int64_t cap = static_cast<int64_t>(sms) * per_sm;
+    if (blocks > cap) blocks = cap;
+    const unsigned g = static_cast<unsigned>(blocks);
+    if (cmax <= 32 * 4) launch_vec<InT, 4>(p, g, threads, st);
+    else if (cmax <= 32 * 8) launch_vec<InT, 8>(p, g, threads, st);
+    else if (cmax <= 32 * 16) launch_vec<InT, 16>(p, g, threads, st);
+    else launch_vec<InT, 48>(p, g, threads, st);
   } else {
     int64_t cap = static_cast<int64_t>(sms) * 8; if (blocks > cap) blocks = cap;
     normalize_fuse_scalar_kernel<InT><<<static_cast<unsigned>(blocks), threads, 0, st>>>(p);
