@@ -37,6 +37,8 @@ WORKLOADS = {
     "c2": (1_000_000, 512, 512, 10_000, 10, 3, 11),
     "c2k5": (1_000_000, 512, 512, 10_000, 5, 3, 11),
     "small": (100_000, 256, 256, 2_048, 10, 3, 11),
+    # BASELINE.json configs[4]: every case is a query against the other folds (n_q == n_db); multi-GPU workload
+    "c5": (int(os.environ.get("EMR2A_C5_N", 10_000_000)), 512, 512, -1, 5, 3, 19),
 }
 
 
@@ -186,10 +188,122 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_c5(args):
+    """BASELINE.json configs[4]: N-case 1024-d fused database, EVERY case a query, 5-fold CV rule (a case
+    is never retrieved from its own fold), K=5, database row-sharded over the ranks.  Rows are in fold
+    order (fold = contiguous fifths of the synthetic, label-shuffled rows).  Per step and rank: K1 on the
+    shard; for every query block (broadcast from the rank that owns those rows): K1, fold-masked K2 against
+    the local shard (whole own-fold tiles skipped), all-gather of the local Top-K, K3 merge, K4 vote with
+    per-fold counters."""
+    import torch
+    import torch.distributed as dist
+    from emr2a_b200 import native, synth
+    from emr2a_b200.dist import gather_keys, shard_range
+    from emr2a_b200.engine import get_engine
+
+    world = int(os.environ.get("WORLD_SIZE", 1)); rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank); dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    eng = get_engine(dev)
+    n, d_img, d_txt, _, k, n_cls, seed = WORKLOADS["c5"]
+    n_folds, dim = 5, d_img + d_txt
+    q_block = int(os.environ.get("EMR2A_C5_QBLOCK", 262144))
+    lo, hi = shard_range(n, rank, world)
+    flags = native.NF_SEGNORM | native.NF_ROWNORM
+    db_img, _ = synth.device_block(lo, hi - lo, d_img, n_cls, seed, dev, label_seed=seed)
+    db_txt, _ = synth.device_block(lo, hi - lo, d_txt, n_cls, seed + 1, dev, label_seed=seed)
+    labels = synth.device_labels(0, n, n_cls, seed, dev)
+    fold = (torch.arange(n, device=dev, dtype=torch.int64) * n_folds // n).to(torch.uint8)
+    prec = args.precision
+    spans = [shard_range(n, r, world) for r in range(world)]
+    torch.cuda.synchronize()
+
+    def step():
+        db = eng.prepare(db_img, db_txt, 1.0, 1.0, flags, prec)
+        hits = votes = sizes = None
+        unverified = 0
+        for owner, (slo, shi) in enumerate(spans):
+            for b0 in range(slo, shi, q_block):
+                b1 = min(b0 + q_block, shi)
+                if owner == rank:
+                    qi, qt = db_img[b0 - lo:b1 - lo], db_txt[b0 - lo:b1 - lo]
+                else:
+                    qi = torch.empty((b1 - b0, d_img), dtype=torch.float32, device=dev)
+                    qt = torch.empty((b1 - b0, d_txt), dtype=torch.float32, device=dev)
+                if world > 1:
+                    dist.broadcast(qi, src=owner); dist.broadcast(qt, src=owner)
+                qs = eng.prepare(qi, qt, 1.0, 1.0, flags, prec)
+                keys = eng.topk_search(qs, db, k, prec, q_fold=fold[b0:b1], db_fold=fold[lo:hi], fold_sorted=True, idx_base=lo)
+                if world > 1:
+                    keys = eng.topk_merge(gather_keys(keys), k)
+                r = eng.vote_metrics(keys, labels, labels[b0:b1], n_cls, k_list=[1, 3, 5], q_group=fold[b0:b1],
+                                     n_groups=n_folds, per_query=False, want_lists=False)
+                hits = r["hit_counts"] if hits is None else hits + r["hit_counts"]
+                votes = r["vote_counts"] if votes is None else votes + r["vote_counts"]
+                sizes = r["group_sizes"] if sizes is None else sizes + r["group_sizes"]
+        if prec == "rescore":
+            unverified, overflow = eng.consume_status()
+            if overflow:
+                raise RuntimeError("rescore re-scan list overflowed on this workload; run with --precision bf16x3")
+        return hits, votes, sizes, unverified
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(1, min(args.warmup, 1))):
+        out = step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = max(1, args.steps)
+    e0.record()
+    for _ in range(steps):
+        out = step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0]) / steps
+    clocks = sampler.stop() if rank == 0 else None
+    hits, votes, sizes, unverified = out
+    if rank == 0:
+        pk = peaks()
+        pairs = float(n) * float(n) * (1.0 - 1.0 / n_folds)          # same-fold pairs are not counted
+        tf = 2.0 * dim * pairs / (ms / 1e3) / 1e12
+        line = {"metric": "queries/sec (cosine Top-K + vote)", "value": n / (ms / 1e3), "unit": "queries/s", "n_gpus": world,
+                "steps": steps, "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": prec, "data": "synthetic",
+                "config": {"workload": f"c5: {n}-case {dim}-d fused database, every case a query, {n_folds}-fold CV rule, K={k}",
+                           "parallelism": f"database row-sharded x{world}, query blocks of {q_block} broadcast from their owner, "
+                                          "NCCL all-gather of local Top-K", "l2": "inputs larger than L2"},
+                "clocks": clocks, "e2e": None, "gpu_launches": eng.launches - l0,
+                "roofline": {"bound": "tensor", "achieved": tf / world, "peak": pk["tflops"], "unit": "TFLOP/s per GPU",
+                             "frac": tf / world / pk["tflops"], "traffic": None,
+                             "note": "whole step (K1 + broadcasts + K2 + gather + K3 + K4) over admissible pairs only"},
+                "cpu_baseline": None, "unverified_queries": int(unverified),
+                "accuracy": {"top1": float(hits[:, 0].sum()) / n, "top5": float(hits[:, 2].sum()) / n,
+                             "vote_acc": float(votes[:, 1].sum()) / n,
+                             "per_fold_top1": [float(hits[f, 0]) / max(float(sizes[f]), 1.0) for f in range(n_folds)]}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "c5":
+        return run_c5(args)
 
     import torch
     import torch.distributed as dist

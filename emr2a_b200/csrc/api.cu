@@ -47,7 +47,8 @@ int tc_topk_search(const uint16_t* q_hi, const uint16_t* q_lo, const uint16_t* d
                    int64_t Q, int64_t N, int D, int64_t ldq, int64_t lddb, const uint8_t* q_fold,
                    const uint8_t* db_fold, int64_t idx_base, int K, int passes, uint64_t* out_keys,
                    void* workspace, size_t ws_bytes, float* debug_scores, cudaStream_t st, TcPartials* partials,
-                   int fold_sorted);
+                   int fold_sorted, int min_splits);
+int tc_planned_splits(int64_t Q, int64_t N, int min_splits);
 
 size_t rescore_workspace_bytes(int64_t Q, int K);
 int rescore_pipeline(const uint64_t* approx, int KP, const uint32_t* tau, const float* q, int64_t ldq, const float* db,
@@ -119,9 +120,9 @@ static int topk_search_impl(const float* q_f32, int64_t ldq_f32, const uint16_t*
       if (ldq_f32 < D || lddb_f32 < D) return fail(EMR2A_ERR_INVALID, "topk_search(fp32): leading dimension smaller than D");
       return simt_topk_search(q_f32, db_f32, Q, N, D, ldq_f32, lddb_f32, q_fold, db_fold, idx_base, K, out_keys, workspace, ws_bytes, st);
     case EMR2A_PREC_BF16X3:
-      return tc_topk_search(q_hi, q_lo, db_hi, db_lo, Q, N, D, ldq_bf16, lddb_bf16, q_fold, db_fold, idx_base, K, 3, out_keys, workspace, ws_bytes, debug_scores, st, nullptr, fold_sorted);
+      return tc_topk_search(q_hi, q_lo, db_hi, db_lo, Q, N, D, ldq_bf16, lddb_bf16, q_fold, db_fold, idx_base, K, 3, out_keys, workspace, ws_bytes, debug_scores, st, nullptr, fold_sorted, 1);
     case EMR2A_PREC_BF16X1:
-      return tc_topk_search(q_hi, nullptr, db_hi, nullptr, Q, N, D, ldq_bf16, lddb_bf16, q_fold, db_fold, idx_base, K, 1, out_keys, workspace, ws_bytes, debug_scores, st, nullptr, fold_sorted);
+      return tc_topk_search(q_hi, nullptr, db_hi, nullptr, Q, N, D, ldq_bf16, lddb_bf16, q_fold, db_fold, idx_base, K, 1, out_keys, workspace, ws_bytes, debug_scores, st, nullptr, fold_sorted, 1);
     case EMR2A_PREC_BF16_RESCORE: {
       if (K > 10) return fail(EMR2A_ERR_UNSUPPORTED, "topk_search(rescore): K=%d > 10 (use EMR2A_PREC_BF16X3)", K);
       if (!q_f32 || !db_f32) return fail(EMR2A_ERR_INVALID, "topk_search(rescore): q_f32/db_f32 required");
@@ -134,16 +135,20 @@ static int topk_search_impl(const float* q_f32, int64_t ldq_f32, const uint16_t*
       uint8_t* ws = static_cast<uint8_t*>(workspace);
       uint64_t* approx = reinterpret_cast<uint64_t*>(ws);
       TcPartials parts{};
+      // At least two splits so that 64 merged candidates back the verification; with >= 8 splits each
+      // split only keeps 16 (rows it drops are bounded by tau), which halves the epilogue's insertion work.
+      const int planned = tc_planned_splits(Q, N, 2);
+      const int kp = planned >= 8 ? 16 : RESCORE_KP;
       int rc = tc_topk_search(q_hi, nullptr, db_hi, nullptr, Q, N, D, ldq_bf16, lddb_bf16, q_fold, db_fold, idx_base,
-                              RESCORE_KP, 1, nullptr, ws + a_bytes, t_bytes, debug_scores, st, &parts, fold_sorted);
+                              kp, 1, nullptr, ws + a_bytes, t_bytes, debug_scores, st, &parts, fold_sorted, 2);
       if (rc != EMR2A_OK) return rc;
       // several splits: re-score the 64 best approximate candidates of the query (rows outside the per-split
       // lists are bounded by tau); one split: its 32 candidates are all there is
-      int kpm = RESCORE_KP;
+      int kpm = kp;
       const uint64_t* cand = parts.parts;
       if (parts.splits > 1) {
         kpm = RESCORE_KPM;
-        rc = emr2a_topk_merge(parts.parts, parts.splits, Q, RESCORE_KP, Q * RESCORE_KP, RESCORE_KP, kpm, approx, st);
+        rc = emr2a_topk_merge(parts.parts, parts.splits, Q, kp, Q * kp, kp, kpm, approx, st);
         if (rc != EMR2A_OK) return rc;
         cand = approx;
       }

@@ -236,6 +236,8 @@ extern "C" int emr2a_topk_merge(const uint64_t* keys_in, int parts, int64_t Q, i
   else if (total <= 128) topk_merge_reg_kernel<4><<<blocks, 256, 0, st>>>(keys_in, parts, Q, K_in, part_stride, q_stride, K_out, keys_out);
   else if (total <= 256) topk_merge_reg_kernel<8><<<blocks, 256, 0, st>>>(keys_in, parts, Q, K_in, part_stride, q_stride, K_out, keys_out);
   else if (total <= 512) topk_merge_reg_kernel<16><<<blocks, 256, 0, st>>>(keys_in, parts, Q, K_in, part_stride, q_stride, K_out, keys_out);
+  else if (total <= 1024) topk_merge_reg_kernel<32><<<blocks, 256, 0, st>>>(keys_in, parts, Q, K_in, part_stride, q_stride, K_out, keys_out);
+  else if (total <= 2048) topk_merge_reg_kernel<64><<<blocks, 256, 0, st>>>(keys_in, parts, Q, K_in, part_stride, q_stride, K_out, keys_out);
   else topk_merge_scan_kernel<<<blocks, 256, 0, st>>>(keys_in, parts, Q, K_in, part_stride, q_stride, K_out, keys_out);
   EMR2A_LAUNCH_CHECK("topk_merge kernel");
   return EMR2A_OK;

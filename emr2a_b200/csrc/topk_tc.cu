@@ -17,161 +17,10 @@
 // writing its list as packed keys to the partial-list workspace, merged afterwards by K3.
 //
 // Roofline: tensor pipe.  Algorithmic FLOPs = 2 * D * Q * N_admissible; BF16X3 issues 3x that.
-#include <cuda.h>
-#include "common.cuh"
+#include <stdlib.h>
+#include "tc_common.cuh"
 
 namespace emr2a {
-
-constexpr int T_BM = 128;
-constexpr int T_BN = 256;
-constexpr int T_BK = 64;
-constexpr int T_THREADS = 256;
-constexpr uint32_t T_A_BYTES = T_BM * T_BK * 2;   // 16 KB
-constexpr uint32_t T_B_BYTES = T_BN * T_BK * 2;   // 32 KB
-
-struct TcParams {
-  int64_t Q, N;
-  int k_chunks;            // ceil(D / 64)
-  int64_t m_tiles, n_tiles;
-  int splits;
-  int64_t tiles_per_split;
-  const uint8_t* q_fold;
-  const uint8_t* db_fold;  // padded to n_tiles * 256 bytes
-  int fold_sorted;         // both fold vectors are non-decreasing: single-fold tiles of the query's own fold are skipped
-  int64_t idx_base;
-  int K;
-  uint64_t* keys_out;      // [splits][Q][K]
-  uint32_t* tau;           // [Q] order-preserving image of a lower bound of the query's global KCAP-th best score
-  float* debug_scores;     // optional [Q][N] dump of every score (bring-up / tests)
-};
-
-// ---- PTX wrappers -------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {}
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);          // start address
-  d |= static_cast<uint64_t>(0) << 16;                              // leading byte offset (unused for swizzled K-major)
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;                      // stride byte offset: 8 rows * 128 B
-  d |= static_cast<uint64_t>(1) << 46;                              // descriptor version (sm_100)
-  d |= static_cast<uint64_t>(2) << 61;                              // SWIZZLE_128B
-  return d;
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// instruction descriptor: D=F32, A=B=BF16, both K-major, N=256, M=128
-constexpr uint32_t T_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((T_BN >> 3) << 17) | ((T_BM >> 4) << 24);
-
-// ---- register-resident sorted Top-K list ------------------------------------------------
-template <int KCAP>
-struct RegTopK {
-  float s[KCAP];
-  uint32_t i[KCAP];
-  __device__ __forceinline__ void reset() {
-#pragma unroll
-    for (int j = 0; j < KCAP; ++j) { s[j] = -INFINITY; i[j] = 0xFFFFFFFFu; }
-  }
-  __device__ __forceinline__ float threshold() const { return s[KCAP - 1]; }
-  // candidates reach a thread in ascending index order, so strict '>' keeps the lower index on ties
-  __device__ __forceinline__ void insert(float c, uint32_t ci) {
-#pragma unroll
-    for (int j = KCAP - 1; j > 0; --j) {
-      const bool up = c > s[j - 1];
-      const bool here = !up && (c > s[j]);
-      s[j] = up ? s[j - 1] : (here ? c : s[j]);
-      i[j] = up ? i[j - 1] : (here ? ci : i[j]);
-    }
-    const bool top = c > s[0];
-    s[0] = top ? c : s[0];
-    i[0] = top ? ci : i[0];
-  }
-};
-
-__device__ __forceinline__ float select32(const float (&v)[32], int idx) {
-  // 5-level select tree on the bits of idx (keeps v[] in registers)
-  float a[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) a[j] = (idx & 1) ? v[2 * j + 1] : v[2 * j];
-  float b[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) b[j] = (idx & 2) ? a[2 * j + 1] : a[2 * j];
-  float c[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) c[j] = (idx & 4) ? b[2 * j + 1] : b[2 * j];
-  const float d0 = (idx & 8) ? c[1] : c[0];
-  const float d1 = (idx & 8) ? c[3] : c[2];
-  return (idx & 16) ? d1 : d0;
-}
-
-// CV rule at tile granularity (fold-sorted inputs): if every query of the tile is in fold f and every
-// database row of the tile is in fold f, all 128 x 256 pairs are inadmissible -- no TMA, no MMA, no epilogue.
-// The three warp roles evaluate the same predicate from the same global bytes.
-__device__ __forceinline__ int unit_fold(const TcParams& p, int64_t mt) {
-  if (!p.fold_sorted || p.q_fold == nullptr) return -1;
-  const int64_t a = mt * T_BM, b = (a + T_BM - 1 < p.Q) ? a + T_BM - 1 : p.Q - 1;
-  const int lo = __ldg(p.q_fold + a), hi = __ldg(p.q_fold + b);
-  return lo == hi ? lo : -1;
-}
-__device__ __forceinline__ bool tile_skipped(const TcParams& p, int ufold, int64_t t) {
-  if (ufold < 0) return false;
-  const int64_t a = t * T_BN, b = (a + T_BN - 1 < p.N) ? a + T_BN - 1 : p.N - 1;
-  return __ldg(p.db_fold + a) == ufold && __ldg(p.db_fold + b) == ufold;
-}
 
 template <int PASSES, int KCAP, bool HAS_FOLD>
 __global__ void __launch_bounds__(T_THREADS, 1)
@@ -318,49 +167,9 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
         const int64_t n0 = t * T_BN;
         mbar_wait(smem_u32(&bar_tfull[acc]), acc_phase);
         tcgen05_fence_after();
-        const bool edge = (n0 + T_BN > p.N);
-#pragma unroll 1
-        for (int ch = 0; ch < T_BN / 32; ++ch) {
-          float v[32];
-          tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * T_BN + ch * 32), v);
-          const int64_t c0 = n0 + ch * 32;
-          if (p.debug_scores && q < p.Q) {
-#pragma unroll
-            for (int c = 0; c < 32; ++c) if (c0 + c < p.N) p.debug_scores[q * p.N + c0 + c] = v[c];
-          }
-          if (edge) {
-#pragma unroll
-            for (int c = 0; c < 32; ++c) if (c0 + c >= p.N) v[c] = -INFINITY;
-          }
-          if (HAS_FOLD) {
-            const uint4* fp = reinterpret_cast<const uint4*>(p.db_fold + c0);
-            const uint4 f0 = __ldg(fp), f1 = __ldg(fp + 1);
-            const uint32_t w[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const uint32_t f = (w[c >> 2] >> (8 * (c & 3))) & 0xFFu;
-              v[c] = (f == my_fold) ? -INFINITY : v[c];
-            }
-          }
-          float mx = v[0];
-#pragma unroll
-          for (int c = 1; c < 32; ++c) mx = fmaxf(mx, v[c]);
-          if (mx > thr) {
-            uint32_t mask = 0u;
-#pragma unroll
-            for (int c = 0; c < 32; ++c) mask |= (v[c] > thr) ? (1u << c) : 0u;
-            while (mask) {
-              const int c = __ffs(mask) - 1;
-              mask &= mask - 1u;
-              const float val = select32(v, c);
-              if (val > thr) {
-                top.insert(val, static_cast<uint32_t>(c0 + c + p.idx_base));
-                thr = fmaxf(top.threshold(), thr0);
-              }
-            }
-          }
-          __syncwarp();
-        }
+        scan_tile<KCAP, HAS_FOLD>(p, top, thr, thr0,
+                                  tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * T_BN),
+                                  n0, my_fold, q);
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[acc]));
@@ -429,15 +238,32 @@ struct TcPlan {
   size_t keys_bytes, fold_bytes, tau_bytes;
 };
 
-static TcPlan tc_plan(int64_t Q, int64_t N, int K, bool has_fold) {
+// CTA-pair kernel (topk_tc2.cu)
+int tc2_dispatch(int passes, int kcap, bool has_fold, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
+                 const CUtensorMap& d, const TcParams& p, int grid, cudaStream_t st);
+
+static bool use_cta_pairs() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EMR2A_TC2");         // EMR2A_TC2=0 selects the single-CTA kernel
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+static TcPlan tc_plan(int64_t Q, int64_t N, int K, bool has_fold, bool pairs, int min_splits = 1) {
   TcPlan pl{};
-  pl.m_tiles = (Q + T_BM - 1) / T_BM;
+  const int bm = pairs ? 2 * T_BM : T_BM;
+  pl.m_tiles = (Q + bm - 1) / bm;
   pl.n_tiles = (N + T_BN - 1) / T_BN;
-  const int sms = sm_count();
+  const int sms = pairs ? sm_count() / 2 : sm_count();      // concurrent workers: CTAs or CTA pairs
   // pick the split count whose unit count fills whole waves of CTAs best
   int best_s = 1; double best_eff = -1.0;
   const int64_t max_s = pl.n_tiles < 64 ? pl.n_tiles : 64;
-  for (int64_t s = 1; s <= max_s; ++s) {
+  int64_t first_s = min_splits < max_s ? min_splits : max_s;
+  if (first_s < 1) first_s = 1;
+  best_s = static_cast<int>(first_s);
+  for (int64_t s = first_s; s <= max_s; ++s) {
     const int64_t tps = (pl.n_tiles + s - 1) / s;
     const int64_t s_eff = (pl.n_tiles + tps - 1) / tps;       // splits that actually get tiles
     if (s_eff != s) continue;
@@ -452,16 +278,26 @@ static TcPlan tc_plan(int64_t Q, int64_t N, int K, bool has_fold) {
   pl.splits = best_s;
   pl.tiles_per_split = (pl.n_tiles + pl.splits - 1) / pl.splits;
   const int64_t units = pl.m_tiles * pl.splits;
-  pl.grid = static_cast<int>(units < sms ? units : sms);
+  pl.grid = static_cast<int>(units < sms ? units : sms) * (pairs ? 2 : 1);
   pl.keys_bytes = sizeof(uint64_t) * static_cast<size_t>(pl.splits) * Q * K;
   pl.fold_bytes = has_fold ? static_cast<size_t>(pl.n_tiles) * T_BN : 0;
   pl.tau_bytes = (sizeof(uint32_t) * static_cast<size_t>(Q) + 255) & ~static_cast<size_t>(255);
   return pl;
 }
 
+// number of database splits the search will use (the rescore arm sizes its candidate lists by it)
+int tc_planned_splits(int64_t Q, int64_t N, int min_splits) {
+  return tc_plan(Q, N, 1, false, use_cta_pairs(), min_splits).splits;
+}
+
 size_t tc_topk_workspace_bytes(int64_t Q, int64_t N, int K) {
-  TcPlan pl = tc_plan(Q, N, K, true);
-  return ((pl.keys_bytes + 255) & ~static_cast<size_t>(255)) + pl.fold_bytes + pl.tau_bytes + 512;
+  size_t need = 0;
+  for (int pairs = 0; pairs < 4; ++pairs) {
+    TcPlan pl = tc_plan(Q, N, K, true, (pairs & 1) != 0, (pairs & 2) ? 2 : 1);
+    const size_t b = ((pl.keys_bytes + 255) & ~static_cast<size_t>(255)) + pl.fold_bytes + pl.tau_bytes + 512;
+    need = b > need ? b : need;
+  }
+  return need;
 }
 
 template <int PASSES, int KCAP, bool HAS_FOLD>
@@ -488,7 +324,7 @@ int tc_topk_search(const uint16_t* q_hi, const uint16_t* q_lo, const uint16_t* d
                    int64_t Q, int64_t N, int D, int64_t ldq, int64_t lddb,
                    const uint8_t* q_fold, const uint8_t* db_fold, int64_t idx_base, int K, int passes,
                    uint64_t* out_keys, void* workspace, size_t ws_bytes, float* debug_scores, cudaStream_t st,
-                   TcPartials* partials, int fold_sorted) {
+                   TcPartials* partials, int fold_sorted, int min_splits) {
   if (K > 32) return fail(EMR2A_ERR_UNSUPPORTED, "topk_search(bf16): K=%d > 32 (use EMR2A_PREC_FP32)", K);
   const int64_t Dp = (static_cast<int64_t>(D) + T_BK - 1) / T_BK * T_BK;
   if (ldq < Dp || lddb < Dp || (ldq % 8) || (lddb % 8))
@@ -500,7 +336,8 @@ int tc_topk_search(const uint16_t* q_hi, const uint16_t* q_lo, const uint16_t* d
   if (Q >= (1LL << 31) || N >= (1LL << 31) - T_BN) return fail(EMR2A_ERR_UNSUPPORTED, "topk_search(bf16): Q/N too large for one call");
   if (N + idx_base >= 0xFFFFFFFFLL) return fail(EMR2A_ERR_UNSUPPORTED, "topk_search: global index exceeds 32 bits");
   const bool has_fold = q_fold != nullptr;
-  TcPlan pl = tc_plan(Q, N, K, has_fold);
+  const bool pairs = use_cta_pairs();
+  TcPlan pl = tc_plan(Q, N, K, has_fold, pairs, min_splits);
   const size_t keys_off = 0;
   const size_t fold_off = (pl.keys_bytes + 255) & ~static_cast<size_t>(255);
   const size_t tau_off = (fold_off + pl.fold_bytes + 255) & ~static_cast<size_t>(255);
@@ -512,10 +349,11 @@ int tc_topk_search(const uint16_t* q_hi, const uint16_t* q_lo, const uint16_t* d
   CUtensorMap mq_hi, mq_lo, md_hi, md_lo;
   int rc;
   if ((rc = make_plane_map(&mq_hi, q_hi, Q, Dp, ldq, T_BM)) != EMR2A_OK) return rc;
-  if ((rc = make_plane_map(&md_hi, db_hi, N, Dp, lddb, T_BN)) != EMR2A_OK) return rc;
+  const int db_box = pairs ? T_BN / 2 : T_BN;           // a CTA of a pair loads half of the database tile
+  if ((rc = make_plane_map(&md_hi, db_hi, N, Dp, lddb, db_box)) != EMR2A_OK) return rc;
   if (passes == 3) {
     if ((rc = make_plane_map(&mq_lo, q_lo, Q, Dp, ldq, T_BM)) != EMR2A_OK) return rc;
-    if ((rc = make_plane_map(&md_lo, db_lo, N, Dp, lddb, T_BN)) != EMR2A_OK) return rc;
+    if ((rc = make_plane_map(&md_lo, db_lo, N, Dp, lddb, db_box)) != EMR2A_OK) return rc;
   } else {
     mq_lo = mq_hi; md_lo = md_hi;
   }
@@ -535,7 +373,9 @@ int tc_topk_search(const uint16_t* q_hi, const uint16_t* q_lo, const uint16_t* d
     p.q_fold = q_fold; p.db_fold = fpad; p.fold_sorted = fold_sorted;
   }
   const int kcap = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
-  if (passes == 3) {
+  if (pairs) {
+    rc = tc2_dispatch(passes, kcap, has_fold, mq_hi, mq_lo, md_hi, md_lo, p, pl.grid, st);
+  } else if (passes == 3) {
     if (kcap == 8) rc = tc_launch_fold<3, 8>(has_fold, mq_hi, mq_lo, md_hi, md_lo, p, pl.grid, st);
     else if (kcap == 16) rc = tc_launch_fold<3, 16>(has_fold, mq_hi, mq_lo, md_hi, md_lo, p, pl.grid, st);
     else rc = tc_launch_fold<3, 32>(has_fold, mq_hi, mq_lo, md_hi, md_lo, p, pl.grid, st);
