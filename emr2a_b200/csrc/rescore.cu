@@ -71,6 +71,11 @@ __global__ void __launch_bounds__(256) rescore_select_kernel(const RescoreParams
   akey[1] = lane + 32 < p.KP ? p.approx[q * p.KP + lane + 32] : 0ull;
   const uint64_t last = __shfl_sync(0xffffffffu, p.KP > 32 ? akey[1] : akey[0], (p.KP - 1) & 31);
   const float* qrow = p.q + q * p.ldq;
+  // A candidate c with s~(c) + E < s~(K-th candidate) - E cannot be among the exact K best (the K best
+  // filter scores all have exact scores >= s~_K - E), so it is not re-scored: typically ~20 of 64 are.
+  const float E = error_bound(p.q_stats, p.db_stats);
+  const uint64_t kth_approx = __shfl_sync(0xffffffffu, akey[0], p.K - 1);
+  const float cut = kth_approx != 0ull ? key_score(kth_approx) - 2.0f * E : -INFINITY;
   bool done = false;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -78,7 +83,11 @@ __global__ void __launch_bounds__(256) rescore_select_kernel(const RescoreParams
       uint64_t kk[4];
       float acc[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) { kk[c] = __shfl_sync(0xffffffffu, akey[h], g + c); acc[c] = 0.f; }
+      for (int c = 0; c < 4; ++c) {
+        kk[c] = __shfl_sync(0xffffffffu, akey[h], g + c);
+        if (kk[c] != 0ull && key_score(kk[c]) < cut) kk[c] = 0ull;      // sorted by s~: everything after is below too
+        acc[c] = 0.f;
+      }
       if (kk[0] == 0ull) { done = true; break; }      // lists are packed: nothing valid beyond the first empty slot
       if (VEC) {
         for (int e = lane * 4; e < p.D; e += 128) {
@@ -137,7 +146,6 @@ __global__ void __launch_bounds__(256) rescore_select_kernel(const RescoreParams
   }
   if (bounded) {
     const uint64_t kth = __shfl_sync(0xffffffffu, mine, p.K - 1);
-    const float E = error_bound(p.q_stats, p.db_stats);
     const bool ok = kth != 0ull && key_score(kth) > tau + E;
     if (!ok && lane == 0) {
       const int i = atomicAdd(&p.status[0], 1);

@@ -40,7 +40,8 @@ def sharded_search_and_vote(eng, db_segs_local: Sequence, q_segs: Sequence, db_l
                             n_classes: int, k: int, row_offset: int, db_flags: int, q_flags: int,
                             q_weights=(1.0, 1.0), k_list=(1, 3, 5), precision: str = "auto",
                             q_fold=None, db_fold_local=None, q_group=None, n_groups: int = 1,
-                            want_lists: bool = True, timers: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+                            want_lists: bool = True, timers: Optional[dict] = None,
+                            defer_status: bool = False) -> Dict[str, torch.Tensor]:
     """Each rank: K1 on its database shard and on the (replicated) queries, local K2 with
     ``idx_base = row_offset``; all-gather keys; K3 merge; K4 vote on the merged lists."""
     n_q = int(q_segs[0].shape[0])
@@ -72,7 +73,9 @@ def sharded_search_and_vote(eng, db_segs_local: Sequence, q_segs: Sequence, db_l
                            n_groups=n_groups, want_lists=want_lists)
     res["keys"] = keys
     res["precision"] = prec
-    if status is not None:
+    if status is not None and defer_status:
+        res["status"] = status          # device int32[4]: the caller checks [1] == 0 (see Engine.check_deferred)
+    elif status is not None:
         st = status.cpu()
         if int(st[1]):            # some rank could not verify within its re-scan capacity: redo with the 3-pass arm
             return sharded_search_and_vote(eng, db_segs_local, q_segs, db_labels_global, q_labels, n_classes, k,

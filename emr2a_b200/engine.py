@@ -274,6 +274,14 @@ class Engine:
         self._status_log = []
         return torch.stack([st[:, 0].sum(), st[:, 1].max(), st[:, 2].max(), st[:, 3].max()]).to(torch.int32)
 
+    @staticmethod
+    def check_deferred(statuses: Sequence[torch.Tensor]) -> Tuple[int, bool]:
+        """Evaluate status tensors returned by calls made with ``defer_status=True`` (one sync for all)."""
+        if not statuses:
+            return 0, False
+        st = torch.stack(list(statuses)).cpu().numpy()
+        return int(st[:, 0].sum()), bool(st[:, 1].any())
+
     def consume_status(self) -> Tuple[int, bool]:
         """(number of queries the rescore bound could not verify -- they were re-searched exactly --,
         overflow of the re-scan list) over all rescore searches since the last call.  Synchronises."""
