@@ -78,7 +78,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -436,8 +436,8 @@ def main():
     roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tflops"], "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
                 "peak_source": pk["src"] + " (bf16 sustained)",
-                "kernel": "emr2a_topk_search = tc_topk_kernel (tcgen05) + K3 merge of partial lists"
-                          + (" + exact fp32 rescore of 32 candidates/query + (empty) re-scan" if res["precision"] == "rescore" else ""),
+                "kernel": "emr2a_topk_search = tc2_topk_kernel (tcgen05 cta_group::2, TMA, fused Top-K) + K3 merge of partial lists"
+                          + (" + exact fp32 rescore of <=64 candidates/query + (empty) re-scan" if res["precision"] == "rescore" else ""),
                 "kernel_ms": k2_avg_ms,
                 "issued_tflops": achieved * passes, "issued_frac": achieved * passes / pk["tflops"],
                 "share_of_step": k2_avg_ms / ms_per_step}
