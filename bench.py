@@ -37,6 +37,10 @@ WORKLOADS = {
     "c2": (1_000_000, 512, 512, 10_000, 10, 3, 11),
     "c2k5": (1_000_000, 512, 512, 10_000, 5, 3, 11),
     "small": (100_000, 256, 256, 2_048, 10, 3, 11),
+    # BASELINE.json configs[2]: late fusion (w_text*<T,T> + (1-w_text)*<I,I>, merge-then-Top-K), 5M cases
+    "c3": (5_000_000, 512, 512, 10_000, 10, 3, 13),
+    # BASELINE.json configs[3]: Qwen3-VL-shaped 4096-d image + 1024-d text, bf16 INPUTS, fp32 accumulation, 2M cases
+    "c4": (2_000_000, 4096, 1024, 10_000, 10, 3, 17),
     # BASELINE.json configs[4]: every case is a query against the other folds (n_q == n_db); multi-GPU workload
     "c5": (int(os.environ.get("EMR2A_C5_N", 10_000_000)), 512, 512, -1, 5, 3, 19),
 }
@@ -324,6 +328,14 @@ def main():
     dim = d_img + d_txt
     lo, hi = shard_range(n_db, rank, world)
     flags = native.NF_SEGNORM | native.NF_ROWNORM          # normalise each modality, concat, normalise (a12+a13)
+    q_weights = (1.0, 1.0)
+    in_dtype = torch.float32
+    if args.workload == "c3":                              # late fusion: unit modalities, weights folded into the queries
+        w_text = 0.25
+        flags = native.NF_SEGNORM
+        q_weights = (np.float32(1 - w_text), np.float32(w_text))
+    if args.workload == "c4":
+        in_dtype = torch.bfloat16
     k_list = [1, 3, 5, k]
 
     # ---- synthetic inputs, generated on the device (per shard; same rows for any N) ----
@@ -334,6 +346,8 @@ def main():
     q_row0 = 50_003_968
     q_img, q_labels = synth.device_block(q_row0, n_q, d_img, n_cls, seed, dev, label_seed=seed)
     q_txt, _ = synth.device_block(q_row0, n_q, d_txt, n_cls, seed + 1, dev, label_seed=seed)
+    if in_dtype != torch.float32:
+        db_img, db_txt, q_img, q_txt = (t.to(in_dtype) for t in (db_img, db_txt, q_img, q_txt))
     torch.cuda.synchronize()
 
     timers = {"k2_start": torch.cuda.Event(enable_timing=True), "k2_end": torch.cuda.Event(enable_timing=True)}
@@ -343,7 +357,7 @@ def main():
 
     def step(record_k2=False):
         r = sharded_search_and_vote(eng, (db_img, db_txt), (q_img, q_txt), db_labels, q_labels, n_cls, k,
-                                    row_offset=lo, db_flags=flags, q_flags=flags, k_list=k_list,
+                                    row_offset=lo, db_flags=flags, q_flags=flags, q_weights=q_weights, k_list=k_list,
                                     precision=args.precision, timers=timers if record_k2 else None,
                                     defer_status=True)
         if "status" in r:
@@ -401,8 +415,8 @@ def main():
 
         def e2e_step():
             return eng.search_and_vote_host((h_img, h_txt), (hq_img, hq_txt), h_lab, hq_lab, n_cls, k,
-                                            db_flags=flags, q_flags=flags, k_list=k_list, precision=args.precision,
-                                            row_offset=lo, reduce_fn=reduce_fn)
+                                            db_flags=flags, q_flags=flags, q_weights=q_weights, k_list=k_list,
+                                            precision=args.precision, row_offset=lo, reduce_fn=reduce_fn)
         for _ in range(2):
             out = e2e_step()
         barrier()
@@ -444,7 +458,7 @@ def main():
 
     # ---- CPU baseline + parity on the sample (rank 0, N = 1) ----
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload in ("c2", "c2k5", "small"):
         cpu, pick, ref = cpu_reference_leg(db_img.cpu().numpy(), db_txt.cpu().numpy(), q_img.cpu().numpy(),
                                            q_txt.cpu().numpy(), db_labels.cpu().numpy(), q_labels.cpu().numpy(),
                                            k, args.cpu_sample, n_q)
@@ -463,10 +477,12 @@ def main():
                 "dtype": {"bf16x3": "bf16x3 split (fp32-equivalent), fp32 accumulate", "bf16x1": "bf16, fp32 accumulate",
                           "fp32": "f32", "rescore": "bf16 tensor-core filter (fp32 accumulate) + exact f32 rescoring, verified"}[res["precision"]],
                 "data": "synthetic",
-                "config": {"workload": f"{args.workload}: {n_db}-case database, {d_img}+{d_txt}-d concat fusion (fp32 in), "
-                                       f"{n_q} queries, K={k}, {n_cls} classes",
+                "config": {"workload": f"{args.workload}: {n_db}-case database, {d_img}+{d_txt}-d "
+                                       + ("late fusion (w_text=0.25, merge-then-Top-K)" if args.workload == "c3" else "concat fusion")
+                                       + (" (bf16 in)" if in_dtype != torch.float32 else " (fp32 in)")
+                                       + f", {n_q} queries, K={k}, {n_cls} classes",
                            "parallelism": f"database row-sharded x{world}, NCCL all-gather of local Top-K" if world > 1 else "single GPU",
-                           "l2": "inputs (4.1 GB database) larger than L2; no flush needed",
+                           "l2": "inputs (multi-GB database) larger than L2; no flush needed",
                            "step": "K1 normalise+fuse (db shard + queries) -> K2 GEMM+Top-K -> K3 merge -> K4 vote"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                 "unverified_queries": int(unverified_total),

@@ -206,6 +206,127 @@ __global__ void __launch_bounds__(256, (MAXC <= 8 ? 2 : 1)) normalize_fuse_vec_k
   if (STATS && lane == 0 && warp0 < p.n) stats_flush(p.stats, max_n2, max_r2);
 }
 
+// Wide rows (D > 2048): one 256-thread block per row, CPT chunks of 4 elements per thread, block-wide
+// reductions through shared memory; the next row's loads are in flight while this one is processed.
+__device__ __forceinline__ float2 block_sum2(float a, float b, float2* red) {
+  a = warp_sum(a); b = warp_sum(b);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = make_float2(a, b);
+  __syncthreads();
+  float2 t = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int w = 0; w < 8; ++w) { t.x += red[w].x; t.y += red[w].y; }
+  __syncthreads();
+  return t;
+}
+
+template <typename InT, int CPT>
+__device__ __forceinline__ void load_row_block(const NfParams& p, int64_t row, int c0, int ctot, float4 (&v)[CPT]) {
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) {
+    const int c = threadIdx.x + 256 * j;
+    if (c < c0) v[j] = Loader<InT>::load4(p.seg0, row * p.ld0 + 4 * c);
+    else if (c < ctot) v[j] = Loader<InT>::load4(p.seg1, row * p.ld1 + 4 * (c - c0));
+    else v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+template <typename InT, int CPT>
+__global__ void __launch_bounds__(256, 2) normalize_fuse_block_kernel(const NfParams p) {
+  __shared__ float2 red[8];
+  const int c0 = p.d0 >> 2;
+  const int ctot = (p.d0 + p.d1) >> 2;
+  const int cpad = p.out_hi ? static_cast<int>(p.ld_bf16 >> 2) : ctot;
+  float max_n2 = 0.f, max_r2 = 0.f;
+  float4 nxt[CPT];
+  if (blockIdx.x < p.n) load_row_block<InT, CPT>(p, blockIdx.x, c0, ctot, nxt);
+  for (int64_t row = blockIdx.x; row < p.n; row += gridDim.x) {
+    float4 v[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) v[j] = nxt[j];
+    if (row + gridDim.x < p.n) load_row_block<InT, CPT>(p, row + gridDim.x, c0, ctot, nxt);
+    if (p.flags & EMR2A_NF_SEGNORM) {
+      float ss0 = 0.f, ss1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const int c = threadIdx.x + 256 * j;
+        if (c < c0) ss0 += sq4(v[j]); else ss1 += sq4(v[j]);
+      }
+      const float2 t = block_sum2(ss0, ss1, red);
+      const RowDiv n0 = row_div(__fsqrt_rn(t.x) + EMR2A_EPS);
+      const RowDiv n1 = row_div(__fsqrt_rn(t.y) + EMR2A_EPS);
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const int c = threadIdx.x + 256 * j;
+        if (c < c0) div4(v[j], n0); else if (c < ctot) div4(v[j], n1);
+      }
+    }
+    if (p.w0 != 1.0f || p.w1 != 1.0f) {
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const int c = threadIdx.x + 256 * j;
+        if (c < c0) mul4(v[j], p.w0); else if (c < ctot) mul4(v[j], p.w1);
+      }
+    }
+    float inv = 1.0f;
+    if (p.flags & (EMR2A_NF_ROWNORM | EMR2A_NF_ZERO_GUARD)) {
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) ss += sq4(v[j]);
+      float nrm = __fsqrt_rn(block_sum2(ss, 0.f, red).x);
+      const bool guard = (p.flags & EMR2A_NF_ZERO_GUARD) != 0;
+      if (!guard) nrm += EMR2A_EPS;
+      if (!(guard && nrm == 0.f)) {
+        const RowDiv dv = row_div(nrm);
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) div4(v[j], dv);
+        inv = dv.r;
+      }
+    }
+    if (p.inv_norm && threadIdx.x == 0) p.inv_norm[row] = inv;
+    if (p.out_f32) {
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const int c = threadIdx.x + 256 * j;
+        if (c < ctot) *reinterpret_cast<float4*>(p.out_f32 + row * p.ld_f32 + 4 * c) = v[j];
+      }
+    }
+    if (p.out_hi) {
+      float n2 = 0.f, r2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const int c = threadIdx.x + 256 * j;
+        if (c < cpad) {
+          const __nv_bfloat162 h01 = __floats2bfloat162_rn(v[j].x, v[j].y);
+          const __nv_bfloat162 h23 = __floats2bfloat162_rn(v[j].z, v[j].w);
+          const uint32_t u01 = *reinterpret_cast<const uint32_t*>(&h01);
+          const uint32_t u23 = *reinterpret_cast<const uint32_t*>(&h23);
+          *reinterpret_cast<uint2*>(p.out_hi + row * p.ld_bf16 + 4 * c) = make_uint2(u01, u23);
+          if (p.out_lo || p.stats) {
+            const float e0 = v[j].x - __uint_as_float(u01 << 16);
+            const float e1 = v[j].y - __uint_as_float(u01 & 0xFFFF0000u);
+            const float e2 = v[j].z - __uint_as_float(u23 << 16);
+            const float e3 = v[j].w - __uint_as_float(u23 & 0xFFFF0000u);
+            n2 += sq4(v[j]);
+            r2 += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+            if (p.out_lo) {
+              const __nv_bfloat162 l01 = __floats2bfloat162_rn(e0, e1);
+              const __nv_bfloat162 l23 = __floats2bfloat162_rn(e2, e3);
+              *reinterpret_cast<uint2*>(p.out_lo + row * p.ld_bf16 + 4 * c) =
+                  make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+            }
+          }
+        }
+      }
+      if (p.stats) {
+        const float2 t = block_sum2(n2, r2, red);
+        max_n2 = fmaxf(max_n2, t.x);
+        max_r2 = fmaxf(max_r2, t.y);
+      }
+    }
+  }
+  if (p.stats && threadIdx.x == 0 && blockIdx.x < p.n) stats_flush(p.stats, max_n2, max_r2);
+}
+
 // Generic path (any d0/d1/alignment): scalar loads, the row is re-read through L1/L2.
 template <typename InT>
 __global__ void __launch_bounds__(256) normalize_fuse_scalar_kernel(const NfParams p) {
@@ -293,7 +414,14 @@ static int launch_nf(const NfParams& p, bool vec_ok, cudaStream_t st) {
   const int cpad = p.out_hi ? static_cast<int>(p.ld_bf16 >> 2) : ctot;
   const int cmax = cpad > ctot ? cpad : ctot;
   int64_t blocks = (warps_needed + 7) / 8;
-  if (vec_ok && cmax <= 32 * 48) {
+  if (vec_ok && cmax > 32 * 16 && cmax <= 256 * 8) {
+    // wide rows: a block per row
+    int64_t g = p.n < static_cast<int64_t>(sms) * 2 ? p.n : static_cast<int64_t>(sms) * 2;
+    const unsigned gg = static_cast<unsigned>(g);
+    if (cmax <= 256 * 3) normalize_fuse_block_kernel<InT, 3><<<gg, threads, 0, st>>>(p);
+    else if (cmax <= 256 * 5) normalize_fuse_block_kernel<InT, 5><<<gg, threads, 0, st>>>(p);
+    else normalize_fuse_block_kernel<InT, 8><<<gg, threads, 0, st>>>(p);
+  } else if (vec_ok && cmax <= 32 * 48) {
     // persistent grid-stride grid: a multiple of the SM count (resident CTAs per SM follow the register footprint)
     int per_sm = cmax <= 32 * 8 ? 2 : 1;
     const int64_t cap = static_cast<int64_t>(sms) * per_sm;
