@@ -38,6 +38,11 @@ __device__ __forceinline__ void stats_flush(float* stats, float max_norm2, float
 
 template <typename InT> struct Loader;
 template <> struct Loader<float> {
+  typedef float4 Raw;
+  static __device__ __forceinline__ Raw load_raw(const void* base, int64_t elem) {
+    return ldg_stream_f4(reinterpret_cast<const float4*>(static_cast<const float*>(base) + elem));
+  }
+  static __device__ __forceinline__ float4 widen(const Raw& r) { return r; }
   static __device__ __forceinline__ float4 load4(const void* base, int64_t elem) {
     return ldg_stream_f4(reinterpret_cast<const float4*>(static_cast<const float*>(base) + elem));
   }
@@ -46,6 +51,18 @@ template <> struct Loader<float> {
   }
 };
 template <> struct Loader<__nv_bfloat16> {
+  typedef uint2 Raw;
+  static __device__ __forceinline__ Raw load_raw(const void* base, int64_t elem) {
+    return ldg_stream_u2(reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(base) + elem));
+  }
+  static __device__ __forceinline__ float4 widen(const Raw& r) {
+    float4 f;
+    f.x = __uint_as_float(r.x << 16);
+    f.y = __uint_as_float(r.x & 0xFFFF0000u);
+    f.z = __uint_as_float(r.y << 16);
+    f.w = __uint_as_float(r.y & 0xFFFF0000u);
+    return f;
+  }
   static __device__ __forceinline__ float4 load4(const void* base, int64_t elem) {
     uint2 r = ldg_stream_u2(reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(base) + elem));
     float4 f;
@@ -220,30 +237,47 @@ __device__ __forceinline__ float2 block_sum2(float a, float b, float2* red) {
 }
 
 template <typename InT, int CPT>
-__device__ __forceinline__ void load_row_block(const NfParams& p, int64_t row, int c0, int ctot, float4 (&v)[CPT]) {
+__device__ __forceinline__ void load_row_block(const NfParams& p, int64_t row, int c0, int ctot,
+                                               typename Loader<InT>::Raw (&v)[CPT]) {
 #pragma unroll
   for (int j = 0; j < CPT; ++j) {
     const int c = threadIdx.x + 256 * j;
-    if (c < c0) v[j] = Loader<InT>::load4(p.seg0, row * p.ld0 + 4 * c);
-    else if (c < ctot) v[j] = Loader<InT>::load4(p.seg1, row * p.ld1 + 4 * (c - c0));
-    else v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < c0) v[j] = Loader<InT>::load_raw(p.seg0, row * p.ld0 + 4 * c);
+    else if (c < ctot) v[j] = Loader<InT>::load_raw(p.seg1, row * p.ld1 + 4 * (c - c0));
   }
 }
 
 template <typename InT, int CPT>
 __global__ void __launch_bounds__(256, 2) normalize_fuse_block_kernel(const NfParams p) {
+  typedef typename Loader<InT>::Raw Raw;
+  // rows are prefetched UNCONVERTED; bf16 rows are half as many bytes, so two of them are kept in flight
+  constexpr int PF = sizeof(Raw) == 16 ? 1 : 2;
   __shared__ float2 red[8];
   const int c0 = p.d0 >> 2;
   const int ctot = (p.d0 + p.d1) >> 2;
   const int cpad = p.out_hi ? static_cast<int>(p.ld_bf16 >> 2) : ctot;
   float max_n2 = 0.f, max_r2 = 0.f;
-  float4 nxt[CPT];
-  if (blockIdx.x < p.n) load_row_block<InT, CPT>(p, blockIdx.x, c0, ctot, nxt);
-  for (int64_t row = blockIdx.x; row < p.n; row += gridDim.x) {
+  Raw ring[PF][CPT];
+#pragma unroll
+  for (int s = 0; s < PF; ++s) {
+    const int64_t r = blockIdx.x + static_cast<int64_t>(s) * gridDim.x;
+    if (r < p.n) load_row_block<InT, CPT>(p, r, c0, ctot, ring[s]);
+  }
+  for (int64_t base = blockIdx.x; base < p.n; base += static_cast<int64_t>(PF) * gridDim.x) {
+#pragma unroll
+   for (int s = 0; s < PF; ++s) {
+    const int64_t row = base + static_cast<int64_t>(s) * gridDim.x;
+    if (row >= p.n) break;
     float4 v[CPT];
 #pragma unroll
-    for (int j = 0; j < CPT; ++j) v[j] = nxt[j];
-    if (row + gridDim.x < p.n) load_row_block<InT, CPT>(p, row + gridDim.x, c0, ctot, nxt);
+    for (int j = 0; j < CPT; ++j) {
+      const int c = threadIdx.x + 256 * j;
+      v[j] = c < ctot ? Loader<InT>::widen(ring[s][j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    {
+      const int64_t r2 = row + static_cast<int64_t>(PF) * gridDim.x;
+      if (r2 < p.n) load_row_block<InT, CPT>(p, r2, c0, ctot, ring[s]);
+    }
     if (p.flags & EMR2A_NF_SEGNORM) {
       float ss0 = 0.f, ss1 = 0.f;
 #pragma unroll
@@ -323,6 +357,7 @@ __global__ void __launch_bounds__(256, 2) normalize_fuse_block_kernel(const NfPa
         max_r2 = fmaxf(max_r2, t.y);
       }
     }
+   }
   }
   if (p.stats && threadIdx.x == 0 && blockIdx.x < p.n) stats_flush(p.stats, max_n2, max_r2);
 }

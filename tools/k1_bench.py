@@ -6,14 +6,18 @@ from emr2a_b200 import native, synth
 from emr2a_b200.engine import get_engine
 eng = get_engine(); dev = eng.device
 n, d = int(os.environ.get("N", 1_000_000)), int(os.environ.get("D", 512))
-a, _ = synth.device_block(0, n, d, 3, 11, dev); b, _ = synth.device_block(0, n, d, 3, 12, dev)
+d2 = int(os.environ.get("D2", d))
+a, _ = synth.device_block(0, n, d, 3, 11, dev); b, _ = synth.device_block(0, n, d2, 3, 12, dev)
+isz = 4
+if os.environ.get("DTYPE") == "bf16":
+    a, b, isz = a.to(torch.bfloat16), b.to(torch.bfloat16), 2
 flags = native.NF_SEGNORM | native.NF_ROWNORM
-D = 2 * d
+D = d + d2
 modes = {"f32 out (API)": dict(want_f32=True, want_planes=False), "hi+lo planes (bf16x3)": dict(want_f32=False, want_planes=True, want_lo=True),
          "f32+hi+stats (rescore)": dict(want_f32=True, want_planes=True, want_lo=False, want_stats=True),
          "hi only (bf16x1)": dict(want_f32=False, want_planes=True, want_lo=False)}
-bytes_per_row = {"f32 out (API)": D * 4 + D * 4, "hi+lo planes (bf16x3)": D * 4 + D * 4, "f32+hi+stats (rescore)": D * 4 + D * 4 + D * 2,
-                 "hi only (bf16x1)": D * 4 + D * 2}
+bytes_per_row = {"f32 out (API)": D * isz + D * 4, "hi+lo planes (bf16x3)": D * isz + D * 4, "f32+hi+stats (rescore)": D * isz + D * 4 + D * 2,
+                 "hi only (bf16x1)": D * isz + D * 2}
 for name, kw in modes.items():
     for _ in range(3):
         o = eng.normalize_fuse(a, b, 1.0, 1.0, flags, **kw)
