@@ -443,10 +443,10 @@ def main():
     flops = 2.0 * dim * n_q * (hi - lo)
     passes = {"bf16x3": 3, "bf16x1": 1, "fp32": 1, "rescore": 1}[res["precision"]]
     achieved = flops / (k2_avg_ms / 1e3) / 1e12
-    # DRAM bytes of the dominant kernel (tc_topk_kernel<1,32,0>, full 1M-row shard) from the committed ncu
-    # --set full capture profiles/r01_ncu_step_c2_rescore.md: 3.924 GB read + 0.034 GB written per launch
-    # (algorithmic: 2.05 GB bf16 database plane + 20 MB query plane + 33 MB partial lists).
-    traffic = 3.958e9 if (res["precision"] == "rescore" and world == 1 and args.workload == "c2") else None
+    # DRAM bytes of the dominant kernel (tc2_topk_kernel<1,16,0>, full 1M-row shard) from the committed ncu
+    # --set full capture profiles/r01_ncu_step_c2_rescore.md: 3.574 GB read + 0.034 GB written per launch
+    # (algorithmic: 2.05 GB bf16 database plane + 20 MB query plane + 31 MB partial lists).
+    traffic = 3.608e9 if (res["precision"] == "rescore" and world == 1 and args.workload == "c2") else None
     roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tflops"], "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
                 "peak_source": pk["src"] + " (bf16 sustained)",
