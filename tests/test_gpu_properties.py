@@ -1,0 +1,96 @@
+"""Property tests (hypothesis) of the search arms against the oracle on random shapes, including the
+edge cases the reference semantics define: K > N, single rows, zero rows (epsilon path), duplicate
+rows (exact ties -> lower index first), odd dimensions, fold masks."""
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from emr2a_b200.engine import get_engine
+    return get_engine()
+
+
+def _reference_topk(oracle, qs, db, k, q_fold=None, db_fold=None):
+    idx, sc = oracle.search_topk_batched(qs, db, k, q_fold=q_fold, db_fold=db_fold)
+    return idx, sc
+
+
+@settings(max_examples=30, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(q=st.integers(1, 300), n=st.integers(1, 3000), d=st.integers(1, 300), k=st.integers(1, 10),
+       arm=st.sampled_from(["fp32", "bf16x3", "rescore"]), masked=st.booleans(), seed=st.integers(0, 10_000),
+       zero_rows=st.booleans(), dups=st.booleans())
+def test_search_matches_oracle_on_random_shapes(eng, oracle, q, n, d, k, arm, masked, seed, zero_rows, dups):
+    import torch
+    from emr2a_b200 import native
+    from emr2a_b200.engine import unpack_keys
+    rng = np.random.default_rng(seed)
+    raw_db = rng.standard_normal((n, d)).astype(np.float32)
+    raw_q = rng.standard_normal((q, d)).astype(np.float32)
+    if zero_rows:
+        raw_db[rng.integers(0, n)] = 0.0                       # norm 0 -> divided by 1e-8 -> stays 0 -> score 0
+    if dups and n >= 2:
+        raw_db[n - 1] = raw_db[0]                               # exact tie between index 0 and n-1
+        raw_q[0] = raw_db[0]
+    db, qs = oracle.unit_rows(raw_db), oracle.unit_rows(raw_q)
+    kw, okw = {}, {}
+    if masked:
+        qf, df = rng.integers(0, 3, q).astype(np.uint8), rng.integers(0, 3, n).astype(np.uint8)
+        kw = dict(q_fold=torch.from_numpy(qf), db_fold=torch.from_numpy(df))
+        okw = dict(q_fold=qf, db_fold=df)
+    keys = eng.topk_search(eng.prepare(raw_q, flags=native.NF_ROWNORM, precision=arm),
+                           eng.prepare(raw_db, flags=native.NF_ROWNORM, precision=arm), k, arm, **kw)
+    unverified, overflow = eng.consume_status()
+    assert not overflow
+    sc, idx = unpack_keys(keys)
+    o_idx, o_sc = _reference_topk(oracle, qs, db, k, **okw)
+    tol = 1e-5 if arm == "bf16x3" else 2e-6
+    valid = o_idx >= 0
+    assert np.array_equal(idx >= 0, valid)                       # same number of admissible neighbours (K > N, masks)
+    assert np.max(np.abs(np.where(valid, sc - o_sc, 0)), initial=0) <= tol
+    full = qs.astype(np.float64) @ db.astype(np.float64).T
+    if masked:
+        full = np.where(okw["q_fold"][:, None] == okw["db_fold"][None, :], -np.inf, full)
+    srt = -np.sort(-full, axis=1)[:, :k + 1]
+    gaps = np.abs(np.diff(srt, axis=1))
+    gaps = np.where(np.isfinite(gaps), gaps, np.inf)
+    safe = gaps.min(axis=1) > 2 * tol if gaps.shape[1] else np.ones(q, bool)
+    assert np.array_equal(idx[safe], o_idx[safe])
+    if dups and n >= 2 and k >= 2 and not masked and not zero_rows:
+        assert list(idx[0][:2]) == [0, n - 1]                    # identical rows: the lower index ranks first
+
+
+@settings(max_examples=15, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(n_tr=st.integers(3, 400), n_te=st.integers(1, 60), d=st.integers(2, 64), top_k=st.integers(1, 12),
+       fusion=st.sampled_from(["concat", "late", "image_only", "text_only"]), seed=st.integers(0, 1000))
+def test_evaluate_processed_fold_matches_oracle(oracle, n_tr, n_te, d, top_k, fusion, seed):
+    """Whole fold (fusion -> Top-K -> votes -> metrics dict) for random sizes, including top_k > n_train."""
+    from emr2a_b200.utils.cv_evaluator import CVRetrievalEvaluator
+    rng = np.random.default_rng(seed)
+    unit = lambda a: oracle.unit_rows(a.astype(np.float32))     # noqa: E731
+    tr_i, tr_t = unit(rng.standard_normal((n_tr, d))), unit(rng.standard_normal((n_tr, d + 3)))
+    te_i, te_t = unit(rng.standard_normal((n_te, d))), unit(rng.standard_normal((n_te, d + 3)))
+    codes_tr, codes_te = rng.integers(0, 3, n_tr), rng.integers(0, 3, n_te)
+    names = lambda c: [f"class_{int(x)}" for x in c]            # noqa: E731
+    ev = CVRetrievalEvaluator(top_k=top_k)
+    r = ev.evaluate_processed_fold(tr_i, tr_t, te_i, te_t, names(codes_tr), names(codes_te),
+                                   [f"q{j}" for j in range(n_te)], fusion=fusion, top_k_list=[1, 3, 5, top_k], w_text=0.4)
+    # the reference averages the macro metrics over the classes PRESENT in train+test (cv_evaluator.py:312)
+    present = sorted(set(codes_tr.tolist()) | set(codes_te.tolist()))
+    remap = {c: i for i, c in enumerate(present)}
+    o = oracle.cv_fold_eval(tr_i, tr_t, te_i, te_t, np.array([remap[c] for c in codes_tr]),
+                            np.array([remap[c] for c in codes_te]), len(present), fusion=fusion, top_k=top_k,
+                            top_k_list=(1, 3, 5, top_k), w_text=0.4)
+    got_sc = np.array(r["all_top_scores"])
+    assert got_sc.shape == o["top_scores"].shape                 # min(top_k, n_train) neighbours per query
+    assert np.max(np.abs(got_sc - o["top_scores"])) < 2e-6
+    gaps = np.abs(np.diff(o["top_scores"], axis=1))
+    safe = gaps.min(axis=1) > 4e-6 if gaps.shape[1] else np.ones(n_te, bool)
+    got_idx = np.array([[int(x.split("_")[1]) for x in row] for row in r["all_top_patient_ids"]])
+    assert np.array_equal(got_idx[safe], o["top_idx"][safe])
+    if safe.all():
+        for key in ("top1", "top3", "top5", "vote_acc", "weighted_vote_acc", "macro_precision", "macro_recall", "macro_f1"):
+            assert abs(float(r[key]) - o[key]) < 1e-12, key
