@@ -82,7 +82,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "25"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -90,16 +90,19 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, windows=None):
+        """Summary of the samples that arrived inside the given (t0, t1) wall-clock windows (the timed regions)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
+            if windows and not any(a <= ts <= b + 0.12 for a, b in windows):
+                continue
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except Exception:
@@ -108,7 +111,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "window": "timed regions (device-resident loop + e2e loop), nvidia-smi -lms 100"}
 
 
 def cpu_reference_leg(db_img, db_txt, q_img, q_txt, db_labels, q_labels, k, sample, full_q):
@@ -370,15 +374,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)      # started early: nvidia-smi needs ~0.2 s before its first sample
+    if rank == 0:
+        sampler.start()
+    windows = []
     for _ in range(max(args.warmup, 3)):
         res = step()
     barrier()
 
     # ---- timed region: device-resident ----
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = eng.launches
+    w0 = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -390,11 +396,11 @@ def main():
         k2_events.append((e0, e1))
     ev1.record()
     barrier()
+    windows.append((w0, time.time()))
     unverified_total, overflow = eng.check_deferred(deferred)
     assert not overflow, "rescore re-scan list overflowed: results of the timed steps are not valid"
     ms = ev0.elapsed_time(ev1)
     launches = eng.launches - launches0
-    clocks = sampler.stop() if rank == 0 else None
     k2_ms = [a.elapsed_time(b) for a, b in k2_events]
     t = torch.tensor([ms, sum(k2_ms) / len(k2_ms)], device=dev, dtype=torch.float64)
     if world > 1:
@@ -416,17 +422,20 @@ def main():
         def e2e_step():
             return eng.search_and_vote_host((h_img, h_txt), (hq_img, hq_txt), h_lab, hq_lab, n_cls, k,
                                             db_flags=flags, q_flags=flags, q_weights=q_weights, k_list=k_list,
-                                            precision=args.precision, row_offset=lo, reduce_fn=reduce_fn)
+                                            precision=args.precision, row_offset=lo, reduce_fn=reduce_fn,
+                                            chunk_rows=(int(os.environ["EMR2A_E2E_CHUNK"]) if "EMR2A_E2E_CHUNK" in os.environ else None))
         for _ in range(2):
             out = e2e_step()
         barrier()
         e_steps = max(2, min(args.steps, 5))
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        w0 = time.time()
         t0.record()
         for _ in range(e_steps):
             out = e2e_step()
         t1.record()
         barrier()
+        windows.append((w0, time.time()))
         te = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -437,6 +446,8 @@ def main():
         # the two paths must agree bit for bit
         assert torch.equal(out["top_idx"], res["top_idx"].cpu()), "e2e and device-resident results differ"
         del h_img, h_txt
+
+    clocks = sampler.stop(windows) if rank == 0 else None
 
     # ---- roofline of the dominant kernel (K2, tensor pipe) ----
     pk = peaks()

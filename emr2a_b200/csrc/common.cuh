@@ -13,7 +13,6 @@
 namespace emr2a {
 
 // ---- thread-local error text -------------------------------------------------
-void set_error(const char* fmt, ...);
 int fail(int code, const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* where);
 

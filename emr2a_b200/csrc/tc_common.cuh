@@ -164,49 +164,63 @@ template <int KCAP, bool HAS_FOLD>
 __device__ __forceinline__ void scan_tile(const TcParams& p, RegTopK<KCAP>& top, float& thr, const float thr0,
                                           const uint32_t taddr, const int64_t n0, const uint32_t my_fold,
                                           const int64_t q) {
-          const bool edge = (n0 + T_BN > p.N);
-  #pragma unroll 1
-          for (int ch = 0; ch < T_BN / 32; ++ch) {
-            float v[32];
-            tmem_ld32(taddr + static_cast<uint32_t>(ch * 32), v);
-            const int64_t c0 = n0 + ch * 32;
-            if (p.debug_scores && q < p.Q) {
-  #pragma unroll
-              for (int c = 0; c < 32; ++c) if (c0 + c < p.N) p.debug_scores[q * p.N + c0 + c] = v[c];
-            }
-            if (edge) {
-  #pragma unroll
-              for (int c = 0; c < 32; ++c) if (c0 + c >= p.N) v[c] = -INFINITY;
-            }
-            if (HAS_FOLD) {
-              const uint4* fp = reinterpret_cast<const uint4*>(p.db_fold + c0);
-              const uint4 f0 = __ldg(fp), f1 = __ldg(fp + 1);
-              const uint32_t w[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-  #pragma unroll
-              for (int c = 0; c < 32; ++c) {
-                const uint32_t f = (w[c >> 2] >> (8 * (c & 3))) & 0xFFu;
-                v[c] = (f == my_fold) ? -INFINITY : v[c];
-              }
-            }
-            float mx = v[0];
-  #pragma unroll
-            for (int c = 1; c < 32; ++c) mx = fmaxf(mx, v[c]);
-            if (mx > thr) {
-              uint32_t mask = 0u;
-  #pragma unroll
-              for (int c = 0; c < 32; ++c) mask |= (v[c] > thr) ? (1u << c) : 0u;
-              while (mask) {
-                const int c = __ffs(mask) - 1;
-                mask &= mask - 1u;
-                const float val = select32(v, c);
-                if (val > thr) {
-                  top.insert(val, static_cast<uint32_t>(c0 + c + p.idx_base));
-                  thr = fmaxf(top.threshold(), thr0);
-                }
-              }
-            }
-            __syncwarp();
-          }
+  const bool edge = (n0 + T_BN > p.N);
+#pragma unroll 1
+  for (int ch = 0; ch < T_BN / 32; ++ch) {
+    float v[32];
+    tmem_ld32(taddr + static_cast<uint32_t>(ch * 32), v);
+    const int64_t c0 = n0 + ch * 32;
+    if (p.debug_scores && q < p.Q) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) if (c0 + c < p.N) p.debug_scores[q * p.N + c0 + c] = v[c];
+    }
+    if (edge) {                                   // columns past the last database row
+#pragma unroll
+      for (int c = 0; c < 32; ++c) if (c0 + c >= p.N) v[c] = -INFINITY;
+    }
+    if (HAS_FOLD) {                               // CV rule: rows of the query's own fold are inadmissible
+      const uint4* fp = reinterpret_cast<const uint4*>(p.db_fold + c0);
+      const uint4 f0 = __ldg(fp), f1 = __ldg(fp + 1);
+      const uint32_t w[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const uint32_t f = (w[c >> 2] >> (8 * (c & 3))) & 0xFFu;
+        v[c] = (f == my_fold) ? -INFINITY : v[c];
+      }
+    }
+    float mx = v[0];
+#pragma unroll
+    for (int c = 1; c < 32; ++c) mx = fmaxf(mx, v[c]);
+    if (mx > thr) {                               // rare: at least one score beats the current threshold
+      uint32_t mask = 0u;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) mask |= (v[c] > thr) ? (1u << c) : 0u;
+      while (mask) {
+        const int c = __ffs(mask) - 1;
+        mask &= mask - 1u;
+        const float val = select32(v, c);
+        if (val > thr) {
+          top.insert(val, static_cast<uint32_t>(c0 + c + p.idx_base));
+          thr = fmaxf(top.threshold(), thr0);
+        }
+      }
+    }
+    __syncwarp();                                 // tcgen05.ld is warp-collective: reconverge before the next chunk
+  }
+}
+
+// Start threshold of a work unit from the shared per-query bound tau[q]: units of the same query tile that
+// finished earlier published their KCAP-th best score; the global KCAP-th best is at least that, so rows
+// strictly below it can be skipped without changing the merged list (">= bound" is kept, hence one ulp down).
+__device__ __forceinline__ float unit_start_threshold(const TcParams& p, int64_t q) {
+  if (p.tau == nullptr || q >= p.Q) return -INFINITY;
+  const uint32_t t = __ldcg(p.tau + q);
+  if (t == 0u) return -INFINITY;
+  const float b = unorder_f32(t);
+  const uint32_t bits = __float_as_uint(b);
+  if (b > 0.f) return __uint_as_float(bits - 1u);
+  if (b < 0.f) return __uint_as_float(bits + 1u);
+  return -1e-45f;                                 // just below zero
 }
 
 }  // namespace emr2a

@@ -151,15 +151,7 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constan
       const int64_t t1 = (t0 + p.tiles_per_split < p.n_tiles) ? t0 + p.tiles_per_split : p.n_tiles;
       const uint32_t my_fold = (HAS_FOLD && q < p.Q) ? p.q_fold[q] : 0xFFFFu;
       top.reset();
-      // Units of the same query tile that finished earlier published their KCAP-th best score: the global
-      // KCAP-th best is at least that, so rows strictly below it can be skipped here without changing the
-      // merged list (">= bound" is kept, hence the step down by one ulp).  It removes the list warm-up --
-      // a burst of warp-serialised insertions -- from every unit but the first of a query tile.
-      float thr0 = -INFINITY;
-      if (p.tau != nullptr && q < p.Q) {
-        const uint32_t t = __ldcg(p.tau + q);
-        if (t != 0u) thr0 = __uint_as_float(__float_as_uint(unorder_f32(t)) - ((unorder_f32(t) > 0.f) ? 1u : 0u) + ((unorder_f32(t) < 0.f) ? 1u : 0u));
-      }
+      const float thr0 = unit_start_threshold(p, q);
       float thr = thr0;
       const int ufold = HAS_FOLD ? unit_fold(p, mt) : -1;
       for (int64_t t = t0; t < t1; ++t) {
