@@ -155,3 +155,56 @@ def test_dropin_shims_exist_for_every_reference_module():
                          "RetrievalEvaluator"]
     assert u.__all__ == ["l2_normalize", "concat_embeddings", "compute_accuracy", "compute_top_k_accuracy",
                          "compute_precision_recall_f1", "compute_confusion_matrix"]
+
+
+REFERENCE = os.environ.get("EMR2A_REFERENCE", "/root/reference")
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "pipelines")), reason="reference tree not present (GPU box)")
+def test_reference_scripts_run_on_the_dropin(tmp_path):
+    """The reference's own step-3 script, launched unchanged through emr2a_b200/run.py from the reference
+    root, must reach THIS implementation: without a GPU it stops at our 'no CPU fallback' error instead of
+    silently running the reference's numpy path; with a GPU it completes and writes retrieval_results.json."""
+    import json
+    import subprocess
+    import sys
+    rng = np.random.default_rng(0)
+    manifest = tmp_path / "manifest.jsonl"
+    emb = {}
+    with manifest.open("w") as fh:
+        for i in range(40):
+            pid = f"p{i:03d}"
+            fh.write(json.dumps({"patient_id": pid, "label": f"class_{i % 2}", "slices": [], "meta": {}}) + "\n")
+            emb[pid] = rng.standard_normal((3, 16)).astype(np.float32)
+    np.savez(tmp_path / "emb.npz", **emb)
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
+    env.pop("PYTHONPATH", None)
+    out = subprocess.run([sys.executable, os.path.join(REPO, "emr2a_b200", "run.py"), "pipelines.step3_retrieval.run",
+                          "--manifest_path", str(manifest), "--embeddings_path", str(tmp_path / "emb.npz"),
+                          "--output_dir", str(tmp_path / "out")], cwd=REFERENCE, env=env, capture_output=True, text=True)
+    import torch
+    if torch.cuda.is_available():
+        assert out.returncode == 0, out.stderr[-2000:]
+        res = json.load(open(tmp_path / "out" / "retrieval_results.json"))
+        assert set(res) == {"image_top1", "image_top3", "image_top5", "image_weighted"}
+    else:
+        assert out.returncode != 0
+        assert "no CPU fallback" in out.stderr, out.stderr[-2000:]
+        assert "emr2a_b200" in out.stderr
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "analysis")), reason="reference tree not present (GPU box)")
+def test_dropin_import_resolution_from_reference_root():
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); import utils, retrieval, utils.cv_evaluator as c, utils.vlm_review as v; "
+            "import pipelines.step3_retrieval.evaluate_retrieval as s3; "
+            "print(c.CVRetrievalEvaluator.__module__, s3.RetrievalEvaluator.__module__, v.__file__)"
+            % os.path.join(REPO, "emr2a_b200", "dropin"))
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
+    env.pop("PYTHONPATH", None)
+    out = subprocess.run([sys.executable, "-c", code], cwd=REFERENCE, env=env, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-1500:]
+    a, b, c = out.stdout.strip().splitlines()[-1].split()
+    assert a == "emr2a_b200.utils.cv_evaluator" and b == "emr2a_b200.retrieval.evaluator"
+    assert c == os.path.join(REFERENCE, "utils", "vlm_review.py")
