@@ -47,6 +47,41 @@ __global__ void __launch_bounds__(256) topk_merge_reg_kernel(const uint64_t* __r
   }
 }
 
+// P-way merge of SORTED lists (parts <= 32, K_in <= 32): lane p owns list p, staged in shared memory
+// ([slot][lane] layout: conflict-free), and exposes its head; each round is one warp arg-max over the
+// heads, the winning lane advances.  ~40 instructions per output key instead of ~150 for the
+// register kernel above, which re-scans every key of the query each round.
+constexpr int PW_WARPS = 8;
+__global__ void __launch_bounds__(PW_WARPS * 32) topk_merge_pway_kernel(const uint64_t* __restrict__ in, int parts, int64_t Q,
+                                                                        int K_in, int64_t part_stride, int64_t q_stride,
+                                                                        int K_out, uint64_t* __restrict__ out) {
+  extern __shared__ uint64_t pw_keys[];                       // [PW_WARPS][K_in][32]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * PW_WARPS + warp;
+  if (q >= Q) return;
+  uint64_t* mine_list = pw_keys + static_cast<size_t>(warp) * K_in * 32;
+  if (lane < parts) {
+    const uint64_t* src = in + lane * part_stride + q * q_stride;
+    for (int j = 0; j < K_in; ++j) mine_list[j * 32 + lane] = src[j];
+  }
+  __syncwarp();
+  int ptr = 0;
+  uint64_t head = lane < parts ? mine_list[lane] : 0ull;
+  uint64_t keep = 0ull;
+  for (int r = 0; r < K_out; ++r) {
+    const uint64_t best = warp_max_u64(head);
+    if ((r & 31) == lane) keep = best;
+    if (best != 0ull && head == best) {                       // keys are unique: exactly one lane advances
+      ++ptr;
+      head = ptr < K_in ? mine_list[ptr * 32 + lane] : 0ull;
+    }
+    if ((r & 31) == 31 || r == K_out - 1) {
+      const int base = r & ~31;
+      if (base + lane <= r) out[q * K_out + base + lane] = keep;
+    }
+  }
+}
+
 // Generic fallback (parts * K_in > 256): re-scan from memory each round.
 __global__ void __launch_bounds__(256) topk_merge_scan_kernel(const uint64_t* __restrict__ in, int parts, int64_t Q,
                                                               int K_in, int64_t part_stride, int64_t q_stride,
@@ -231,6 +266,14 @@ extern "C" int emr2a_topk_merge(const uint64_t* keys_in, int parts, int64_t Q, i
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int total = parts * K_in;
   const unsigned blocks = static_cast<unsigned>((Q * 32 + 255) / 256);
+  if (parts <= 32 && K_in <= 32 && total > 32) {
+    const size_t smem = sizeof(uint64_t) * PW_WARPS * K_in * 32;          // up to 64 KB
+    EMR2A_CUDA_TRY(cudaFuncSetAttribute(topk_merge_pway_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    topk_merge_pway_kernel<<<static_cast<unsigned>((Q + PW_WARPS - 1) / PW_WARPS), PW_WARPS * 32, smem, st>>>(
+        keys_in, parts, Q, K_in, part_stride, q_stride, K_out, keys_out);
+    EMR2A_LAUNCH_CHECK("topk_merge_pway_kernel");
+    return EMR2A_OK;
+  }
   if (total <= 32) topk_merge_reg_kernel<1><<<blocks, 256, 0, st>>>(keys_in, parts, Q, K_in, part_stride, q_stride, K_out, keys_out);
   else if (total <= 64) topk_merge_reg_kernel<2><<<blocks, 256, 0, st>>>(keys_in, parts, Q, K_in, part_stride, q_stride, K_out, keys_out);
   else if (total <= 128) topk_merge_reg_kernel<4><<<blocks, 256, 0, st>>>(keys_in, parts, Q, K_in, part_stride, q_stride, K_out, keys_out);

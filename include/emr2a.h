@@ -166,7 +166,8 @@ int emr2a_topk_search(const float* q_f32, int64_t ldq_f32,
                       void* workspace, size_t ws_bytes, void* stream);
 
 /*
- * K3 -- merge `parts` sorted partial Top-K lists per query into one.
+ * K3 -- merge `parts` partial Top-K lists per query into one.  Every input list must be sorted
+ * best-first with its empty slots (0) at the end, as K2 and this function produce them.
  *   keys_in[(p * part_stride) + q * q_stride + j], j < K_in   ->  keys_out[q * K_out + j]
  * Used for the per-CTA partial lists of K2 and for the lists gathered from the
  * other GPUs (row-sharded database; NCCL all-gather).
