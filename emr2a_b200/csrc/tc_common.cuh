@@ -165,6 +165,15 @@ __device__ __forceinline__ void scan_tile(const TcParams& p, RegTopK<KCAP>& top,
                                           const uint32_t taddr, const int64_t n0, const uint32_t my_fold,
                                           const int64_t q) {
   const bool edge = (n0 + T_BN > p.N);
+  // Fold-sorted rows: a tile whose first and last row share a fold holds that fold only.  Then the
+  // per-element mask is unnecessary: either every row of the tile is inadmissible for this thread's
+  // query (nothing to scan, but the warp still runs the collective TMEM loads) or none is.
+  bool mask_rows = HAS_FOLD, all_masked = false;
+  if (HAS_FOLD && p.fold_sorted) {
+    const int64_t last = (n0 + T_BN - 1 < p.N) ? n0 + T_BN - 1 : p.N - 1;
+    const uint32_t f_lo = __ldg(p.db_fold + n0), f_hi = __ldg(p.db_fold + last);
+    if (f_lo == f_hi) { mask_rows = false; all_masked = (f_lo == my_fold); }
+  }
 #pragma unroll 1
   for (int ch = 0; ch < T_BN / 32; ++ch) {
     float v[32];
@@ -178,7 +187,11 @@ __device__ __forceinline__ void scan_tile(const TcParams& p, RegTopK<KCAP>& top,
 #pragma unroll
       for (int c = 0; c < 32; ++c) if (c0 + c >= p.N) v[c] = -INFINITY;
     }
-    if (HAS_FOLD) {                               // CV rule: rows of the query's own fold are inadmissible
+    if (HAS_FOLD && all_masked) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) v[c] = -INFINITY;
+    }
+    if (HAS_FOLD && mask_rows) {                  // CV rule: rows of the query's own fold are inadmissible
       const uint4* fp = reinterpret_cast<const uint4*>(p.db_fold + c0);
       const uint4 f0 = __ldg(fp), f1 = __ldg(fp + 1);
       const uint32_t w[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
