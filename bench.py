@@ -201,9 +201,9 @@ def run_c5(args):
     """BASELINE.json configs[4]: N-case 1024-d fused database, EVERY case a query, 5-fold CV rule (a case
     is never retrieved from its own fold), K=5, database row-sharded over the ranks.  Rows are in fold
     order (fold = contiguous fifths of the synthetic, label-shuffled rows).  Per step and rank: K1 on the
-    shard; for every query block (broadcast from the rank that owns those rows): K1, fold-masked K2 against
-    the local shard (whole own-fold tiles skipped), all-gather of the local Top-K, K3 merge, K4 vote with
-    per-fold counters."""
+    shard; one all-gather of the raw rows (every case is a query); for every query block: K1, fold-masked K2
+    against the local shard (whole own-fold tiles skipped); then all-gather of the local Top-K, K3 merge, K4 vote
+    with per-fold counters."""
     import torch
     import torch.distributed as dist
     from emr2a_b200 import native, synth
@@ -227,31 +227,45 @@ def run_c5(args):
     fold = (torch.arange(n, device=dev, dtype=torch.int64) * n_folds // n).to(torch.uint8)
     prec = args.precision
     spans = [shard_range(n, r, world) for r in range(world)]
+    per = spans[0][1] - spans[0][0]
     torch.cuda.synchronize()
 
     def step():
+        # (1) every rank needs every case as a query: ONE all-gather of the raw rows over NVLink (41 GB per GPU at
+        #     10M cases) instead of a broadcast per query block -- with fold-ordered rows a rank has nothing to do for
+        #     query blocks of the fold its shard lies in, so any per-block collective would make it wait for the others.
+        if world > 1:
+            full_img = torch.empty((world * per, d_img), dtype=torch.float32, device=dev)
+            full_txt = torch.empty((world * per, d_txt), dtype=torch.float32, device=dev)
+            pad_i, pad_t = db_img, db_txt
+            if hi - lo < per:
+                pad_i = torch.zeros((per, d_img), dtype=torch.float32, device=dev); pad_i[:hi - lo] = db_img
+                pad_t = torch.zeros((per, d_txt), dtype=torch.float32, device=dev); pad_t[:hi - lo] = db_txt
+            dist.all_gather_into_tensor(full_img, pad_i)
+            dist.all_gather_into_tensor(full_txt, pad_t)
+        else:
+            full_img, full_txt = db_img, db_txt
+        # (2) local work, no communication: K1 on the shard, then every query block against it
         db = eng.prepare(db_img, db_txt, 1.0, 1.0, flags, prec)
+        local = []
+        for b0 in range(0, n, q_block):
+            b1 = min(b0 + q_block, n)
+            qs = eng.prepare(full_img[b0:b1], full_txt[b0:b1], 1.0, 1.0, flags, prec)
+            local.append(eng.topk_search(qs, db, k, prec, q_fold=fold[b0:b1], db_fold=fold[lo:hi], fold_sorted=True,
+                                         idx_base=lo))
+        # (3) exchange: all-gather of the local Top-K of each block, K3 merge, K4 vote with per-fold counters
         hits = votes = sizes = None
+        for i, b0 in enumerate(range(0, n, q_block)):
+            b1 = min(b0 + q_block, n)
+            keys = local[i]
+            if world > 1:
+                keys = eng.topk_merge(gather_keys(keys), k)
+            r = eng.vote_metrics(keys, labels, labels[b0:b1], n_cls, k_list=[1, 3, 5], q_group=fold[b0:b1],
+                                 n_groups=n_folds, per_query=False, want_lists=False)
+            hits = r["hit_counts"] if hits is None else hits + r["hit_counts"]
+            votes = r["vote_counts"] if votes is None else votes + r["vote_counts"]
+            sizes = r["group_sizes"] if sizes is None else sizes + r["group_sizes"]
         unverified = 0
-        for owner, (slo, shi) in enumerate(spans):
-            for b0 in range(slo, shi, q_block):
-                b1 = min(b0 + q_block, shi)
-                if owner == rank:
-                    qi, qt = db_img[b0 - lo:b1 - lo], db_txt[b0 - lo:b1 - lo]
-                else:
-                    qi = torch.empty((b1 - b0, d_img), dtype=torch.float32, device=dev)
-                    qt = torch.empty((b1 - b0, d_txt), dtype=torch.float32, device=dev)
-                if world > 1:
-                    dist.broadcast(qi, src=owner); dist.broadcast(qt, src=owner)
-                qs = eng.prepare(qi, qt, 1.0, 1.0, flags, prec)
-                keys = eng.topk_search(qs, db, k, prec, q_fold=fold[b0:b1], db_fold=fold[lo:hi], fold_sorted=True, idx_base=lo)
-                if world > 1:
-                    keys = eng.topk_merge(gather_keys(keys), k)
-                r = eng.vote_metrics(keys, labels, labels[b0:b1], n_cls, k_list=[1, 3, 5], q_group=fold[b0:b1],
-                                     n_groups=n_folds, per_query=False, want_lists=False)
-                hits = r["hit_counts"] if hits is None else hits + r["hit_counts"]
-                votes = r["vote_counts"] if votes is None else votes + r["vote_counts"]
-                sizes = r["group_sizes"] if sizes is None else sizes + r["group_sizes"]
         if prec == "rescore":
             unverified, overflow = eng.consume_status()
             if overflow:
@@ -292,12 +306,13 @@ def run_c5(args):
                 "steps": steps, "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": prec, "data": "synthetic",
                 "config": {"workload": f"c5: {n}-case {dim}-d fused database, every case a query, {n_folds}-fold CV rule, K={k}",
-                           "parallelism": f"database row-sharded x{world}, query blocks of {q_block} broadcast from their owner, "
-                                          "NCCL all-gather of local Top-K", "l2": "inputs larger than L2"},
+                           "parallelism": f"database row-sharded x{world}; raw rows all-gathered once per step (every case is a "
+                                          f"query), query blocks of {q_block} searched locally, NCCL all-gather of local Top-K",
+                           "l2": "inputs larger than L2"},
                 "clocks": clocks, "e2e": None, "gpu_launches": eng.launches - l0,
                 "roofline": {"bound": "tensor", "achieved": tf / world, "peak": pk["tflops"], "unit": "TFLOP/s per GPU",
                              "frac": tf / world / pk["tflops"], "traffic": None,
-                             "note": "whole step (K1 + broadcasts + K2 + gather + K3 + K4) over admissible pairs only"},
+                             "note": "whole step (row all-gather + K1 + K2 + key gather + K3 + K4) over admissible pairs only"},
                 "cpu_baseline": None, "unverified_queries": int(unverified),
                 "accuracy": {"top1": float(hits[:, 0].sum()) / n, "top5": float(hits[:, 2].sum()) / n,
                              "vote_acc": float(votes[:, 1].sum()) / n,
