@@ -554,6 +554,26 @@ def main():
         # the two paths must agree bit for bit
         assert torch.equal(out["top_idx"], res["top_idx"].cpu()), "e2e and device-resident results differ"
         del h_img, h_txt
+        # serving shape: the database stays resident in HBM (Engine.build_index), a step copies only the queries
+        # host->device and the result lists device->host
+        if world == 1:
+            index = eng.build_index((db_img, db_txt), db_labels, n_cls, flags=flags, precision=args.precision,
+                                    expected_queries=n_q, k=k)
+            for _ in range(2):
+                r2 = index.search((hq_img, hq_txt), hq_lab, k=k, q_weights=q_weights, k_list=k_list)
+                lists = [r2[nm].cpu() for nm in ("top_idx", "top_scores", "top_labels", "pred_vote")]
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(e_steps):
+                r2 = index.search((hq_img, hq_txt), hq_lab, k=k, q_weights=q_weights, k_list=k_list)
+                lists = [r2[nm].cpu() for nm in ("top_idx", "top_scores", "top_labels", "pred_vote")]
+            torch.cuda.synchronize()
+            r_ms = (time.perf_counter() - t0) / e_steps * 1e3
+            assert torch.equal(lists[0], res["top_idx"].cpu())
+            e2e["resident_index"] = {"value": n_q / (r_ms / 1e3), "unit": "queries/s", "ms_per_step": r_ms,
+                                     "h2d_bytes_per_step": int(hq_img.numel() * 4 + hq_txt.numel() * 4 + hq_lab.numel() * 4),
+                                     "api": "Engine.build_index once + DatabaseIndex.search per step (queries from pinned host memory)"}
+            del index
 
     clocks = sampler.stop(windows) if rank == 0 else None
 

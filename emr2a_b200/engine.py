@@ -375,6 +375,18 @@ class Engine:
         return res
 
 
+    # ------------------------------------------------------ resident database
+    def build_index(self, db_segs: Sequence, db_labels, n_classes: int, flags: int = native.NF_ROWNORM,
+                    weights=(1.0, 1.0), precision: str = "auto", expected_queries: int = 4096, k: int = 10) -> "DatabaseIndex":
+        """Prepare a database ONCE (K1: normalise + fuse + bf16 planes) and keep it in HBM; every later
+        ``DatabaseIndex.search`` only pays for the queries.  The reference re-normalises the database on every
+        call (retrieval/similarity.py:5-6); a serving deployment does not have to."""
+        n_db = int(db_segs[0].shape[0])
+        dim = sum(int(s.shape[1]) for s in db_segs if s is not None)
+        prec = self.pick_precision(expected_queries, n_db, dim, k, precision)
+        op = self.prepare(db_segs[0], db_segs[1] if len(db_segs) > 1 else None, weights[0], weights[1], flags, prec)
+        return DatabaseIndex(self, op, self.to_device(db_labels, torch.int32), n_classes, flags, prec)
+
     # ------------------------------------------------- all folds at once (CV)
     @staticmethod
     def _rows(op: "Operand", lo: int, hi: int) -> "Operand":
@@ -529,6 +541,46 @@ class Engine:
             out[name] = t
         out["d2h_bytes"] = d2h
         return out
+
+
+class DatabaseIndex:
+    """A database resident in HBM in the layout the search kernels consume (see ``Engine.build_index``)."""
+
+    def __init__(self, engine: Engine, operand: Operand, labels: torch.Tensor, n_classes: int, flags: int, precision: str):
+        self.engine, self.operand, self.labels = engine, operand, labels
+        self.n_classes, self.flags, self.precision = n_classes, flags, precision
+
+    @property
+    def rows(self) -> int:
+        return self.operand.n
+
+    def search(self, q_segs: Sequence, q_labels=None, k: int = 10, q_weights=(1.0, 1.0), q_flags: Optional[int] = None,
+               k_list: Sequence[int] = (1, 3, 5), want_lists: bool = True) -> Dict[str, torch.Tensor]:
+        """K1 on the queries (host or device arrays) -> K2 against the resident rows -> K4 vote.  Without
+        ``q_labels`` the hit/vote counters are meaningless and only lists and predictions should be read."""
+        eng = self.engine
+        prec = self.precision
+        if prec == "rescore" and k > _RESCORE_MAX_K:
+            raise ValueError(f"this index was built for the rescore arm (K <= {_RESCORE_MAX_K}); rebuild it with precision='bf16x3'")
+        qs = eng.prepare(q_segs[0], q_segs[1] if len(q_segs) > 1 else None, q_weights[0], q_weights[1],
+                         self.flags if q_flags is None else q_flags, prec)
+        keys = eng.topk_search(qs, self.operand, k, prec)
+        n_q = qs.n
+        if q_labels is None:
+            q_labels = torch.full((n_q,), -1, dtype=torch.int32, device=eng.device)
+        res = eng.vote_metrics(keys, self.labels, q_labels, self.n_classes, k_list=k_list, want_lists=want_lists)
+        if prec == "rescore":
+            unverified, overflow = eng.consume_status()
+            if overflow:
+                raise Emr2aOverflow("rescore verification overflowed for this query batch; rebuild the index with "
+                                    "precision='bf16x3' for databases with very dense score neighbourhoods")
+            res["unverified"] = unverified
+        res["keys"] = keys
+        return res
+
+
+class Emr2aOverflow(RuntimeError):
+    pass
 
 
 _engines: Dict[int, Engine] = {}

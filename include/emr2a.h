@@ -59,10 +59,11 @@ enum emr2a_precision {
   EMR2A_PREC_FP32 = 0,      /* fp32 FMA on CUDA cores: exact-order reference arithmetic, any shape */
   EMR2A_PREC_BF16X3 = 1,    /* tcgen05 bf16 tensor cores, 2-way split (hi*hi + hi*lo + lo*hi), fp32 accumulate: |err| ~ 1e-6 */
   EMR2A_PREC_BF16X1 = 2,    /* tcgen05 bf16 tensor cores, hi plane only (bf16-input variant), fp32 accumulate */
-  EMR2A_PREC_BF16_RESCORE = 3 /* 1-pass bf16 tensor-core FILTER keeping K' = 32 candidates per query, exact fp32
-                                 re-scoring of the candidates from the fp32 rows, selection verified against a rigorous
-                                 error bound; unverifiable queries are re-searched exactly (fp32).  K <= 10.
-                                 Scores are fp32 dot products (|err| ~ 1e-7), about 2.4x faster than BF16X3. */
+  EMR2A_PREC_BF16_RESCORE = 3 /* 1-pass bf16 tensor-core FILTER (16 or 32 candidates per query and database split, the
+                                 64 best after merging), exact fp32 RE-SCORING of the candidates from the fp32 rows,
+                                 selection VERIFIED against a rigorous error bound (K1 stats); queries the bound cannot
+                                 verify are re-searched exactly in fp32.  K <= 10.  Scores are fp32 dot products
+                                 (|err| ~ 1e-7); about 3x faster than BF16X3. */
 };
 
 /* score normalisation modes of emr2a_late_fuse_scores (retrieval/fusion.py:31-42) */

@@ -238,3 +238,23 @@ def test_run_cv_processed_equals_fold_by_fold(oracle):
                     assert fr[key] == slow[key], (fusion, f, key)
         assert set(fast["summary"]) == {"top1", "top3", "top5", "vote_acc", "weighted_vote_acc", "macro_precision",
                                         "macro_recall", "macro_f1"}
+
+
+def test_resident_index_matches_one_shot_search(oracle):
+    from emr2a_b200 import native, synth
+    from emr2a_b200.engine import get_engine
+    eng = get_engine()
+    both = synth.two_modal(30_000 + 500, 64, 64, 3, seed=9)
+    db = {k: v[:30_000] for k, v in both.items()}
+    qs = {k: v[30_000:] for k, v in both.items()}
+    flags = native.NF_SEGNORM | native.NF_ROWNORM
+    for prec in ("rescore", "fp32"):
+        one = eng.search_and_vote((db["image"], db["text"]), (qs["image"], qs["text"]), db["labels"], qs["labels"], 3, 5,
+                                  db_flags=flags, q_flags=flags, k_list=[1, 3, 5], precision=prec)
+        index = eng.build_index((db["image"], db["text"]), db["labels"], 3, flags=flags, precision=prec)
+        assert index.rows == 30_000
+        for _ in range(2):                                    # the index is reusable
+            r = index.search((qs["image"], qs["text"]), qs["labels"], k=5, k_list=[1, 3, 5])
+            assert np.array_equal(r["top_idx"].cpu().numpy(), one["top_idx"].cpu().numpy())
+            assert np.array_equal(r["hit_counts"].cpu().numpy(), one["hit_counts"].cpu().numpy())
+            assert np.array_equal(r["pred_weighted"].cpu().numpy(), one["pred_weighted"].cpu().numpy())
