@@ -338,9 +338,36 @@ __global__ void __launch_bounds__(256) late_fuse_kernel(const float* __restrict_
   }
 }
 
+// ---- mean over the slices of each patient (ingest) ---------------------------------------
+// One block per patient; threads stride over the feature dimension (coalesced), slices are added in
+// order in fp32 and divided by the count -- numpy's `arr.mean(axis=0)` arithmetic.  HBM-bound:
+// total_slices * D * 4 bytes read + n * D * 4 written.
+__global__ void __launch_bounds__(128) segment_mean_kernel(const float* __restrict__ x, int64_t ld,
+                                                           const int64_t* __restrict__ offsets, int D,
+                                                           float* __restrict__ out, int64_t ld_out) {
+  const int64_t seg = blockIdx.x;
+  const int64_t r0 = offsets[seg], r1 = offsets[seg + 1];
+  const float cnt = static_cast<float>(r1 - r0);
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float acc = 0.f;
+    for (int64_t r = r0; r < r1; ++r) acc = __fadd_rn(acc, __ldg(x + r * ld + c));
+    out[seg * ld_out + c] = r1 > r0 ? __fdiv_rn(acc, cnt) : 0.f;
+  }
+}
+
 }  // namespace emr2a
 
 using namespace emr2a;
+
+extern "C" int emr2a_segment_mean(const float* x, int64_t ld, const int64_t* offsets, int64_t n_segments, int D,
+                                  float* out, int64_t ld_out, void* stream) {
+  if (!x || !offsets || !out || n_segments < 0 || D <= 0 || ld < D || ld_out < D)
+    return fail(EMR2A_ERR_INVALID, "segment_mean: bad arguments");
+  if (n_segments == 0) return EMR2A_OK;
+  segment_mean_kernel<<<static_cast<unsigned>(n_segments), 128, 0, static_cast<cudaStream_t>(stream)>>>(x, ld, offsets, D, out, ld_out);
+  EMR2A_LAUNCH_CHECK("segment_mean_kernel");
+  return EMR2A_OK;
+}
 
 extern "C" int emr2a_scores(const float* q, const float* db, int64_t Q, int64_t N, int D, int64_t ldq,
                             int64_t lddb, float* out, int64_t ld_out, void* stream) {

@@ -197,6 +197,19 @@ class Engine:
             self.launches += 1
         return keys
 
+    def segment_mean(self, x, offsets) -> torch.Tensor:
+        """Mean over the slices of each patient: rows [offsets[p], offsets[p+1]) of ``x`` -> row p."""
+        x = self.to_device(x, torch.float32)
+        off = self.to_device(offsets, torch.int64)
+        n_seg = int(off.shape[0]) - 1
+        out = torch.empty((max(n_seg, 0), x.shape[1]), dtype=torch.float32, device=self.device)
+        if n_seg > 0:
+            with torch.cuda.device(self.device):
+                native.check(self.lib.emr2a_segment_mean(x.data_ptr(), _ld(x), off.data_ptr(), n_seg, int(x.shape[1]),
+                                                         out.data_ptr(), int(x.shape[1]), self._stream()))
+            self.launches += 1
+        return out
+
     # --------------------------------------------------------------------- K2
     def pick_precision(self, Q: int, N: int, D: int, K: int, requested: str = "auto") -> str:
         req = os.environ.get("EMR2A_PRECISION", requested) if requested == "auto" else requested

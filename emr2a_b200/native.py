@@ -43,6 +43,7 @@ _SIGNATURES = {
     "emr2a_vote_metrics": (_int, [_p, _i64, _int, _p, _i64, _p, _p, _int, _int, C.POINTER(C.c_int32), _int, _int,
                                   _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "emr2a_topk_from_scores": (_int, [_p, _i64, _i64, _i64, _int, _p, _p]),
+    "emr2a_segment_mean": (_int, [_p, _i64, _p, _i64, _int, _p, _i64, _p]),
     # diagnostics (not part of the reference-facing surface)
     "emr2a_debug_topk_search_dump": (_int, [_p, _p, _p, _p, _i64, _i64, _int, _i64, _i64, _p, _p, _i64, _int, _int,
                                             _p, _p, _sz, _p, _p]),

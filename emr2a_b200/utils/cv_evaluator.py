@@ -236,6 +236,14 @@ class CVRetrievalEvaluator:
         """Fold loop + summary (utils/cv_evaluator.py:336-389)."""
         splits = self.stratified_split(patient_ids, labels)
         label_of = dict(zip(patient_ids, labels))
+        # the embeddings dict is stacked ONCE (the reference re-stacks N dict lookups per fold, :366-371);
+        # fold matrices are row gathers of these arrays -- identical values
+        row_of = {p: i for i, p in enumerate(patient_ids)}
+        all_img = all_txt = None
+        if fusion in {"concat", "image_only", "late"}:
+            all_img = np.stack([embeddings[p]["image"] for p in patient_ids])
+        if fusion in {"concat", "text_only", "late"}:
+            all_txt = np.stack([embeddings[p]["text"] for p in patient_ids])
         fold_results = []
         for fold, (train_ids, test_ids) in enumerate(splits):
             logger.info(f"Processing fold {fold + 1}/{self.cv_folds}")
@@ -247,14 +255,13 @@ class CVRetrievalEvaluator:
                 counts[lab] = counts.get(lab, 0) + 1
             logger.info(f"Train label distribution: {counts}")
 
-            def stack(ids, modality):
-                return np.stack([embeddings[p][modality] for p in ids])
-
+            tr_rows = [row_of[p] for p in train_ids]
+            te_rows = [row_of[p] for p in test_ids]
             tr_img = te_img = tr_txt = te_txt = None
             if fusion in {"concat", "image_only", "late"}:
-                tr_img, te_img = stack(train_ids, "image"), stack(test_ids, "image")
+                tr_img, te_img = all_img[tr_rows], all_img[te_rows]
             if fusion in {"concat", "text_only", "late"}:
-                tr_txt, te_txt = stack(train_ids, "text"), stack(test_ids, "text")
+                tr_txt, te_txt = all_txt[tr_rows], all_txt[te_rows]
             res = self.evaluate_fold(tr_img, tr_txt, te_img, te_txt, train_labels, test_labels, test_ids,
                                      fusion, top_k_list, w_text, train_ids)
             res["fold"] = fold + 1

@@ -208,6 +208,16 @@ int emr2a_vote_metrics(const uint64_t* keys, int64_t Q, int K,
                        unsigned long long* confusion, unsigned long long* group_sizes,
                        void* stream);
 
+/*
+ * Ingest: mean over the slices of each patient,
+ *   out[p, :] = mean(x[offsets[p] : offsets[p+1], :], axis=0)
+ * (pipelines/step3_retrieval/evaluate_retrieval.py:66-67 `embeddings[pid].mean(axis=0)`,
+ * analysis/run_cv_experiments.py:316-333 aggregate_embeddings).  x [total_slices, ld] fp32,
+ * offsets int64 [n_segments + 1] (device), slices added in order in fp32 then divided by the count.
+ */
+int emr2a_segment_mean(const float* x, int64_t ld, const int64_t* offsets, int64_t n_segments, int D,
+                       float* out, int64_t ld_out, void* stream);
+
 /* Top-K of a given score matrix (the *_from_scores helpers and get_all_top_labels,
  * retrieval/evaluator.py:195-208, 235-275): keys out [Q, K]. */
 int emr2a_topk_from_scores(const float* scores, int64_t Q, int64_t N, int64_t ld, int K,

@@ -451,3 +451,25 @@ def test_c4_bf16_inputs_wide_rows(eng, oracle):
         keys = eng.topk_search(qs, db, K, prec)
         eng.consume_status()
         _check_topk(oracle, keys, oq, odb, K, tol=tol)
+
+
+def test_ingest_mean_pool_and_loaders(eng, tmp_path):
+    """Slice mean-pool on the GPU equals numpy's ``arr.mean(axis=0)`` per patient bit for bit (the ingest of
+    pipelines/step3_retrieval/evaluate_retrieval.py:66-67), for ragged slice counts; both .npz layouts load."""
+    from emr2a_b200 import ingest
+    rng = np.random.default_rng(3)
+    per = [rng.standard_normal((int(rng.integers(1, 9)), 96)).astype(np.float32) * 3 for _ in range(57)]
+    per.append(rng.standard_normal(96).astype(np.float32))            # already pooled (ndim 1)
+    got = _np(ingest.mean_pool_patients(per))
+    want = np.stack([np.atleast_2d(a).mean(axis=0) for a in per])
+    assert got.dtype == np.float32 and np.array_equal(got, want)
+    ids = [f"p{i:03d}" for i in range(len(per) - 1)]
+    np.savez(tmp_path / "step2.npz", **{pid: a for pid, a in zip(ids, per[:-1])})
+    ids2, pooled = ingest.load_patient_npz(tmp_path / "step2.npz")
+    assert ids2 == ids and np.array_equal(_np(pooled), want[:-1])
+    np.savez(tmp_path / "cv.npz", patient_ids=np.array(ids, dtype=object), image_matrix=want[:-1], text_matrix=want[:-1] * 2)
+    m = ingest.load_matrix_npz(tmp_path / "cv.npz")
+    assert m["patient_ids"] == ids and np.array_equal(m["image"], want[:-1]) and np.array_equal(m["text"], want[:-1] * 2)
+    emb = {pid: {"image": want[i], "text": want[i] * 2} for i, pid in enumerate(ids)}
+    a, b = ingest.embeddings_to_arrays(ids, emb)
+    assert np.array_equal(a, want[:-1]) and np.array_equal(b, want[:-1] * 2)
