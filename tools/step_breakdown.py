@@ -6,7 +6,7 @@ sys.path.insert(0, REPO)
 from emr2a_b200 import native, synth
 from emr2a_b200.engine import get_engine
 eng = get_engine(); dev = eng.device
-n, d, q, k, c = 1_000_000, 512, 10_000, 10, 3
+n, d, q, k, c = int(os.environ.get("N", 1_000_000)), 512, 10_000, 10, 3
 flags = native.NF_SEGNORM | native.NF_ROWNORM
 di, _ = synth.device_block(0, n, d, c, 11, dev, label_seed=11); dt, _ = synth.device_block(0, n, d, c, 12, dev, label_seed=11)
 qi, ql = synth.device_block(50_003_968, q, d, c, 11, dev, label_seed=11); qt, _ = synth.device_block(50_003_968, q, d, c, 12, dev, label_seed=11)
