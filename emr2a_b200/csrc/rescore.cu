@@ -7,7 +7,8 @@
 // Bound:    |s~ - s| <= E = r_q * n_d + (n_q + r_q) * r_d + 1e-5 * n_q * n_d   for every pair, where
 //           n_* = max row norm and r_* = max ||row - bf16(row)|| over the queries / database rows
 //           (K1 `stats`, Cauchy-Schwarz on the two quantisation residuals; the last term covers
-//           the fp32 accumulation inside the tensor core).
+//           the fp32 accumulation inside the tensor core).  bf16 keeps 8 significant bits, so r ~ 1.7e-3 for a
+//           unit row and E ~ 4e-3.
 // Verify:   every row outside the candidate list has s~ <= tau (the KP-th approximate score), hence
 //           s <= tau + E.  If the exact K-th best candidate score exceeds tau + E strictly, no
 //           outside row can enter the Top-K and the selection is exact.  Otherwise the query is
@@ -252,7 +253,15 @@ __global__ void __launch_bounds__(256) rescan_merge_kernel(const RescoreParams p
 }
 
 int rescore_fallback_blocks() { return 2 * sm_count(); }
-int rescore_cap(int64_t Q) { return static_cast<int>(Q < 1024 ? Q : 1024); }
+// Capacity of the exact re-scan list.  A re-scan group (8 queries) streams the whole fp32 database once
+// (HBM-bound), the 3-pass tensor-core search of ALL queries costs about 0.04 * Q such groups, so beyond
+// ~4 % unverifiable queries handing the batch to BF16X3 (status[1]) is cheaper than re-scanning.
+int rescore_cap(int64_t Q) {
+  int64_t cap = Q / 25;
+  if (cap < 64) cap = 64;
+  if (cap > 1024) cap = 1024;
+  return static_cast<int>(cap < Q ? cap : Q);
+}
 
 size_t rescore_workspace_bytes(int64_t Q, int K) {
   const int cap = rescore_cap(Q);

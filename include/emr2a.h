@@ -151,7 +151,7 @@ int emr2a_late_fuse_scores(const float* text_scores, const float* image_scores, 
  * admissible rows are 0.
  * status_out (int32[4], nullable except for BF16_RESCORE; zero it before the call):
  *   [0] number of queries whose selection the error bound could not verify (they were re-searched
- *       exactly), [1] != 0: more such queries than the re-scan list holds (min(Q,1024)) -- the caller
+ *       exactly), [1] != 0: more such queries than the re-scan list holds (about 4 % of Q, 64..1024) -- the caller
  *       must repeat the call with EMR2A_PREC_BF16X3 or EMR2A_PREC_FP32.
  */
 size_t emr2a_topk_search_workspace_bytes(int64_t Q, int64_t N, int D, int K, int precision);

@@ -44,7 +44,11 @@ def test_search_matches_oracle_on_random_shapes(eng, oracle, q, n, d, k, arm, ma
     keys = eng.topk_search(eng.prepare(raw_q, flags=native.NF_ROWNORM, precision=arm),
                            eng.prepare(raw_db, flags=native.NF_ROWNORM, precision=arm), k, arm, **kw)
     unverified, overflow = eng.consume_status()
-    assert not overflow
+    if overflow:           # degenerate score ties (e.g. D = 1): the contract is "repeat with BF16X3", as the engine does
+        assert arm == "rescore"
+        arm = "bf16x3"
+        keys = eng.topk_search(eng.prepare(raw_q, flags=native.NF_ROWNORM, precision=arm),
+                               eng.prepare(raw_db, flags=native.NF_ROWNORM, precision=arm), k, arm, **kw)
     sc, idx = unpack_keys(keys)
     o_idx, o_sc = _reference_topk(oracle, qs, db, k, **okw)
     tol = 1e-5 if arm == "bf16x3" else 2e-6
