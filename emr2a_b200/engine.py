@@ -63,6 +63,7 @@ class Engine:
             self.sm_count, self.cc_major, self.cc_minor = native.device_check()
         self.launches = 0       # kernels of ours launched through this engine (bench reports it)
         self._status_log: List[torch.Tensor] = []   # status_out of rescore searches not yet checked
+        self._dense = set()     # (rows, dim) of databases whose score neighbourhoods defeated the rescore bound
 
     # ------------------------------------------------------------------ utils
     def _stream(self) -> int:
@@ -218,7 +219,7 @@ class Engine:
                 raise ValueError(f"unknown precision {req!r}")
             return req
         if float(Q) * float(N) * float(D) >= _TC_MIN_MACS:
-            if K <= _RESCORE_MAX_K:
+            if K <= _RESCORE_MAX_K and (N, D) not in self._dense:
                 return "rescore"
             if K <= 32:
                 return "bf16x3"
@@ -379,6 +380,7 @@ class Engine:
         if prec == "rescore":
             unverified, overflow = self.consume_status()      # the step's only host sync, after all work is queued
             if overflow:      # more unverifiable queries than the exact re-scan list holds: take the 3-pass arm
+                self._dense.add((n_db, dim))          # and remember it for this database shape ("auto" skips rescore)
                 return self.search_and_vote(db_segs, q_segs, db_labels, q_labels, n_classes, k, db_weights, q_weights,
                                             db_flags, q_flags, k_list, "bf16x3", wacc_f32, q_fold, db_fold, q_group,
                                             n_groups, want_lists)
