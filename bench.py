@@ -613,14 +613,17 @@ def main():
         line = {"metric": "queries/sec (cosine Top-K + vote)", "value": qps, "unit": "queries/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": {"bf16x3": "bf16x3 split (fp32-equivalent), fp32 accumulate", "bf16x1": "bf16, fp32 accumulate",
-                          "fp32": "f32", "rescore": "bf16 tensor-core filter (fp32 accumulate) + exact f32 rescoring, verified"}[res["precision"]],
+                "dtype": {"bf16x3": "bf16x3", "bf16x1": "bf16", "fp32": "f32", "rescore": "bf16+f32"}[res["precision"]],
                 "data": "synthetic",
                 "config": {"workload": f"{args.workload}: {n_db}-case database, {d_img}+{d_txt}-d "
                                        + ("late fusion (w_text=0.25, merge-then-Top-K)" if args.workload == "c3" else "concat fusion")
                                        + (" (bf16 in)" if in_dtype != torch.float32 else " (fp32 in)")
                                        + f", {n_q} queries, K={k}, {n_cls} classes",
                            "parallelism": f"database row-sharded x{world}, NCCL all-gather of local Top-K" if world > 1 else "single GPU",
+                           "arithmetic": {"bf16x3": "tcgen05 bf16 2-way split (hi*lo + lo*hi + hi*hi), fp32 accumulate",
+                                          "bf16x1": "tcgen05 bf16 operands, fp32 accumulate", "fp32": "CUDA-core fp32 FMA",
+                                          "rescore": "tcgen05 bf16 filter (fp32 accumulate) + exact f32 re-scoring of the "
+                                                     "candidates, selection verified by an error bound"}[res["precision"]],
                            "l2": "inputs (multi-GB database) larger than L2; no flush needed",
                            "step": "K1 normalise+fuse (db shard + queries) -> K2 GEMM+Top-K -> K3 merge -> K4 vote"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
