@@ -48,7 +48,7 @@ size_t rescore_workspace_bytes(int64_t Q, int K);
 int rescore_pipeline(const uint64_t* approx, int KP, const uint32_t* tau, const float* q, int64_t ldq, const float* db,
                      int64_t lddb, int64_t Q, int64_t N, int D, int64_t idx_base, int K, const float* q_stats,
                      const float* db_stats, const uint8_t* q_fold, const uint8_t* db_fold, uint64_t* out_keys,
-                     int* status, void* workspace, size_t ws_bytes, cudaStream_t st);
+                     int* status, uint8_t* qflags, void* workspace, size_t ws_bytes, cudaStream_t st);
 
 constexpr int RESCORE_KP = 32;    // candidates kept per (query, database split) by the filter; 16 leaves too little slack (measured)
 constexpr int RESCORE_KPM = 64;   // candidates per query re-scored after merging the splits
@@ -96,7 +96,8 @@ static int topk_search_impl(const float* q_f32, int64_t ldq_f32, const uint16_t*
                             const uint16_t* db_lo, int64_t lddb_bf16, int64_t Q, int64_t N, int D,
                             const uint8_t* q_fold, const uint8_t* db_fold, int fold_sorted, int64_t idx_base, int K,
                             int precision, const float* q_stats, const float* db_stats, uint64_t* out_keys,
-                            int32_t* status, void* workspace, size_t ws_bytes, float* debug_scores, void* stream) {
+                            int32_t* status, uint8_t* qflags, void* workspace, size_t ws_bytes, float* debug_scores,
+                            void* stream) {
   if (Q < 0 || N < 0 || D <= 0 || K <= 0 || !out_keys) return fail(EMR2A_ERR_INVALID, "topk_search: bad arguments (Q=%lld N=%lld D=%d K=%d)", (long long)Q, (long long)N, D, K);
   if ((q_fold == nullptr) != (db_fold == nullptr)) return fail(EMR2A_ERR_INVALID, "topk_search: q_fold and db_fold must be given together");
   if (idx_base < 0) return fail(EMR2A_ERR_INVALID, "topk_search: negative idx_base");
@@ -148,7 +149,7 @@ static int topk_search_impl(const float* q_f32, int64_t ldq_f32, const uint16_t*
         cand = approx;
       }
       return rescore_pipeline(cand, kpm, parts.tau, q_f32, ldq_f32, db_f32, lddb_f32, Q, N, D, idx_base, K, q_stats,
-                              db_stats, q_fold, db_fold, out_keys, status, ws + a_bytes + t_bytes, r_bytes, st);
+                              db_stats, q_fold, db_fold, out_keys, status, qflags, ws + a_bytes + t_bytes, r_bytes, st);
     }
     default:
       return fail(EMR2A_ERR_INVALID, "topk_search: unknown precision %d", precision);
@@ -160,11 +161,11 @@ extern "C" int emr2a_topk_search(const float* q_f32, int64_t ldq_f32, const uint
                                  const uint16_t* db_lo, int64_t lddb_bf16, int64_t Q, int64_t N, int D,
                                  const uint8_t* q_fold, const uint8_t* db_fold, int fold_sorted, int64_t idx_base,
                                  int K, int precision, const float* q_stats, const float* db_stats,
-                                 uint64_t* out_keys, int32_t* status_out, void* workspace, size_t ws_bytes,
-                                 void* stream) {
+                                 uint64_t* out_keys, int32_t* status_out, uint8_t* unverified_out, void* workspace,
+                                 size_t ws_bytes, void* stream) {
   return topk_search_impl(q_f32, ldq_f32, q_hi, q_lo, ldq_bf16, db_f32, lddb_f32, db_hi, db_lo, lddb_bf16, Q, N, D,
                           q_fold, db_fold, fold_sorted, idx_base, K, precision, q_stats, db_stats, out_keys,
-                          status_out, workspace, ws_bytes, nullptr, stream);
+                          status_out, unverified_out, workspace, ws_bytes, nullptr, stream);
 }
 
 // Diagnostics: same as emr2a_topk_search on the tensor-core arms, additionally dumping every
@@ -177,6 +178,6 @@ extern "C" int emr2a_debug_topk_search_dump(const uint16_t* q_hi, const uint16_t
   if (precision != EMR2A_PREC_BF16X3 && precision != EMR2A_PREC_BF16X1)
     return fail(EMR2A_ERR_INVALID, "debug dump is for the tensor-core arms only");
   return topk_search_impl(nullptr, 0, q_hi, q_lo, ldq, nullptr, 0, db_hi, db_lo, lddb, Q, N, D, q_fold, db_fold, 0,
-                          idx_base, K, precision, nullptr, nullptr, out_keys, nullptr, workspace, ws_bytes,
+                          idx_base, K, precision, nullptr, nullptr, out_keys, nullptr, nullptr, workspace, ws_bytes,
                           debug_scores, stream);
 }

@@ -35,6 +35,7 @@ struct RescoreParams {
   int* status;              // [0] = #unverified queries, [1] = flag list overflow
   int* flag_list;
   int cap;
+  uint8_t* qflags;          // optional [Q]: 1 = selection not verified by the bound (valid even when the list overflows)
   // exact re-scan
   const uint8_t* q_fold;
   const uint8_t* db_fold;
@@ -145,14 +146,16 @@ __global__ void __launch_bounds__(256) rescore_select_kernel(const RescoreParams
     const uint32_t t = __ldcg(p.tau + q);
     if (t != 0u) { tau = fmaxf(tau, unorder_f32(t)); bounded = true; }
   }
+  bool ok = true;
   if (bounded) {
     const uint64_t kth = __shfl_sync(0xffffffffu, mine, p.K - 1);
-    const bool ok = kth != 0ull && key_score(kth) > tau + E;
+    ok = kth != 0ull && key_score(kth) > tau + E;
     if (!ok && lane == 0) {
       const int i = atomicAdd(&p.status[0], 1);
       if (i < p.cap) p.flag_list[i] = static_cast<int>(q); else p.status[1] = 1;
     }
   }
+  if (p.qflags != nullptr && lane == 0) p.qflags[q] = ok ? 0 : 1;
 }
 
 // Exact re-search of the flagged queries against every database row (fp32, CUDA cores).  A block
@@ -273,7 +276,7 @@ size_t rescore_workspace_bytes(int64_t Q, int K) {
 int rescore_pipeline(const uint64_t* approx, int KP, const uint32_t* tau, const float* q, int64_t ldq, const float* db,
                      int64_t lddb, int64_t Q, int64_t N, int D, int64_t idx_base, int K, const float* q_stats,
                      const float* db_stats, const uint8_t* q_fold, const uint8_t* db_fold, uint64_t* out_keys,
-                     int* status, void* workspace, size_t ws_bytes, cudaStream_t st) {
+                     int* status, uint8_t* qflags, void* workspace, size_t ws_bytes, cudaStream_t st) {
   if (!q_stats || !db_stats) return fail(EMR2A_ERR_INVALID, "topk_search(rescore): q_stats/db_stats (K1 stats) required");
   if (!status) return fail(EMR2A_ERR_INVALID, "topk_search(rescore): status_out required");
   if (rescore_workspace_bytes(Q, K) > ws_bytes) return fail(EMR2A_ERR_WORKSPACE, "topk_search(rescore): workspace too small");
@@ -281,6 +284,7 @@ int rescore_pipeline(const uint64_t* approx, int KP, const uint32_t* tau, const 
   p.approx = approx; p.KP = KP; p.tau = tau; p.q = q; p.ldq = ldq; p.db = db; p.lddb = lddb; p.Q = Q; p.N = N; p.D = D;
   p.idx_base = idx_base; p.K = K; p.q_stats = q_stats; p.db_stats = db_stats; p.out = out_keys; p.status = status;
   p.cap = rescore_cap(Q);
+  p.qflags = qflags;
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   p.flag_list = reinterpret_cast<int*>(ws);
   const size_t off = (sizeof(int) * static_cast<size_t>(p.cap) + 255) & ~static_cast<size_t>(255);

@@ -64,6 +64,7 @@ class Engine:
         self.launches = 0       # kernels of ours launched through this engine (bench reports it)
         self._status_log: List[torch.Tensor] = []   # status_out of rescore searches not yet checked
         self._dense = set()     # (rows, dim) of databases whose score neighbourhoods defeated the rescore bound
+        self.last_unverified: Optional[torch.Tensor] = None   # uint8 [Q] of the latest rescore search
 
     # ------------------------------------------------------------------ utils
     def _stream(self) -> int:
@@ -262,6 +263,7 @@ class Engine:
             if k > _RESCORE_MAX_K:
                 raise ValueError(f"topk_search(rescore): K={k} > {_RESCORE_MAX_K}")
             status = torch.zeros((4,), dtype=torch.int32, device=self.device)
+            self.last_unverified = torch.empty((Q,), dtype=torch.uint8, device=self.device)
         if q_fold is not None:
             q_fold = self.to_device(q_fold, torch.uint8)
             db_fold = self.to_device(db_fold, torch.uint8)
@@ -273,7 +275,8 @@ class Engine:
                 native.ptr(db.hi), native.ptr(db.lo), _ld(db.hi) if db.hi is not None else 0,
                 Q, N, D, native.ptr(q_fold), native.ptr(db_fold), int(fold_sorted),
                 int(idx_base), int(k), prec, native.ptr(q.stats), native.ptr(db.stats),
-                keys.data_ptr(), native.ptr(status), ws_ptr, ws_bytes, self._stream()))
+                keys.data_ptr(), native.ptr(status), native.ptr(self.last_unverified if status is not None else None),
+                ws_ptr, ws_bytes, self._stream()))
         self.launches += 2 if status is None else 6
         if status is not None:
             self._status_log.append(status)
@@ -379,11 +382,26 @@ class Engine:
                                 q_group=q_group, n_groups=n_groups, want_lists=want_lists)
         if prec == "rescore":
             unverified, overflow = self.consume_status()      # the step's only host sync, after all work is queued
-            if overflow:      # more unverifiable queries than the exact re-scan list holds: take the 3-pass arm
-                self._dense.add((n_db, dim))          # and remember it for this database shape ("auto" skips rescore)
-                return self.search_and_vote(db_segs, q_segs, db_labels, q_labels, n_classes, k, db_weights, q_weights,
-                                            db_flags, q_flags, k_list, "bf16x3", wacc_f32, q_fold, db_fold, q_group,
-                                            n_groups, want_lists)
+            if overflow:
+                # More unverifiable queries than the exact re-scan list holds (dense score neighbourhoods):
+                # re-search ONLY those queries with the 3-pass arm, patch their keys, vote again.
+                flagged = torch.nonzero(self.last_unverified).squeeze(1)
+                if int(flagged.numel()) * 2 > n_q:
+                    self._dense.add((n_db, dim))      # mostly unverifiable: "auto" goes straight to bf16x3 next time
+                q_dev = [self._embedding(s)[0].index_select(0, flagged) for s in q_segs if s is not None]
+                db3 = self.prepare(db_segs[0], db_segs[1] if len(db_segs) > 1 else None, db_weights[0], db_weights[1],
+                                   db_flags, "bf16x3")
+                qs3 = self.prepare(q_dev[0], q_dev[1] if len(q_dev) > 1 else None, q_weights[0], q_weights[1], q_flags,
+                                   "bf16x3")
+                qf = self.to_device(q_fold, torch.uint8).index_select(0, flagged) if q_fold is not None else None
+                keys3 = self.topk_search(qs3, db3, k, "bf16x3", q_fold=qf, db_fold=db_fold)
+                keys.index_copy_(0, flagged, keys3)
+                res = self.vote_metrics(keys, db_labels, q_labels, n_classes, k_list=k_list, wacc_f32=wacc_f32,
+                                        q_group=q_group, n_groups=n_groups, want_lists=want_lists)
+                res["precision"] = "rescore+bf16x3"
+                res["unverified"] = int(flagged.numel())
+                res["keys"] = keys
+                return res
             res["unverified"] = unverified
         res["keys"] = keys
         res["precision"] = prec

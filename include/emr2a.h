@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define EMR2A_ABI_VERSION 4
+#define EMR2A_ABI_VERSION 5
 
 enum emr2a_status {
   EMR2A_OK = 0,
@@ -152,7 +152,10 @@ int emr2a_late_fuse_scores(const float* text_scores, const float* image_scores, 
  * status_out (int32[4], nullable except for BF16_RESCORE; zero it before the call):
  *   [0] number of queries whose selection the error bound could not verify (they were re-searched
  *       exactly), [1] != 0: more such queries than the re-scan list holds (about 4 % of Q, 64..1024) -- the caller
- *       must repeat the call with EMR2A_PREC_BF16X3 or EMR2A_PREC_FP32.
+ *       must repeat the call with EMR2A_PREC_BF16X3 or EMR2A_PREC_FP32, for all queries or only for those
+ *       marked in unverified_out.
+ * unverified_out (uint8 [Q], nullable, BF16_RESCORE only): 1 for every query the bound could not verify
+ *   (complete even when the re-scan list overflowed), 0 otherwise.
  */
 size_t emr2a_topk_search_workspace_bytes(int64_t Q, int64_t N, int D, int K, int precision);
 int emr2a_topk_search(const float* q_f32, int64_t ldq_f32,
@@ -163,7 +166,7 @@ int emr2a_topk_search(const float* q_f32, int64_t ldq_f32,
                       const uint8_t* q_fold, const uint8_t* db_fold, int fold_sorted,
                       int64_t idx_base, int K, int precision,
                       const float* q_stats, const float* db_stats,
-                      uint64_t* out_keys, int32_t* status_out,
+                      uint64_t* out_keys, int32_t* status_out, uint8_t* unverified_out,
                       void* workspace, size_t ws_bytes, void* stream);
 
 /*

@@ -210,7 +210,7 @@ def test_rescore_unverifiable_queries_are_rescanned_exactly(eng, oracle):
 
 def test_rescore_overflow_falls_back_to_three_pass(eng, oracle):
     """Every query unverifiable (database = one tight cluster) and more queries than the re-scan list
-    holds: the engine must notice the overflow flag and redo the search with the BF16X3 arm."""
+    holds: the engine must notice the overflow flag and re-search the unverified queries with the BF16X3 arm."""
     from emr2a_b200.engine import unpack_keys
     rng = np.random.default_rng(5)
     N, Q, D, K = 3000, 1500, 128, 5
@@ -219,7 +219,7 @@ def test_rescore_overflow_falls_back_to_three_pass(eng, oracle):
     qs = oracle.unit_rows((c + 0.05 * rng.standard_normal((Q, D))).astype(np.float32))
     labels = rng.integers(0, 3, N).astype(np.int32)
     r = eng.search_and_vote((db,), (qs,), labels, labels[:Q], 3, K, db_flags=0, q_flags=0, precision="rescore")
-    assert r["precision"] == "bf16x3"
+    assert r["precision"] == "rescore+bf16x3" and r["unverified"] > 1400
     _check_topk(oracle, r["keys"], qs, db, K, tol=SCORE_TOL, min_safe=0.0)     # a tight cluster has few clear gaps
     # below the capacity (64 for small batches) the exact re-scan handles all of them
     r = eng.search_and_vote((db,), (qs[:60],), labels, labels[:60], 3, K, db_flags=0, q_flags=0, precision="rescore")
@@ -478,14 +478,15 @@ def test_ingest_mean_pool_and_loaders(eng, tmp_path):
 def test_rescore_on_clustered_database_matches_fp32_arm(eng):
     """Real embedding sets are clustered (near-duplicate cases, often stored contiguously).  Small clusters fit
     into the per-split candidate lists and verify.  Clusters larger than a split's list (16/32 rows within the
-    filter's error band 2E ~ 8e-3) cannot be verified: nearly every query is flagged, the re-scan list overflows
-    and the engine hands the batch to the BF16X3 arm.  Either way the result must equal the fp32 arm's."""
+    filter's error band 2E ~ 8e-3) cannot be verified: those queries are flagged, the re-scan list overflows
+    and the engine re-searches the flagged queries with the BF16X3 arm.  Either way the result must equal the
+    fp32 arm's."""
     import torch
     from emr2a_b200 import native
     from emr2a_b200.engine import unpack_keys
     g = torch.Generator(device="cuda").manual_seed(5)
     D, Q, K = 256, 1500, 10
-    for n_clusters, per, noise, expect in ((2500, 8, 0.05, "rescore"), (400, 250, 0.02, "bf16x3")):
+    for n_clusters, per, noise, expect in ((2500, 8, 0.05, "rescore"), (400, 250, 0.02, "rescore+bf16x3")):
         centres = torch.randn((n_clusters, D), generator=g, device="cuda")
         db = centres.repeat_interleave(per, dim=0) + noise * torch.randn((n_clusters * per, D), generator=g, device="cuda")
         pick = torch.randint(0, n_clusters, (Q,), generator=g, device="cuda")
@@ -501,3 +502,30 @@ def test_rescore_on_clustered_database_matches_fp32_arm(eng):
         assert np.array_equal(i32 // per, ir // per)             # neighbours come from the query's own cluster
         gaps = np.abs(np.diff(s32, axis=1)).min(axis=1) > 2 * tol
         assert np.array_equal(i32[gaps], ir[gaps])
+
+
+def test_rescore_partial_overflow_only_flagged_queries_are_redone(eng):
+    """A batch where a minority of the queries sits in large tight clusters: those (and only those) are
+    re-searched with BF16X3; everything else keeps its verified fp32 result."""
+    import torch
+    from emr2a_b200 import native
+    from emr2a_b200.engine import unpack_keys
+    g = torch.Generator(device="cuda").manual_seed(11)
+    D, K = 128, 5
+    base = torch.randn((60_000, D), generator=g, device="cuda")
+    c = torch.randn((4, D), generator=g, device="cuda")
+    blob = c.repeat_interleave(300, dim=0) + 0.01 * torch.randn((1200, D), generator=g, device="cuda")
+    db = torch.cat([base, blob])
+    q_easy = torch.randn((1400, D), generator=g, device="cuda")
+    q_hard = c[torch.randint(0, 4, (200,), generator=g, device="cuda")] + 0.01 * torch.randn((200, D), generator=g, device="cuda")
+    qs = torch.cat([q_easy, q_hard])
+    labels = torch.zeros((db.shape[0],), dtype=torch.int32, device="cuda")
+    ql = torch.zeros((qs.shape[0],), dtype=torch.int32, device="cuda")
+    ref = eng.search_and_vote((db,), (qs,), labels, ql, 1, K, precision="fp32")
+    got = eng.search_and_vote((db,), (qs,), labels, ql, 1, K, precision="rescore")
+    assert got["precision"] == "rescore+bf16x3" and 200 <= got["unverified"] < 400
+    (s32, i32), (sr, ir) = unpack_keys(ref["keys"]), unpack_keys(got["keys"])
+    assert np.max(np.abs(s32 - sr)[:1400]) < F32_TOL and np.max(np.abs(s32 - sr)) < SCORE_TOL
+    gaps = np.abs(np.diff(s32, axis=1)).min(axis=1) > 2 * SCORE_TOL
+    assert np.array_equal(i32[gaps], ir[gaps]) and gaps[:1400].mean() > 0.95
+    assert np.all(ir[1400:] >= 60_000)                         # hard queries retrieve from the blobs
