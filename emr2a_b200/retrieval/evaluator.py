@@ -6,6 +6,7 @@ of the reference (cosine -> argsort -> label compare, once per k) are replaced b
 one K1 -> K2 -> K4 pass per metric family on the GPU; StandardScaler / PCA and the
 python-``random`` split stay on the host exactly as in the reference.
 """
+import os
 import random
 from typing import Dict, List, Optional, Tuple
 
@@ -50,10 +51,34 @@ class RetrievalEvaluator:
             train += members[cut:]
         return train, test
 
+    preprocess: str = os.environ.get("EMR2A_PREPROCESS", "host")
+
+    def _preprocess_on_gpu(self, n_train: int, n_features: int) -> bool:
+        mode = self.preprocess
+        if mode not in ("host", "gpu", "auto"):
+            raise ValueError(f"unknown preprocess mode {mode!r} (host, gpu, auto)")
+        if mode != "auto":
+            return mode == "gpu"
+        from ..preprocess import sklearn_solver
+        n_comp = min(self.pca_dim, n_train - 1, n_features) if self.use_pca else 0
+        return n_comp <= 0 or sklearn_solver(n_train, n_features, n_comp) != "randomized"
+
     def process_embeddings(self, train_embeddings: np.ndarray, test_embeddings: np.ndarray
                            ) -> Tuple[np.ndarray, np.ndarray]:
-        """StandardScaler (+ PCA when ``use_pca``) fitted on train (host, sklearn --
-        retrieval/evaluator.py:50-73), row normalisation on the GPU (K1)."""
+        """StandardScaler (+ PCA when ``use_pca``) fitted on train (retrieval/evaluator.py:50-73), row
+        normalisation by K1.  Runs on the device under the same rule as
+        ``CVRetrievalEvaluator.preprocess`` (env ``EMR2A_PREPROCESS``: host / gpu / auto), else sklearn on the host."""
+        train_embeddings = np.asarray(train_embeddings)
+        test_embeddings = np.asarray(test_embeddings)
+        if train_embeddings.ndim == 2 and self._preprocess_on_gpu(*train_embeddings.shape):
+            from .. import preprocess as pp
+            eng = get_engine()
+            tf = pp.fit(train_embeddings, self.pca_dim if self.use_pca else None, eng)
+            tr = pp.transform(tf, train_embeddings, eng).cpu().numpy()
+            te = pp.transform(tf, test_embeddings, eng).cpu().numpy()
+            if train_embeddings.dtype == np.float64:
+                tr, te = tr.astype(np.float64), te.astype(np.float64)
+            return tr, te
         scaler = StandardScaler()
         tr = scaler.fit_transform(train_embeddings)
         te = scaler.transform(test_embeddings)

@@ -4,12 +4,15 @@ Same constructor, methods, argument order, defaults, result keys, file formats a
 errors as the reference class (utils/cv_evaluator.py:26-501).  Inside a fold, everything
 after ``process_embeddings`` -- fusion, similarity, Top-K, votes, hit flags and confusion
 counts (reference lines 186-310, a per-query python loop) -- is one K1 -> K2 -> K4 pass
-on the GPU.  StratifiedKFold / StandardScaler / PCA stay on the host (sklearn) exactly
-as in the reference, so the fold membership and the preprocessing are identical.
+on the GPU.  StratifiedKFold stays sklearn-on-host (identical fold membership).  The per-fold
+StandardScaler + PCA run either on the host with sklearn, exactly as the reference does, or on the
+GPU (``emr2a_b200.preprocess``: hand-written moment / standardise kernels + an exact float64
+eigen-decomposition) -- see ``CVRetrievalEvaluator.preprocess``.
 """
 import csv
 import json
 import logging
+import os
 import random
 from pathlib import Path
 from typing import Dict, List, Optional, Tuple
@@ -32,6 +35,16 @@ _SUMMARY_METRICS = ("top1", "top3", "top5", "vote_acc", "weighted_vote_acc",
 
 
 class CVRetrievalEvaluator:
+    #: where StandardScaler + PCA of ``process_embeddings`` run (env ``EMR2A_PREPROCESS``, default "host"):
+    #:   "host"  sklearn on the CPU, as the reference (bit-for-bit its preprocessing, given the same numpy seed);
+    #:   "gpu"   emr2a_b200.preprocess: scaler identical to sklearn's, PCA = the deterministic exact basis
+    #:           (float64), all on the device.  sklearn's own fp32 solvers sit 1e-6 ("covariance_eigh") to
+    #:           2e-4 ("full") from that basis on the golden folds, its unseeded "randomized" solver further;
+    #:   "auto"  "gpu" whenever sklearn itself would use a deterministic solver for the fold's shape
+    #:           ("full" / "covariance_eigh"), "host" where it picks the unseeded *randomized* solver, so a
+    #:           seeded reference run can still be reproduced exactly.
+    preprocess: str = os.environ.get("EMR2A_PREPROCESS", "host")
+
     def __init__(self, cv_folds: int = 5, pca_dim: int = 128, top_k: int = 5, seed: int = 42):
         self.cv_folds = cv_folds
         self.pca_dim = pca_dim
@@ -39,6 +52,16 @@ class CVRetrievalEvaluator:
         self.seed = seed
         self.rng = np.random.RandomState(seed)
         self.random = random.Random(seed)
+
+    def _preprocess_on_gpu(self, n_train: int, n_features: int) -> bool:
+        mode = self.preprocess
+        if mode not in ("host", "gpu", "auto"):
+            raise ValueError(f"unknown preprocess mode {mode!r} (host, gpu, auto)")
+        if mode != "auto":
+            return mode == "gpu"
+        from ..preprocess import sklearn_solver
+        n_comp = min(self.pca_dim, n_train - 1, n_features)
+        return n_comp <= 0 or sklearn_solver(n_train, n_features, n_comp) != "randomized"
 
     # ------------------------------------------------------------------ host
     def stratified_split(self, patient_ids: List[str], labels: List[str]) -> List[Tuple[List[str], List[str]]]:
@@ -66,8 +89,16 @@ class CVRetrievalEvaluator:
 
     def process_embeddings(self, train_embeddings: np.ndarray, test_embeddings: np.ndarray
                            ) -> Tuple[np.ndarray, np.ndarray]:
-        """StandardScaler -> PCA(min(pca_dim, n-1, D)) fitted on the train fold (host,
-        sklearn: utils/cv_evaluator.py:73-93), then row normalisation on the GPU."""
+        """StandardScaler -> PCA(min(pca_dim, n-1, D)) fitted on the train fold
+        (utils/cv_evaluator.py:73-93), then row normalisation (K1).  Device or host, see ``preprocess``."""
+        train_embeddings = np.asarray(train_embeddings)
+        test_embeddings = np.asarray(test_embeddings)
+        if train_embeddings.ndim == 2 and self._preprocess_on_gpu(*train_embeddings.shape):
+            tr, te = self.process_embeddings_device(train_embeddings, test_embeddings)
+            tr, te = tr.cpu().numpy(), te.cpu().numpy()
+            if train_embeddings.dtype == np.float64:
+                tr, te = tr.astype(np.float64), te.astype(np.float64)
+            return tr, te
         scaler = StandardScaler()
         tr = scaler.fit_transform(train_embeddings)
         te = scaler.transform(test_embeddings)
@@ -77,6 +108,13 @@ class CVRetrievalEvaluator:
             tr = pca.fit_transform(tr)
             te = pca.transform(te)
         return self._normalize_rows(tr), self._normalize_rows(te)
+
+    def process_embeddings_device(self, train_embeddings, test_embeddings):
+        """``process_embeddings`` entirely on the device (host or device arrays in, device tensors out)."""
+        from .. import preprocess as pp
+        eng = get_engine()
+        tf = pp.fit(train_embeddings, self.pca_dim, eng)
+        return pp.transform(tf, train_embeddings, eng), pp.transform(tf, test_embeddings, eng)
 
     # ------------------------------------------------------- GPU primitives
     def _normalize_rows(self, arr: np.ndarray) -> np.ndarray:
@@ -159,10 +197,17 @@ class CVRetrievalEvaluator:
         if top_k_list is None:
             top_k_list = [1, 3, 5, self.top_k]
         tr_img = te_img = tr_txt = te_txt = None
+
+        def process(train, test):
+            shape = tuple(train.shape)
+            if len(shape) == 2 and self._preprocess_on_gpu(*shape):
+                return self.process_embeddings_device(train, test)      # stays in HBM for the search
+            return self.process_embeddings(np.asarray(train), np.asarray(test))
+
         if train_img is not None and test_img is not None:
-            tr_img, te_img = self.process_embeddings(train_img, test_img)
+            tr_img, te_img = process(train_img, test_img)
         if train_txt is not None and test_txt is not None:
-            tr_txt, te_txt = self.process_embeddings(train_txt, test_txt)
+            tr_txt, te_txt = process(train_txt, test_txt)
         return self.evaluate_processed_fold(tr_img, tr_txt, te_img, te_txt, train_labels, test_labels, test_ids,
                                             fusion, top_k_list, w_text, train_ids)
 
@@ -244,6 +289,22 @@ class CVRetrievalEvaluator:
             all_img = np.stack([embeddings[p]["image"] for p in patient_ids])
         if fusion in {"concat", "text_only", "late"}:
             all_txt = np.stack([embeddings[p]["text"] for p in patient_ids])
+        # folds preprocessed on the device: upload each modality once, fold matrices are device row gathers
+        n_train0 = len(splits[0][0]) if splits else 0
+        eng = None
+        if all_img is not None and self._preprocess_on_gpu(n_train0, all_img.shape[1]):
+            eng = get_engine()
+            all_img = eng.to_device(all_img.astype(np.float32, copy=False))
+        if all_txt is not None and self._preprocess_on_gpu(n_train0, all_txt.shape[1]):
+            eng = get_engine()
+            all_txt = eng.to_device(all_txt.astype(np.float32, copy=False))
+
+        def rows_of(mat, rows):
+            if isinstance(mat, np.ndarray):
+                return mat[rows]
+            import torch
+            return mat.index_select(0, torch.as_tensor(rows, dtype=torch.int64, device=mat.device))
+
         fold_results = []
         for fold, (train_ids, test_ids) in enumerate(splits):
             logger.info(f"Processing fold {fold + 1}/{self.cv_folds}")
@@ -259,9 +320,9 @@ class CVRetrievalEvaluator:
             te_rows = [row_of[p] for p in test_ids]
             tr_img = te_img = tr_txt = te_txt = None
             if fusion in {"concat", "image_only", "late"}:
-                tr_img, te_img = all_img[tr_rows], all_img[te_rows]
+                tr_img, te_img = rows_of(all_img, tr_rows), rows_of(all_img, te_rows)
             if fusion in {"concat", "text_only", "late"}:
-                tr_txt, te_txt = all_txt[tr_rows], all_txt[te_rows]
+                tr_txt, te_txt = rows_of(all_txt, tr_rows), rows_of(all_txt, te_rows)
             res = self.evaluate_fold(tr_img, tr_txt, te_img, te_txt, train_labels, test_labels, test_ids,
                                      fusion, top_k_list, w_text, train_ids)
             res["fold"] = fold + 1

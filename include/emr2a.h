@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define EMR2A_ABI_VERSION 5
+#define EMR2A_ABI_VERSION 6
 
 enum emr2a_status {
   EMR2A_OK = 0,
@@ -220,6 +220,25 @@ int emr2a_vote_metrics(const uint64_t* keys, int64_t Q, int K,
  */
 int emr2a_segment_mean(const float* x, int64_t ld, const int64_t* offsets, int64_t n_segments, int D,
                        float* out, int64_t ld_out, void* stream);
+
+/*
+ * Per-fold preprocessing (StandardScaler -> PCA fitted on the train fold: utils/cv_evaluator.py:73-93,
+ * retrieval/evaluator.py:44-73) -- the two HBM-bound passes; the D x D covariance / projection GEMMs and the
+ * symmetric eigen-decomposition are library calls made by the host layer (emr2a_b200/preprocess.py).
+ *
+ * emr2a_column_moments: sum[c] = SUM_r (x[r,c] - shift[c]), sumsq[c] = SUM_r (x[r,c] - shift[c])^2 over the n rows,
+ *   accumulated in float64 (StandardScaler reduces float32 input in float64: sklearn _incremental_mean_and_var).
+ *   shift (float[D], nullable = 0) guards the variance against cancellation.  Deterministic: fixed row partition,
+ *   ordered second stage, no atomics.  workspace: emr2a_column_moments_workspace_bytes(n, D), 8-byte aligned.
+ * emr2a_standardize: out[r,c] = (x[r,c] - mean[c]) / scale[c] in IEEE fp32, mean/scale already cast to float32 --
+ *   the arithmetic of StandardScaler.transform on a float32 array (`X -= astype(mean_, X.dtype); X /= astype(scale_,
+ *   X.dtype)`).  out may alias x.
+ */
+size_t emr2a_column_moments_workspace_bytes(int64_t n, int D);
+int emr2a_column_moments(const float* x, int64_t ld, int64_t n, int D, const float* shift,
+                         double* sum, double* sumsq, void* workspace, size_t ws_bytes, void* stream);
+int emr2a_standardize(const float* x, int64_t ld, int64_t n, int D, const float* mean, const float* scale,
+                      float* out, int64_t ld_out, void* stream);
 
 /* Top-K of a given score matrix (the *_from_scores helpers and get_all_top_labels,
  * retrieval/evaluator.py:195-208, 235-275): keys out [Q, K]. */

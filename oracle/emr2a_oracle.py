@@ -409,3 +409,73 @@ def reference_style_search_and_vote(qs: np.ndarray, db: np.ndarray, db_labels: n
     return {"top_idx": idx_all, "pred_top1": top1, "pred_vote": vote, "pred_weighted": wvote,
             "top1": float(np.mean(top1 == q_labels)), "vote_acc": float(np.mean(vote == q_labels)),
             "weighted_vote_acc": float(np.mean(wvote == q_labels))}
+
+
+# --------------------------------------------------------------------------
+# per-fold preprocessing: StandardScaler -> PCA -> row normalisation
+# --------------------------------------------------------------------------
+# The arithmetic lives in scikit-learn (un-vendored, unpinned by the reference's
+# requirements.txt:1-18; this container has 1.9.0, tests/golden/VERSIONS.json).  The restatement
+# below follows sklearn's published algorithm:
+#   StandardScaler  float64 column mean and population variance (_incremental_mean_and_var reduces float32 input
+#                   in float64), near-constant features get scale 1 (_is_constant_feature), and transform works
+#                   in the dtype of X: `X -= astype(mean_, X.dtype); X /= astype(scale_, X.dtype)`;
+#   PCA             principal axes of the centred data ordered by decreasing variance, sign fixed by
+#                   svd_flip(u_based_decision=False); transform = X @ components^T - mean @ components^T.
+# The basis is computed in float64 (covariance + symmetric eigen-decomposition), i.e. the exact answer that
+# sklearn's "full" and "covariance_eigh" solvers approximate in fp32 and its unseeded "randomized" solver
+# (picked by "auto" for mid-sized folds, utils/cv_evaluator.py:89) approximates differently on every run.
+# Pinned by tests/test_oracle_golden.py against sklearn itself and against the reference's process_embeddings
+# outputs stored in tests/golden/cv_small.npz (240 x 48 / 240 x 40 folds -> sklearn's "full" solver).
+def scaler_fit(train: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """(mean_, scale_) of StandardScaler.fit, float64 (utils/cv_evaluator.py:78-79)."""
+    x = np.asarray(train, dtype=np.float64)
+    n = x.shape[0]
+    mean = x.sum(axis=0) / n
+    dev = x - mean
+    var = ((dev ** 2).sum(axis=0) - dev.sum(axis=0) ** 2 / n) / n
+    eps = np.finfo(np.float64).eps
+    constant = var <= n * eps * var + (n * mean * eps) ** 2
+    scale = np.sqrt(var)
+    scale[constant] = 1.0
+    return mean, scale
+
+
+def scaler_apply(x: np.ndarray, mean: np.ndarray, scale: np.ndarray) -> np.ndarray:
+    """StandardScaler.transform in the dtype of ``x`` (utils/cv_evaluator.py:79-80)."""
+    x = np.array(x, copy=True)
+    x -= mean.astype(x.dtype)
+    x /= scale.astype(x.dtype)
+    return x
+
+
+def pca_exact_fit(z_train: np.ndarray, n_components: int) -> Tuple[np.ndarray, np.ndarray]:
+    """(components_ [P, D], mean_ [D]) of the exact PCA of the rows of ``z_train`` (utils/cv_evaluator.py:89-90)."""
+    z = np.asarray(z_train, dtype=np.float64)
+    n = z.shape[0]
+    mean = z.sum(axis=0) / n
+    cov = (z.T @ z - n * np.outer(mean, mean)) / (n - 1)
+    cov = 0.5 * (cov + cov.T)
+    _, vecs = np.linalg.eigh(cov)
+    comps = vecs[:, ::-1].T[:n_components].copy()
+    pivot = np.argmax(np.abs(comps), axis=1)
+    comps *= np.sign(comps[np.arange(comps.shape[0]), pivot])[:, None]
+    return comps, mean
+
+
+def process_embeddings_exact(train: np.ndarray, test: np.ndarray, pca_dim: Optional[int]
+                             ) -> Tuple[np.ndarray, np.ndarray]:
+    """CVRetrievalEvaluator.process_embeddings (utils/cv_evaluator.py:73-93) with the exact PCA basis;
+    ``pca_dim=None`` skips the PCA (RetrievalEvaluator.process_embeddings with use_pca=False,
+    retrieval/evaluator.py:50-73)."""
+    mean, scale = scaler_fit(train)
+    tr = scaler_apply(np.asarray(train, dtype=np.float32), mean, scale)
+    te = scaler_apply(np.asarray(test, dtype=np.float32), mean, scale)
+    n_comp = min(pca_dim, tr.shape[0] - 1, tr.shape[1]) if pca_dim is not None else 0
+    if n_comp > 0:
+        comps, zmean = pca_exact_fit(tr, n_comp)
+        w = comps.astype(np.float32)
+        bias = zmean.astype(np.float32)[None, :] @ w.T
+        tr = tr @ w.T - bias
+        te = te @ w.T - bias
+    return unit_rows(tr), unit_rows(te)

@@ -112,3 +112,54 @@ def test_batched_search_matches_loop(oracle):
     idx, sc = oracle.search_topk_batched(qs, db, 6, q_fold=fold_db[395:405], db_fold=fold_db)
     for i in range(len(qs)):
         assert np.all(fold_db[idx[i]] != fold_db[395 + i])
+
+
+# ------------------------------------------------------------------ per-fold preprocessing
+def test_scaler_oracle_equals_sklearn(oracle):
+    from sklearn.preprocessing import StandardScaler
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal((1000, 64)) * rng.uniform(0.01, 30, 64) + rng.uniform(-50, 50, 64)).astype(np.float32)
+    x[:, 5] = 3.25                                   # constant feature -> scale 1
+    sk = StandardScaler().fit(x)
+    mean, scale = oracle.scaler_fit(x)
+    np.testing.assert_allclose(mean, sk.mean_, rtol=1e-14, atol=1e-14)
+    np.testing.assert_allclose(scale, sk.scale_, rtol=1e-13)
+    assert scale[5] == 1.0
+    assert np.array_equal(oracle.scaler_apply(x, mean, scale), sk.transform(x))
+
+
+def test_exact_pca_oracle_is_what_sklearn_computes_in_float64(golden, oracle):
+    from sklearn.decomposition import PCA
+    from sklearn.preprocessing import StandardScaler
+    g = golden("cv_small.npz")
+    z = StandardScaler().fit_transform(g["image"][g["f3_train_idx"]])
+    comps, mean = oracle.pca_exact_fit(z, 16)
+    for solver in ("full", "covariance_eigh"):
+        sk = PCA(16, svd_solver=solver).fit(z.astype(np.float64))
+        assert np.max(np.abs(sk.components_ - comps)) < 1e-10
+        assert np.max(np.abs(sk.mean_ - mean)) < 1e-12
+
+
+def test_process_embeddings_oracle_vs_reference_outputs(golden, oracle):
+    """The reference's process_embeddings on the golden folds ran sklearn's fp32 "full" SVD (240 x 48 / 240 x 40):
+    it sits within 2.5e-4 of the exact basis (fp32 LAPACK rounding at eigenvalue gaps of ~0.2 %)."""
+    g = golden("cv_small.npz")
+    pca_dim = int(g["meta"][4])
+    worst = 0.0
+    for f in range(5):
+        tr_i, te_i = g[f"f{f}_train_idx"], g[f"f{f}_test_idx"]
+        for mod, key in (("image", "img"), ("text", "txt")):
+            tr, te = oracle.process_embeddings_exact(g[mod][tr_i], g[mod][te_i], pca_dim)
+            assert tr.dtype == np.float32 and tr.shape == g[f"f{f}_{key}_tr"].shape
+            worst = max(worst, np.abs(tr - g[f"f{f}_{key}_tr"]).max(), np.abs(te - g[f"f{f}_{key}_te"]).max())
+    assert worst < 5e-4
+
+
+def test_sklearn_solver_rule_matches_sklearn():
+    from sklearn.decomposition import PCA
+    from emr2a_b200.preprocess import sklearn_solver
+    rng = np.random.default_rng(1)
+    for n, d, p in ((240, 48, 16), (600, 40, 16), (520, 300, 16), (520, 300, 280), (100, 600, 50), (5200, 512, 128)):
+        x = rng.standard_normal((n, d)).astype(np.float32)
+        sk = PCA(n_components=min(p, n - 1, d)).fit(x)
+        assert sklearn_solver(n, d, min(p, n - 1, d)) == sk._fit_svd_solver, (n, d, p)
