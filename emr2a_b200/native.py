@@ -18,7 +18,7 @@ F32, BF16 = 0, 1
 NF_SEGNORM, NF_ROWNORM, NF_ZERO_GUARD = 1, 2, 4
 PREC_FP32, PREC_BF16X3, PREC_BF16X1, PREC_BF16_RESCORE = 0, 1, 2, 3
 SCORE_NONE, SCORE_ZSCORE, SCORE_MINMAX = 0, 1, 2
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _p = C.c_void_p
 _i64 = C.c_int64
@@ -46,6 +46,8 @@ _SIGNATURES = {
     "emr2a_column_moments_workspace_bytes": (_sz, [_i64, _int]),
     "emr2a_column_moments": (_int, [_p, _i64, _i64, _int, _p, _p, _p, _p, _sz, _p]),
     "emr2a_standardize": (_int, [_p, _i64, _i64, _int, _p, _p, _p, _i64, _p]),
+    "emr2a_scale_segments": (_int, [_p, _i64, _int, _int, _i64, _p, _p, _p]),
+    "emr2a_keys_add_offset": (_int, [_p, _i64, _int, _p, _p]),
     "emr2a_segment_mean": (_int, [_p, _i64, _p, _i64, _int, _p, _i64, _p]),
     # diagnostics (not part of the reference-facing surface)
     "emr2a_debug_topk_search_dump": (_int, [_p, _p, _p, _p, _i64, _i64, _int, _i64, _i64, _p, _p, _i64, _int, _int,

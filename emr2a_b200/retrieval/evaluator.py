@@ -113,6 +113,11 @@ class RetrievalEvaluator:
         k_max = max(max(top_k_list), _WEIGHTED_K)
         k_eff = min(k_max, n_db) if n_db > 0 else 1
         keys = eng.topk_search(q_op, db_op, k_eff, prec)
+        return RetrievalEvaluator._family_from_keys(eng, keys, db_codes, q_codes, n_classes, top_k_list)
+
+    @staticmethod
+    def _family_from_keys(eng, keys, db_codes, q_codes, n_classes, top_k_list):
+        k_eff = int(keys.shape[1])
         hits = eng.vote_metrics(keys, db_codes, q_codes, n_classes, k_list=list(top_k_list), wacc_f32=True,
                                 per_query=False, want_lists=False)
         k5 = min(_WEIGHTED_K, k_eff)
@@ -184,8 +189,16 @@ class RetrievalEvaluator:
                 q_op = eng.prepare(test_text, test_image, np.float32(text_weight), np.float32(1 - text_weight),
                                    native.NF_SEGNORM, prec)
                 accs, weighted, top5 = self._family(eng, db_op, q_op, db_codes, q_codes, n_cls, top_k_list, prec)
+            elif self._late_fused(len(test_labels), len(train_labels)):
+                # z-score / min-max without the [Q, N] score matrix: per-query statistics from database moments /
+                # K = 1 searches, then the ordinary fused search with scaled query segments (emr2a_b200/late.py)
+                from ..late import late_fusion_search
+                k_eff = min(max(max(top_k_list), _WEIGHTED_K), len(train_labels))
+                keys = late_fusion_search(np.asarray(train_text), np.asarray(train_image), np.asarray(test_text),
+                                          np.asarray(test_image), text_weight, mode, k_eff, engine=eng)
+                accs, weighted, top5 = self._family_from_keys(eng, keys, db_codes, q_codes, n_cls, top_k_list)
             else:
-                # z-score / min-max need every score of a query: materialise [Q, N] like the reference does
+                # small problems: materialise [Q, N] and apply the reference's elementwise arithmetic op for op
                 fused = self._late_score_matrix(train_text, test_text, train_image, test_image, text_weight, mode)
                 accs = [self._topk_acc_from_device_scores(fused, db_codes, q_codes, n_cls, k) for k in top_k_list]
                 weighted, top5 = self._weighted_from_device_scores(fused, db_codes, q_codes, n_cls)
@@ -196,6 +209,16 @@ class RetrievalEvaluator:
             t5 = top5.cpu().numpy()
             results["all_top_labels_top5"] = [[lab[c] for c in row if c >= 0] for row in t5]
         return results
+
+    #: late fusion with z-score / min-max: score matrices beyond this many elements are never materialised
+    #: (env ``EMR2A_LATE_FUSED=1`` / ``0`` forces the fused / materialised path)
+    late_materialise_max: int = 1 << 26
+
+    def _late_fused(self, n_q: int, n_db: int) -> bool:
+        forced = os.environ.get("EMR2A_LATE_FUSED")
+        if forced in ("0", "1"):
+            return forced == "1"
+        return n_q * n_db > self.late_materialise_max
 
     def _late_score_matrix(self, train_text, test_text, train_image, test_image, text_weight, mode):
         eng = get_engine()

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define EMR2A_ABI_VERSION 6
+#define EMR2A_ABI_VERSION 7
 
 enum emr2a_status {
   EMR2A_OK = 0,
@@ -239,6 +239,19 @@ int emr2a_column_moments(const float* x, int64_t ld, int64_t n, int D, const flo
                          double* sum, double* sumsq, void* workspace, size_t ws_bytes, void* stream);
 int emr2a_standardize(const float* x, int64_t ld, int64_t n, int D, const float* mean, const float* scale,
                       float* out, int64_t ld_out, void* stream);
+
+/*
+ * Late fusion with z-score / min-max score normalisation without the [Q, N] score matrix
+ * (retrieval/fusion.py:4-14, 31-42; retrieval/evaluator.py:150-157).  Per query the fused score is an affine map
+ *     fused[d] = < [g_t * Tq ; g_i * Iq], [Td ; Id] > - c
+ * of the two similarity vectors, so the Top-K is the ordinary fused search with per-row scaled query segments
+ * and the constant applied to the winning scores afterwards:
+ * emr2a_scale_segments: x[r, 0:d0] *= g0[r], x[r, d0:d0+d1] *= g1[r]   (fp32 rows, in place; g1 nullable if d1 = 0)
+ * emr2a_keys_add_offset: score of every non-empty key of query q += offset[q] (order within a query is unchanged).
+ */
+int emr2a_scale_segments(float* x, int64_t n, int d0, int d1, int64_t ld, const float* g0, const float* g1,
+                         void* stream);
+int emr2a_keys_add_offset(uint64_t* keys, int64_t Q, int K, const float* offset, void* stream);
 
 /* Top-K of a given score matrix (the *_from_scores helpers and get_all_top_labels,
  * retrieval/evaluator.py:195-208, 235-275): keys out [Q, K]. */
