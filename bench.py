@@ -66,8 +66,19 @@ def peaks():
     if os.path.exists(path):
         with open(path) as fh:
             p = json.load(fh)
-        return {"hbm_gbs": p["hbm_gbs"], "tflops": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "src": "measured"}
-    return {"hbm_gbs": 6650.0, "tflops": 1590.0, "src": "fallback"}
+        return {"hbm_gbs": p["hbm_gbs"], "tflops": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "tflops_burst": p["bf16_tflops"], "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1590.0, "tflops_burst": 1590.0, "src": "fallback"}
+
+
+def tensor_peak(pk, timed_seconds):
+    """Roofline denominator for the tensor-bound kernel: MEASURED_PEAKS.json holds a burst figure (a kernel timed
+    alone, boost clocks) and a sustained one (back to back for 4 s, power-capped clocks).  A timed region shorter
+    than that 4 s window runs at burst clocks, so the burst figure is the honest denominator; longer ones (C5, C4)
+    use the sustained figure.  Both fractions are reported."""
+    if timed_seconds >= 4.0:
+        return pk["tflops"], "bf16 sustained (timed region >= 4 s)"
+    return pk["tflops_burst"], "bf16 burst (timed region < 4 s)"
 
 
 class ClockSampler:
@@ -310,8 +321,11 @@ def run_c5(args):
                                           f"query), query blocks of {q_block} searched locally, NCCL all-gather of local Top-K",
                            "l2": "inputs larger than L2"},
                 "clocks": clocks, "e2e": None, "gpu_launches": eng.launches - l0,
-                "roofline": {"bound": "tensor", "achieved": tf / world, "peak": pk["tflops"], "unit": "TFLOP/s per GPU",
-                             "frac": tf / world / pk["tflops"], "traffic": None,
+                "roofline": {"bound": "tensor", "achieved": tf / world, "peak": tensor_peak(pk, ms * steps / 1e3)[0],
+                             "unit": "TFLOP/s per GPU", "frac": tf / world / tensor_peak(pk, ms * steps / 1e3)[0],
+                             "peak_source": pk["src"] + " " + tensor_peak(pk, ms * steps / 1e3)[1],
+                             "frac_of_burst": tf / world / pk["tflops_burst"], "frac_of_sustained": tf / world / pk["tflops"],
+                             "traffic": None,
                              "note": "whole step (row all-gather + K1 + K2 + key gather + K3 + K4) over admissible pairs only"},
                 "cpu_baseline": None, "unverified_queries": int(unverified),
                 "accuracy": {"top1": float(hits[:, 0].sum()) / n, "top5": float(hits[:, 2].sum()) / n,
@@ -601,13 +615,15 @@ def main():
     # --set full capture profiles/r01_ncu_step_c2_rescore.md: 3.574 GB read + 0.034 GB written per launch
     # (algorithmic: 2.05 GB bf16 database plane + 20 MB query plane + 31 MB partial lists).
     traffic = 3.608e9 if (res["precision"] == "rescore" and world == 1 and args.workload == "c2") else None
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tflops"], "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
-                "peak_source": pk["src"] + " (bf16 sustained)",
+    t_peak, t_src = tensor_peak(pk, ms_per_step * args.steps / 1e3)
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": t_peak, "unit": "TFLOP/s",
+                "frac": achieved / t_peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
+                "peak_source": pk["src"] + " " + t_src,
+                "frac_of_burst": achieved / pk["tflops_burst"], "frac_of_sustained": achieved / pk["tflops"],
                 "kernel": "emr2a_topk_search = tc2_topk_kernel (tcgen05 cta_group::2, TMA, fused Top-K) + K3 merge of partial lists"
                           + (" + exact fp32 rescore of <=64 candidates/query + (empty) re-scan" if res["precision"] == "rescore" else ""),
                 "kernel_ms": k2_avg_ms,
-                "issued_tflops": achieved * passes, "issued_frac": achieved * passes / pk["tflops"],
+                "issued_tflops": achieved * passes, "issued_frac": achieved * passes / t_peak,
                 "share_of_step": k2_avg_ms / ms_per_step}
 
     # ---- CPU baseline + parity on the sample (rank 0, N = 1) ----

@@ -212,9 +212,11 @@ class CVRetrievalEvaluator:
                                             fusion, top_k_list, w_text, train_ids)
 
     def evaluate_processed_fold(self, tr_img, tr_txt, te_img, te_txt, train_labels, test_labels, test_ids,
-                                fusion="concat", top_k_list=None, w_text=0.5, train_ids=None) -> Dict:
+                                fusion="concat", top_k_list=None, w_text=0.5, train_ids=None, lists: bool = True,
+                                codes=None) -> Dict:
         """The GPU part of ``evaluate_fold``: from processed (unit-row) arrays onward
-        (utils/cv_evaluator.py:186-334)."""
+        (utils/cv_evaluator.py:186-334).  ``lists=False`` leaves the per-sample python lists out;
+        ``codes = (classes, train_codes, test_codes)`` passes already encoded labels (array fast path)."""
         if top_k_list is None:
             top_k_list = [1, 3, 5, self.top_k]
         eng = get_engine()
@@ -240,13 +242,16 @@ class CVRetrievalEvaluator:
         else:
             raise ValueError(f"Unknown fusion type: {fusion}")
 
-        classes, (db_codes, q_codes) = encode(train_labels, test_labels)
+        if codes is not None:
+            classes, db_codes, q_codes = codes
+        else:
+            classes, (db_codes, q_codes) = encode(train_labels, test_labels)
         n_cls = len(classes)
-        n_db, n_q = len(train_labels), len(test_labels)
+        n_db, n_q = len(db_codes), len(q_codes)
         k_eff = max(1, min(int(self.top_k), n_db))
         out = eng.search_and_vote(db_segs, q_segs, db_codes, q_codes, n_cls, k_eff,
                                   db_weights=(1.0, 1.0), q_weights=qw, db_flags=flags, q_flags=flags,
-                                  k_list=[int(k) for k in top_k_list], wacc_f32=False)
+                                  k_list=[int(k) for k in top_k_list], wacc_f32=False, want_lists=lists)
 
         results: Dict = {}
         hits = out["hit_counts"][0].cpu().numpy()
@@ -264,6 +269,9 @@ class CVRetrievalEvaluator:
         results["confusion_matrix_top1"] = confusion_dict(conf[0], classes)
         results["confusion_matrix_vote"] = confusion_dict(conf[1], classes)
 
+        if not lists:
+            results["test_patient_ids"] = test_ids
+            return results
         idx = out["top_idx"].cpu().numpy()
         valid = (idx >= 0).sum(axis=1)
         results["all_top_labels"] = gather_lists(train_labels, idx, valid)
@@ -327,6 +335,69 @@ class CVRetrievalEvaluator:
                                      fusion, top_k_list, w_text, train_ids)
             res["fold"] = fold + 1
             res["train_ids"] = train_ids
+            fold_results.append(res)
+            logger.info(f"Fold {fold + 1} results: Top1={res['top1']:.4f}, "
+                        f"Vote Acc={res['vote_acc']:.4f}, "
+                        f"Weighted Acc={res['weighted_vote_acc']:.4f}")
+        return {"fold_results": fold_results, "summary": self._compute_summary(fold_results)}
+
+    def run_cv_arrays(self, labels, image=None, text=None, fusion: str = "concat",
+                      top_k_list: Optional[List[int]] = None, w_text: float = 0.5,
+                      patient_ids: Optional[List[str]] = None, lists: bool = False) -> Dict:
+        """Array form of ``run_cv`` for large cohorts, the WHOLE reference pipeline on the device: the same
+        StratifiedKFold split (host, sklearn), then per fold StandardScaler + PCA fitted on the train rows
+        (``emr2a_b200.preprocess``, i.e. ``preprocess = "gpu"`` semantics whatever the attribute says), fusion,
+        Top-K search, votes and metrics.  ``image`` / ``text``: [N, D] matrices (numpy or device tensors) in
+        ``labels`` order -- no per-patient dict, no python loop over cases.  Same result structure as ``run_cv``;
+        with ``lists=False`` (default) the per-sample python lists are left out."""
+        import torch
+        from .. import preprocess as pp
+        if top_k_list is None:
+            top_k_list = [1, 3, 5, self.top_k]
+        need_img = fusion in {"concat", "image_only", "late"}
+        need_txt = fusion in {"concat", "text_only", "late"}
+        if fusion not in {"concat", "image_only", "text_only", "late"}:
+            raise ValueError(f"Unknown fusion type: {fusion}")
+        if need_img and image is None:
+            raise ValueError(f"{fusion} fusion requires image embeddings" if fusion == "image_only"
+                             else f"{fusion} fusion requires both image and text embeddings")
+        if need_txt and text is None:
+            raise ValueError(f"{fusion} fusion requires text embeddings" if fusion == "text_only"
+                             else f"{fusion} fusion requires both image and text embeddings")
+        eng = get_engine()
+        n = len(labels)
+        ids = list(patient_ids) if patient_ids is not None else None
+        label_list = labels.tolist() if isinstance(labels, np.ndarray) else list(labels)
+        classes, (codes,) = encode(label_list)
+        codes_t = eng.to_device(codes, torch.int32)
+        mats = {}
+        if need_img:
+            mats["image"] = eng._embedding(image)[0].float()
+        if need_txt:
+            mats["text"] = eng._embedding(text)[0].float()
+        skf = StratifiedKFold(n_splits=self.cv_folds, shuffle=True, random_state=self.seed)
+        fold_results = []
+        for fold, (tr, te) in enumerate(skf.split(np.zeros(n, dtype=np.int8), label_list)):
+            logger.info(f"Processing fold {fold + 1}/{self.cv_folds}")
+            logger.info(f"Train: {len(tr)}, Test: {len(te)}")
+            tr_t = torch.from_numpy(tr).to(eng.device)
+            te_t = torch.from_numpy(te).to(eng.device)
+            proc = {}
+            for name, mat in mats.items():
+                x_tr = mat.index_select(0, tr_t)
+                tf = pp.fit(x_tr, self.pca_dim, eng)
+                proc[name] = (pp.transform(tf, x_tr, eng), pp.transform(tf, mat.index_select(0, te_t), eng))
+                del x_tr
+            tr_img, te_img = proc.get("image", (None, None))
+            tr_txt, te_txt = proc.get("text", (None, None))
+            train_labels = [label_list[j] for j in tr] if lists else None
+            train_ids = [ids[j] for j in tr] if (lists and ids is not None) else None
+            test_ids = [ids[j] for j in te] if ids is not None else te.tolist()
+            res = self.evaluate_processed_fold(tr_img, tr_txt, te_img, te_txt, train_labels, None, test_ids, fusion,
+                                               top_k_list, w_text, train_ids, lists=lists,
+                                               codes=(classes, codes_t.index_select(0, tr_t), codes_t.index_select(0, te_t)))
+            res["fold"] = fold + 1
+            res["train_ids"] = ([ids[j] for j in tr] if ids is not None else tr.tolist()) if lists else []
             fold_results.append(res)
             logger.info(f"Fold {fold + 1} results: Top1={res['top1']:.4f}, "
                         f"Vote Acc={res['vote_acc']:.4f}, "

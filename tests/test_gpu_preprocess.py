@@ -179,3 +179,34 @@ def test_holdout_evaluator_gpu_scaler_equals_host(oracle):
     g_tr, g_te = ho.process_embeddings(x[:300], x[300:])
     o_tr, o_te = oracle.process_embeddings_exact(x[:300], x[300:], 12)
     assert np.max(np.abs(g_tr - o_tr)) < 1e-5 and np.max(np.abs(g_te - o_te)) < 1e-5
+
+
+@pytest.mark.parametrize("fusion,w", [("concat", 0.5), ("late", 0.3), ("image_only", 0.5)])
+def test_run_cv_arrays_equals_run_cv_with_gpu_preprocessing(golden, fusion, w):
+    """The array form of the whole pipeline against the dict-shaped run_cv (both with device preprocessing)."""
+    from emr2a_b200 import synth
+    from emr2a_b200.utils.cv_evaluator import CVRetrievalEvaluator
+    g = golden("cv_small.npz")
+    n, d_img, d_txt, n_cls, pca_dim, top_k = [int(v) for v in g["meta"]]
+    ids = synth.patient_ids(n)
+    labels = [f"class_{c}" for c in g["labels"]]
+    emb = {pid: {"image": g["image"][j], "text": g["text"][j]} for j, pid in enumerate(ids)}
+    ev = CVRetrievalEvaluator(cv_folds=5, pca_dim=pca_dim, top_k=top_k, seed=42)
+    ev.preprocess = "gpu"
+    a = ev.run_cv(ids, labels, emb, fusion=fusion, top_k_list=[1, 3, 5, 5], w_text=w)
+    b = ev.run_cv_arrays(labels, g["image"], g["text"], fusion=fusion, top_k_list=[1, 3, 5, 5], w_text=w,
+                         patient_ids=ids, lists=True)
+    c = ev.run_cv_arrays(np.asarray(g["labels"]), g["image"], g["text"], fusion=fusion, top_k_list=[1, 3, 5, 5], w_text=w)
+    assert a["summary"] == b["summary"]
+    for ra, rb, rc in zip(a["fold_results"], b["fold_results"], c["fold_results"]):
+        assert ra["test_patient_ids"] == rb["test_patient_ids"] and ra["train_ids"] == rb["train_ids"]
+        assert ra["all_top_patient_ids"] == rb["all_top_patient_ids"] and ra["all_top_labels"] == rb["all_top_labels"]
+        assert ra["all_top_scores"] == rb["all_top_scores"]
+        assert ra["confusion_matrix_vote"] == rb["confusion_matrix_vote"]
+        assert "all_top_labels" not in rc and rc["train_ids"] == []
+        for key in ("top1", "top3", "top5", "vote_acc", "weighted_vote_acc", "macro_f1"):
+            assert ra[key] == rc[key]
+    with pytest.raises(ValueError):
+        ev.run_cv_arrays(labels, g["image"], None, fusion="concat")
+    with pytest.raises(ValueError):
+        ev.run_cv_arrays(labels, g["image"], g["text"], fusion="bogus")
