@@ -205,7 +205,7 @@ def run_reference(args):
                                        f"{os.cpu_count()} logical cores"},
             "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_c5(args):
@@ -331,7 +331,7 @@ def run_c5(args):
                 "accuracy": {"top1": float(hits[:, 0].sum()) / n, "top5": float(hits[:, 2].sum()) / n,
                              "vote_acc": float(votes[:, 1].sum()) / n,
                              "per_fold_top1": [float(hits[f, 0]) / max(float(sizes[f]), 1.0) for f in range(n_folds)]}}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -438,11 +438,33 @@ def run_c1(args):
                              "hot_path_only_qps": n / t_cpu, "parity": {"topk_rows_identical": same}},
             "accuracy": {"top1": float(np.mean([r["top1"] for r in full["fold_results"]])),
                          "vote_acc": float(np.mean([r["vote_acc"] for r in full["fold_results"]]))}}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to
+    stdout on rank 0, python logging of the evaluators, ...), so file descriptor 1 is pointed at stderr for the
+    whole run and the JSON line alone goes to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    sys.stdout.flush()
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
     args = parse()
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "c5":
@@ -661,7 +683,7 @@ def main():
                 "unverified_queries": int(unverified_total),
                 "accuracy": {"top1": float(hits[0]) / n_q, f"top{k}": float(hits[3]) / n_q,
                              "vote_acc": float(res["vote_counts"][0, 1]) / n_q}}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -15,8 +15,8 @@ def _run(*args, timeout=600):
     out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), *args], capture_output=True, text=True,
                          timeout=timeout, cwd=REPO)
     assert out.returncode == 0, out.stderr[-2000:]
-    lines = [l for l in out.stdout.strip().splitlines() if l.startswith("{")]
-    assert len(lines) == 1, out.stdout[-2000:]
+    lines = out.stdout.strip().splitlines()          # nothing but the JSON line may reach stdout (library banners go to stderr)
+    assert len(lines) == 1 and lines[0].startswith("{"), out.stdout[-2000:]
     return json.loads(lines[0])
 
 
