@@ -27,6 +27,12 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv and os.environ.get("OMP_NUM_THREADS") == "1" and os.environ.get("TORCHELASTIC_RUN_ID"):
+    # torchrun exports OMP_NUM_THREADS=1 to every rank and OpenBLAS sizes its pool from it when numpy loads; the
+    # reference arm (rank 0 only, no GPU work) gets every host thread BLAS can use, as in the N=1 launch
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 REPO = os.path.dirname(os.path.abspath(__file__))
@@ -177,7 +183,7 @@ def run_reference(args):
         from threadpoolctl import threadpool_info
         threads = max([i.get("num_threads", 1) for i in threadpool_info()] or [1])
     except Exception:
-        threads = os.cpu_count() or 1
+        threads = 1
     t0 = time.perf_counter()
     db = oracle.fuse_concat_cv(oracle.unit_rows(img[:n_db]), oracle.unit_rows(txt[:n_db]))
     t_prep = time.perf_counter() - t0
