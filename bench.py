@@ -224,7 +224,7 @@ def run_c5(args):
     import torch
     import torch.distributed as dist
     from emr2a_b200 import native, synth
-    from emr2a_b200.dist import gather_keys, shard_range
+    from emr2a_b200.dist import shard_range, sharded_cv_search_and_vote
     from emr2a_b200.engine import get_engine
 
     world = int(os.environ.get("WORLD_SIZE", 1)); rank = int(os.environ.get("RANK", 0))
@@ -243,51 +243,16 @@ def run_c5(args):
     labels = synth.device_labels(0, n, n_cls, seed, dev)
     fold = (torch.arange(n, device=dev, dtype=torch.int64) * n_folds // n).to(torch.uint8)
     prec = args.precision
-    spans = [shard_range(n, r, world) for r in range(world)]
-    per = spans[0][1] - spans[0][0]
     torch.cuda.synchronize()
 
     def step():
-        # (1) every rank needs every case as a query: ONE all-gather of the raw rows over NVLink (41 GB per GPU at
-        #     10M cases) instead of a broadcast per query block -- with fold-ordered rows a rank has nothing to do for
-        #     query blocks of the fold its shard lies in, so any per-block collective would make it wait for the others.
-        if world > 1:
-            full_img = torch.empty((world * per, d_img), dtype=torch.float32, device=dev)
-            full_txt = torch.empty((world * per, d_txt), dtype=torch.float32, device=dev)
-            pad_i, pad_t = db_img, db_txt
-            if hi - lo < per:
-                pad_i = torch.zeros((per, d_img), dtype=torch.float32, device=dev); pad_i[:hi - lo] = db_img
-                pad_t = torch.zeros((per, d_txt), dtype=torch.float32, device=dev); pad_t[:hi - lo] = db_txt
-            dist.all_gather_into_tensor(full_img, pad_i)
-            dist.all_gather_into_tensor(full_txt, pad_t)
-        else:
-            full_img, full_txt = db_img, db_txt
-        # (2) local work, no communication: K1 on the shard, then every query block against it
-        db = eng.prepare(db_img, db_txt, 1.0, 1.0, flags, prec)
-        local = []
-        for b0 in range(0, n, q_block):
-            b1 = min(b0 + q_block, n)
-            qs = eng.prepare(full_img[b0:b1], full_txt[b0:b1], 1.0, 1.0, flags, prec)
-            local.append(eng.topk_search(qs, db, k, prec, q_fold=fold[b0:b1], db_fold=fold[lo:hi], fold_sorted=True,
-                                         idx_base=lo))
-        # (3) exchange: all-gather of the local Top-K of each block, K3 merge, K4 vote with per-fold counters
-        hits = votes = sizes = None
-        for i, b0 in enumerate(range(0, n, q_block)):
-            b1 = min(b0 + q_block, n)
-            keys = local[i]
-            if world > 1:
-                keys = eng.topk_merge(gather_keys(keys), k)
-            r = eng.vote_metrics(keys, labels, labels[b0:b1], n_cls, k_list=[1, 3, 5], q_group=fold[b0:b1],
-                                 n_groups=n_folds, per_query=False, want_lists=False)
-            hits = r["hit_counts"] if hits is None else hits + r["hit_counts"]
-            votes = r["vote_counts"] if votes is None else votes + r["vote_counts"]
-            sizes = r["group_sizes"] if sizes is None else sizes + r["group_sizes"]
-        unverified = 0
-        if prec == "rescore":
-            unverified, overflow = eng.consume_status()
-            if overflow:
-                raise RuntimeError("rescore re-scan list overflowed on this workload; run with --precision bf16x3")
-        return hits, votes, sizes, unverified
+        # the library path: one all-gather of the raw rows, communication-free local search of every query block,
+        # exchange of the local Top-K keys, K3 merge, K4 vote with per-fold counters (emr2a_b200/dist.py)
+        r = sharded_cv_search_and_vote(eng, (db_img, db_txt), labels, fold, n_cls, k, lo, flags, k_list=[1, 3, 5],
+                                       precision=prec, n_folds=n_folds, q_block=q_block, fold_sorted=True)
+        if r["precision"] != prec:
+            raise RuntimeError("rescore re-scan list overflowed on this workload; run with --precision bf16x3")
+        return r["hit_counts"], r["vote_counts"], r["group_sizes"], r["unverified"]
 
     def barrier():
         torch.cuda.synchronize()

@@ -103,3 +103,28 @@ def test_c5_shaped_all_queries_fold_rule(eng):
                                    q_block=1 << 20)
     assert torch.equal(again["top_idx"], idx) and torch.equal(again["hit_counts"], out["hit_counts"])
     assert torch.equal(again["confusion"], out["confusion"])
+
+
+def test_sharded_cv_single_rank_equals_engine_path(eng):
+    """dist.sharded_cv_search_and_vote with one rank (no process group) is the engine's one-pass CV; unsorted fold
+    vectors use the per-element mask only.  (World sizes 2 and 8: tools/dist_check.py under torchrun.)"""
+    import torch
+    from emr2a_b200 import native, synth
+    from emr2a_b200.dist import sharded_cv_search_and_vote
+    dev = eng.device
+    n, d, c, k = 60_000, 192, 3, 5
+    xi, lab = synth.device_block(0, n, d, c, 23, dev)
+    xt, _ = synth.device_block(0, n, d, c, 24, dev, label_seed=23)
+    flags = native.NF_SEGNORM | native.NF_ROWNORM
+    keys = ("hit_counts", "vote_counts", "confusion", "group_sizes", "top_idx", "top_scores", "pred_vote", "pred_weighted")
+    sorted_folds = (torch.arange(n, device=dev) * 5 // n).to(torch.uint8)
+    a = sharded_cv_search_and_vote(eng, (xi, xt), lab, sorted_folds, c, k, 0, flags, precision="rescore", q_block=16384,
+                                   want_lists=True)
+    b = eng.cv_search_and_vote((xi, xt), lab, sorted_folds, c, k, flags=flags, precision="rescore", n_folds=5)
+    assert all(torch.equal(a[key], b[key]) for key in keys)
+    mixed = (torch.arange(n, device=dev) % 5).to(torch.uint8)
+    a = sharded_cv_search_and_vote(eng, (xi, xt), lab, mixed, c, k, 0, flags, precision="rescore", q_block=16384,
+                                   fold_sorted=False, want_lists=True)
+    b = eng.cv_search_and_vote((xi, xt), lab, mixed, c, k, flags=flags, precision="rescore", n_folds=5)
+    assert all(torch.equal(a[key], b[key]) for key in keys)
+    assert not bool((mixed[a["top_idx"]] == mixed[:, None]).any())

@@ -5,7 +5,7 @@ import torch, torch.distributed as dist
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 from emr2a_b200 import native, synth
-from emr2a_b200.dist import shard_range, sharded_search_and_vote
+from emr2a_b200.dist import shard_range, sharded_cv_search_and_vote, sharded_search_and_vote
 from emr2a_b200.engine import get_engine
 
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -28,6 +28,23 @@ for prec in ("bf16x3", "fp32"):
     full = eng.search_and_vote((fi, ft), (qi, qt), labels, ql, c, k, db_flags=flags, q_flags=flags, precision=prec)
     same = torch.equal(r["keys"], full["keys"]) and torch.equal(r["pred_vote"], full["pred_vote"]) and torch.equal(r["confusion"], full["confusion"])
     print(f"rank {rank}/{world} {prec}: sharded == single-GPU: {same}", flush=True)
+    ok = ok and same
+# all-queries CV over the sharded cohort == the single-GPU one-pass CV
+n_cv, n_folds = 200_000, 5
+lo, hi = shard_range(n_cv, rank, world)
+xi, _ = synth.device_block(lo, hi - lo, d, c, 19, dev, label_seed=19)
+xt, _ = synth.device_block(lo, hi - lo, d, c, 20, dev, label_seed=19)
+lab = synth.device_labels(0, n_cv, c, 19, dev)
+fold = (torch.arange(n_cv, device=dev, dtype=torch.int64) * n_folds // n_cv).to(torch.uint8)
+fi, _ = synth.device_block(0, n_cv, d, c, 19, dev, label_seed=19)
+ft, _ = synth.device_block(0, n_cv, d, c, 20, dev, label_seed=19)
+for prec in ("rescore", "bf16x3"):
+    r = sharded_cv_search_and_vote(eng, (xi, xt), lab, fold, c, 5, lo, flags, k_list=[1, 3, 5], precision=prec,
+                                   n_folds=n_folds, q_block=65536, want_lists=True)
+    full = eng.cv_search_and_vote((fi, ft), lab, fold, c, 5, flags=flags, k_list=[1, 3, 5], precision=prec, n_folds=n_folds)
+    same = all(torch.equal(r[key], full[key]) for key in ("hit_counts", "vote_counts", "confusion", "group_sizes",
+                                                           "top_idx", "top_scores", "pred_vote", "pred_weighted"))
+    print(f"rank {rank}/{world} cv {prec}: sharded == single-GPU: {same} (unverified {r['unverified']})", flush=True)
     ok = ok and same
 dist.barrier(); dist.destroy_process_group()
 sys.exit(0 if ok else 1)
