@@ -5,8 +5,9 @@
 //           rows with the largest s~ are kept (K <= 10: the slack below the K-th best must hold ~2E of scores).
 // Rescore:  s(q,d) = fp32 dot product of the fp32 rows K1 wrote (the same values the fp32 arm uses).
 // Bound:    |s~ - s| <= E = r_q * n_d + (n_q + r_q) * r_d + 1e-5 * n_q * n_d   for every pair, where
-//           n_* = max row norm and r_* = max ||row - bf16(row)|| over the queries / database rows
-//           (K1 `stats`, Cauchy-Schwarz on the two quantisation residuals; the last term covers
+//           n_d, r_d = max row norm and max ||row - bf16(row)|| over the database rows (K1 `stats`), n_q, r_q = the
+//           same two norms of THIS query (computed here, clamped by the batch maxima of K1 `stats`)
+//           (Cauchy-Schwarz on the two quantisation residuals; the last term covers
 //           the fp32 accumulation inside the tensor core).  bf16 keeps 8 significant bits, so r ~ 1.7e-3 for a
 //           unit row and E ~ 4e-3.
 // Verify:   every row outside the candidate list has s~ <= tau (the KP-th approximate score), hence
@@ -57,9 +58,28 @@ __device__ __forceinline__ float lane_dot(const float* __restrict__ a, const flo
   return acc;
 }
 
-__device__ __forceinline__ float error_bound(const float* qs, const float* ds) {
-  const float nq = qs[0], rq = qs[1], nd = ds[0], rd = ds[1];
+__device__ __forceinline__ float error_bound(float nq, float rq, const float* ds) {
+  const float nd = ds[0], rd = ds[1];
   return rq * nd + (nq + rq) * rd + 1e-5f * nq * nd + 1e-7f;
+}
+
+// The query side of the bound is taken per query: ||q|| and ||q - bf16(q)|| of THIS query's fp32 row (the hi plane
+// the filter used is bf16_rn of exactly these values), clamped by the batch maxima K1 wrote.  Batches whose query
+// norms differ (late fusion with per-query z-score / min-max scaling, emr2a_b200/late.py) get a bound as tight as a
+// homogeneous batch would.
+__device__ __forceinline__ void query_norms(const float* __restrict__ qrow, int D, int lane, const float* qs,
+                                            float& nq, float& rq) {
+  float n2 = 0.f, r2 = 0.f;
+  for (int e = lane; e < D; e += 32) {
+    const float x = __ldg(qrow + e);
+    const float r = x - __bfloat162float(__float2bfloat16_rn(x));
+    n2 = fmaf(x, x, n2);
+    r2 = fmaf(r, r, r2);
+  }
+  n2 = warp_sum(n2);
+  r2 = warp_sum(r2);
+  nq = fminf(sqrtf(n2) * 1.000002f, qs[0]);          // rounded up: the bound must stay an upper bound
+  rq = fminf(sqrtf(r2) * 1.000002f, qs[1]);
 }
 
 template <bool VEC>
@@ -75,7 +95,9 @@ __global__ void __launch_bounds__(256) rescore_select_kernel(const RescoreParams
   const float* qrow = p.q + q * p.ldq;
   // A candidate c with s~(c) + E < s~(K-th candidate) - E cannot be among the exact K best (the K best
   // filter scores all have exact scores >= s~_K - E), so it is not re-scored: typically ~20 of 64 are.
-  const float E = error_bound(p.q_stats, p.db_stats);
+  float nq, rq;
+  query_norms(qrow, p.D, lane, p.q_stats, nq, rq);
+  const float E = error_bound(nq, rq, p.db_stats);
   const uint64_t kth_approx = __shfl_sync(0xffffffffu, akey[0], p.K - 1);
   const float cut = kth_approx != 0ull ? key_score(kth_approx) - 2.0f * E : -INFINITY;
   bool done = false;

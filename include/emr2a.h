@@ -141,7 +141,9 @@ int emr2a_late_fuse_scores(const float* text_scores, const float* image_scores, 
  *                             (bf16 bits; ld >= round_up(D,64), ld % 8 == 0, zero padded, 16-byte aligned)
  *   EMR2A_PREC_BF16X1       : q_hi, db_hi only
  *   EMR2A_PREC_BF16_RESCORE : q_hi, db_hi AND q_f32, db_f32, plus q_stats / db_stats (the float[2] K1
- *                             wrote for each side) and status_out
+ *                             wrote for each side) and status_out; the hi planes must be bf16_rn of the
+ *                             fp32 rows (K1 writes both from the same values) -- the error bound is built
+ *                             per query from the fp32 query row, clamped by q_stats
  * q_fold / db_fold (uint8 0..254, nullable together): a pair with equal fold ids is
  * excluded -- the CV rule that a case is never retrieved from its own fold
  * (utils/cv_evaluator.py:349-376).  `fold_sorted` != 0 promises both fold

@@ -529,3 +529,26 @@ def test_rescore_partial_overflow_only_flagged_queries_are_redone(eng):
     gaps = np.abs(np.diff(s32, axis=1)).min(axis=1) > 2 * SCORE_TOL
     assert np.array_equal(i32[gaps], ir[gaps]) and gaps[:1400].mean() > 0.95
     assert np.all(ir[1400:] >= 60_000)                         # hard queries retrieve from the blobs
+
+
+def test_rescore_bound_is_per_query(eng):
+    """One query 50x longer than the rest of the batch (per-query scaled late-fusion queries look like this): its
+    own error bound is 50x wider, the unit queries keep theirs -- no mass re-scan, and every row equals the fp32 arm."""
+    from emr2a_b200 import synth
+    from emr2a_b200.engine import unpack_keys
+    data = synth.two_modal(40_000 + 3000, 96, 96, 3, seed=77)
+    db = np.concatenate([data["image"][:40_000], data["text"][:40_000]], axis=1)
+    qs = np.concatenate([data["image"][40_000:], data["text"][40_000:]], axis=1)
+    db /= np.linalg.norm(db, axis=1, keepdims=True)
+    qs /= np.linalg.norm(qs, axis=1, keepdims=True)
+    qs[1234] *= 50.0
+    res = {}
+    for prec in ("fp32", "rescore"):
+        res[prec] = unpack_keys(eng.topk_search(eng.prepare(qs, flags=0, precision=prec), eng.prepare(db, flags=0, precision=prec),
+                                                10, prec))
+    unverified, overflow = eng.consume_status()
+    assert not overflow and unverified <= 3, (unverified, overflow)
+    (s32, i32), (sr, ir) = res["fp32"], res["rescore"]
+    assert np.max(np.abs(s32 - sr) / np.maximum(1.0, np.abs(s32))) < F32_TOL
+    clear = np.abs(np.diff(s32, axis=1)).min(axis=1) > 2 * F32_TOL * np.maximum(1.0, np.abs(s32[:, 0]))
+    assert clear.mean() > 0.9 and np.array_equal(i32[clear], ir[clear])

@@ -147,24 +147,6 @@ def test_cv_evaluator_gpu_preprocessing_on_golden_folds(golden, oracle):
         assert np.max(np.abs(got - ref[:5])) <= 2.0 / len(te_i) + 1e-12
 
 
-def test_auto_mode_follows_sklearn_solver_choice():
-    from emr2a_b200.utils.cv_evaluator import CVRetrievalEvaluator
-    from emr2a_b200.retrieval.evaluator import RetrievalEvaluator
-    ev = CVRetrievalEvaluator(pca_dim=128)
-    ev.preprocess = "auto"
-    assert ev._preprocess_on_gpu(240, 48)            # "full"
-    assert ev._preprocess_on_gpu(8000, 512)          # "covariance_eigh"
-    assert not ev._preprocess_on_gpu(1600, 512)      # "randomized": reproduce the seeded reference on the host
-    ev.preprocess = "host"
-    assert not ev._preprocess_on_gpu(240, 48)
-    ev.preprocess = "bogus"
-    with pytest.raises(ValueError):
-        ev._preprocess_on_gpu(240, 48)
-    ho = RetrievalEvaluator(use_pca=False)
-    ho.preprocess = "auto"
-    assert ho._preprocess_on_gpu(1600, 512)          # scaler only: always deterministic
-
-
 def test_holdout_evaluator_gpu_scaler_equals_host(oracle):
     from emr2a_b200.retrieval.evaluator import RetrievalEvaluator
     x = _structured(400, 48, seed=3)

@@ -208,3 +208,21 @@ def test_dropin_import_resolution_from_reference_root():
     a, b, c = out.stdout.strip().splitlines()[-1].split()
     assert a == "emr2a_b200.utils.cv_evaluator" and b == "emr2a_b200.retrieval.evaluator"
     assert c == os.path.join(REFERENCE, "utils", "vlm_review.py")
+
+
+def test_auto_mode_follows_sklearn_solver_choice():
+    from emr2a_b200.utils.cv_evaluator import CVRetrievalEvaluator
+    from emr2a_b200.retrieval.evaluator import RetrievalEvaluator
+    ev = CVRetrievalEvaluator(pca_dim=128)
+    ev.preprocess = "auto"
+    assert ev._preprocess_on_gpu(240, 48)            # "full"
+    assert ev._preprocess_on_gpu(8000, 512)          # "covariance_eigh"
+    assert not ev._preprocess_on_gpu(1600, 512)      # "randomized": reproduce the seeded reference on the host
+    ev.preprocess = "host"
+    assert not ev._preprocess_on_gpu(240, 48)
+    ev.preprocess = "bogus"
+    with pytest.raises(ValueError):
+        ev._preprocess_on_gpu(240, 48)
+    ho = RetrievalEvaluator(use_pca=False)
+    ho.preprocess = "auto"
+    assert ho._preprocess_on_gpu(1600, 512)          # scaler only: always deterministic
