@@ -13,8 +13,8 @@ K winning scores afterwards.  The statistics never need the score matrix either:
 
     z-score   mean_q = <q, S> / N and E[s^2]_q = q^T G q / N from the database's column sums S and Gram matrix G
               (float64, one pass over the unit rows: emr2a_column_moments + a library DGEMM);
-    min-max   max / min of a query's scores = Top-1 of q and of -q: one K = 1 search with the four query blocks
-              [t;0], [-t;0], [0;i], [0;-i] against the same fused database operand.
+    min-max   max / min of a query's scores = Top-1 of q and of -q: a K = 1 search per modality with the query blocks
+              [t], [-t] (resp. [i], [-i]) against that modality's column slice of the same fused database operand.
 """
 from __future__ import annotations
 
@@ -51,84 +51,139 @@ def database_moments(eng: Engine, unit_rows: torch.Tensor) -> Tuple[torch.Tensor
     return s, gram
 
 
-def _zscore_stats(eng: Engine, db_rows: torch.Tensor, q_rows: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """(mean, std + 1e-8) of every query's N scores, float64 [Q]."""
-    n = int(db_rows.shape[0])
-    s, gram = database_moments(eng, db_rows)
-    q64 = q_rows.double()
-    mean = (q64 @ s) / n
-    e2 = ((q64 @ gram) * q64).sum(dim=1) / n
-    std = torch.sqrt(torch.clamp(e2 - mean * mean, min=0.0))
-    return mean, std + 1e-8
+def _column_view(op: Operand, c0: int, c1: int) -> Operand:
+    """Columns [c0, c1) of a prepared operand as an operand of its own (no copy): valid for the tensor-core arms
+    when c0 and c1 are multiples of 64 (whole 128-byte k-chunks, nothing to zero-pad)."""
+    cut = lambda t: None if t is None else t[:, c0:c1]               # noqa: E731
+    return Operand(n=op.n, dim=c1 - c0, f32=cut(op.f32), hi=cut(op.hi), lo=cut(op.lo), stats=op.stats)
 
 
-def _minmax_stats(eng: Engine, db: Operand, qu: torch.Tensor, d_t: int, prec: str):
-    """(min, max - min + 1e-8) per query and modality from one K = 1 search of [t;0], [-t;0], [0;i], [0;-i]."""
-    n_q, dim = int(qu.shape[0]), int(qu.shape[1])
-    blocks = torch.zeros((4 * n_q, dim), dtype=torch.float32, device=eng.device)
-    blocks[0 * n_q:1 * n_q, :d_t] = qu[:, :d_t]
-    blocks[1 * n_q:2 * n_q, :d_t] = -qu[:, :d_t]
-    blocks[2 * n_q:3 * n_q, d_t:] = qu[:, d_t:]
-    blocks[3 * n_q:4 * n_q, d_t:] = -qu[:, d_t:]
-    keys = eng.topk_search(_query_operand(eng, blocks, prec), db, 1, prec)
+def _top1_scores(eng: Engine, q_rows: torch.Tensor, db: Operand, prec: str) -> Optional[torch.Tensor]:
+    """Best score of every query row against ``db`` (float64), None if the rescore bound overflowed."""
+    keys = eng.topk_search(_query_operand(eng, q_rows, prec), db, 1, prec)
     if prec == "rescore":
         _, overflow = eng.consume_status()
         if overflow:
             return None
-    top = eng.vote_metrics(keys, torch.zeros((db.n,), dtype=torch.int32, device=eng.device),
-                           torch.zeros((4 * n_q,), dtype=torch.int32, device=eng.device), 1, k_list=[],
-                           per_query=False, want_lists=True)["top_scores"][:, 0].double()
-    t_max, t_min = top[0 * n_q:1 * n_q], -top[1 * n_q:2 * n_q]
-    i_max, i_min = top[2 * n_q:3 * n_q], -top[3 * n_q:4 * n_q]
-    return (t_min, t_max - t_min + 1e-8), (i_min, i_max - i_min + 1e-8)
+    n_q = int(q_rows.shape[0])
+    zeros_db = torch.zeros((db.n,), dtype=torch.int32, device=eng.device)
+    zeros_q = torch.zeros((n_q,), dtype=torch.int32, device=eng.device)
+    return eng.vote_metrics(keys, zeros_db, zeros_q, 1, k_list=[], per_query=False,
+                            want_lists=True)["top_scores"][:, 0].double()
+
+
+def _minmax_stats(eng: Engine, db: Operand, qu: torch.Tensor, d_t: int, prec: str):
+    """(min, max - min + 1e-8) per query and modality: max / min of a query's scores = Top-1 of q and of -q.
+    When the modality boundary falls on a k-chunk boundary each modality is searched against its own column
+    slice of the fused operand (half the contraction length); otherwise the four zero-padded query blocks
+    [t;0], [-t;0], [0;i], [0;-i] go against the fused rows."""
+    n_q, dim = int(qu.shape[0]), int(qu.shape[1])
+    out = []
+    sliced = prec == "fp32" or (d_t % 64 == 0 and dim % 64 == 0)
+    for c0, c1 in ((0, d_t), (d_t, dim)):
+        if sliced:
+            seg = qu[:, c0:c1]
+            top = _top1_scores(eng, torch.cat([seg, -seg]).contiguous(), _column_view(db, c0, c1), prec)
+        else:
+            blocks = torch.zeros((2 * n_q, dim), dtype=torch.float32, device=eng.device)
+            blocks[:n_q, c0:c1] = qu[:, c0:c1]
+            blocks[n_q:, c0:c1] = -qu[:, c0:c1]
+            top = _top1_scores(eng, blocks, db, prec)
+        if top is None:
+            return None
+        lo = -top[n_q:]
+        out.append((lo, top[:n_q] - lo + 1e-8))
+    return out[0], out[1]
+
+
+class LateFusionIndex:
+    """A database prepared once for late-fusion searches (unit text rows | unit image rows + the planes of the search
+    arm resident in HBM); the z-score moments (column sums + Gram matrix per modality, float64) are computed on first
+    use and kept, so every later query batch only pays O(Q D^2) for its statistics."""
+
+    def __init__(self, db_text, db_image, k: int = 10, precision: str = "auto", expected_queries: int = 4096,
+                 engine: Optional[Engine] = None):
+        self.eng = engine or get_engine()
+        self.n_db, self.d_t, self.d_i = int(db_text.shape[0]), int(db_text.shape[1]), int(db_image.shape[1])
+        if self.n_db == 0:
+            raise ValueError("late fusion: empty database")
+        if int(db_image.shape[0]) != self.n_db:
+            raise ValueError("late fusion: text and image databases have different row counts")
+        self.prec = self.eng.pick_precision(max(expected_queries, 1), self.n_db, self.d_t + self.d_i, k, precision)
+        if self.prec == "bf16x1":
+            raise ValueError("late fusion needs fp32-level scores (fp32, bf16x3 or rescore)")
+        self.db = _db_operand(self.eng, db_text, db_image, self.prec)
+        self._moments = None
+
+    def moments(self):
+        if self._moments is None:
+            f32 = self.db.f32
+            self._moments = (database_moments(self.eng, f32[:, :self.d_t]), database_moments(self.eng, f32[:, self.d_t:]))
+        return self._moments
+
+    def _zscore(self, moments, q_rows: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        s, gram = moments
+        q64 = q_rows.double()
+        mean = (q64 @ s) / self.n_db
+        e2 = ((q64 @ gram) * q64).sum(dim=1) / self.n_db
+        std = torch.sqrt(torch.clamp(e2 - mean * mean, min=0.0))
+        return mean, std + 1e-8
+
+    def search(self, q_text, q_image, text_weight: float, mode: int, k: int) -> Optional[torch.Tensor]:
+        """Packed Top-k keys [Q, k]; None if the rescore bound overflowed (the caller rebuilds with bf16x3)."""
+        eng, prec, d_t, d_i = self.eng, self.prec, self.d_t, self.d_i
+        if prec == "rescore" and k > _RESCORE_MAX_K:
+            raise ValueError(f"this index was built for the rescore arm (K <= {_RESCORE_MAX_K})")
+        qu = eng.normalize_fuse(q_text, q_image, 1.0, 1.0, native.NF_SEGNORM, want_f32=True).f32      # [Q, Dt + Di]
+        n_q = int(qu.shape[0])
+        w64 = float(text_weight)
+        if mode == native.SCORE_ZSCORE:
+            m_t, m_i = self.moments()
+            a_t, b_t = self._zscore(m_t, qu[:, :d_t])
+            a_i, b_i = self._zscore(m_i, qu[:, d_t:])
+        elif mode == native.SCORE_MINMAX:
+            st = _minmax_stats(eng, self.db, qu, d_t, prec)
+            if st is None:
+                return None
+            (a_t, b_t), (a_i, b_i) = st
+        else:
+            zero = torch.zeros((n_q,), dtype=torch.float64, device=eng.device)
+            a_t, b_t, a_i, b_i = zero, zero + 1.0, zero, zero + 1.0
+        # the reference applies mean / std (min / range) as fp32 scalars: (scores - f32(a)) / f32(b), then w * (.)
+        a_t, b_t = a_t.float().double(), b_t.float().double()
+        a_i, b_i = a_i.float().double(), b_i.float().double()
+        g_t = float(np.float32(w64)) / b_t
+        g_i = float(np.float32(1.0 - w64)) / b_i
+        offset = (-(g_t * a_t + g_i * a_i)).float().contiguous()
+        g_t32, g_i32 = g_t.float().contiguous(), g_i.float().contiguous()
+        scaled = qu.clone()
+        if n_q:
+            with torch.cuda.device(eng.device):
+                native.check(eng.lib.emr2a_scale_segments(scaled.data_ptr(), n_q, d_t, d_i, _ld(scaled), g_t32.data_ptr(),
+                                                          g_i32.data_ptr(), eng._stream()))
+            eng.launches += 1
+        keys = eng.topk_search(_query_operand(eng, scaled, prec), self.db, k, prec)
+        if prec == "rescore":
+            _, overflow = eng.consume_status()
+            if overflow:
+                return None
+        if n_q:
+            with torch.cuda.device(eng.device):
+                native.check(eng.lib.emr2a_keys_add_offset(keys.data_ptr(), n_q, k, offset.data_ptr(), eng._stream()))
+            eng.launches += 1
+        return keys
 
 
 def late_fusion_search(db_text, db_image, q_text, q_image, text_weight: float, mode: int, k: int,
                        precision: str = "auto", engine: Optional[Engine] = None) -> torch.Tensor:
     """Packed Top-k keys [Q, k] of  w * norm(cos_T) + (1 - w) * norm(cos_I)  per query, best first, scores = the
-    fused (normalised) scores.  ``mode``: native.SCORE_ZSCORE / SCORE_MINMAX / SCORE_NONE."""
+    fused (normalised) scores.  ``mode``: native.SCORE_ZSCORE / SCORE_MINMAX / SCORE_NONE.  One-shot form of
+    ``LateFusionIndex`` (build + search)."""
     eng = engine or get_engine()
-    n_db, d_t, d_i = int(db_text.shape[0]), int(db_text.shape[1]), int(db_image.shape[1])
-    n_q = int(q_text.shape[0])
-    if n_db == 0:
-        raise ValueError("late_fusion_search: empty database")
-    prec = eng.pick_precision(max(n_q, 1), n_db, d_t + d_i, k, precision)
-    if prec == "bf16x1":
-        raise ValueError("late_fusion_search needs fp32-level scores (fp32, bf16x3 or rescore)")
-    db = _db_operand(eng, db_text, db_image, prec)
-    qu = eng.normalize_fuse(q_text, q_image, 1.0, 1.0, native.NF_SEGNORM, want_f32=True).f32      # [Q, Dt + Di]
-    w64 = float(text_weight)
-    if mode == native.SCORE_ZSCORE:
-        a_t, b_t = _zscore_stats(eng, db.f32[:, :d_t], qu[:, :d_t])
-        a_i, b_i = _zscore_stats(eng, db.f32[:, d_t:], qu[:, d_t:])
-    elif mode == native.SCORE_MINMAX:
-        st = _minmax_stats(eng, db, qu, d_t, prec)
-        if st is None:                                            # rescore bound overflowed: exact-enough 3-pass arm
-            return late_fusion_search(db_text, db_image, q_text, q_image, text_weight, mode, k, "bf16x3", eng)
-        (a_t, b_t), (a_i, b_i) = st
-    else:
-        zero, one = torch.zeros((n_q,), dtype=torch.float64, device=eng.device), torch.ones((n_q,), dtype=torch.float64, device=eng.device)
-        a_t, b_t, a_i, b_i = zero, one, zero, one
-    # the reference applies mean / std (min / range) as fp32 scalars: (scores - f32(a)) / f32(b), then w * (.)
-    a_t, b_t = a_t.float().double(), b_t.float().double()
-    a_i, b_i = a_i.float().double(), b_i.float().double()
-    g_t = float(np.float32(w64)) / b_t
-    g_i = float(np.float32(1.0 - w64)) / b_i
-    offset = (-(g_t * a_t + g_i * a_i)).float().contiguous()
-    g_t32, g_i32 = g_t.float().contiguous(), g_i.float().contiguous()
-    scaled = qu.clone()
-    if n_q:
-        with torch.cuda.device(eng.device):
-            native.check(eng.lib.emr2a_scale_segments(scaled.data_ptr(), n_q, d_t, d_i, _ld(scaled), g_t32.data_ptr(),
-                                                      g_i32.data_ptr(), eng._stream()))
-        eng.launches += 1
-    keys = eng.topk_search(_query_operand(eng, scaled, prec), db, k, prec)
-    if prec == "rescore":
-        _, overflow = eng.consume_status()
-        if overflow:
-            return late_fusion_search(db_text, db_image, q_text, q_image, text_weight, mode, k, "bf16x3", eng)
-    if n_q:
-        with torch.cuda.device(eng.device):
-            native.check(eng.lib.emr2a_keys_add_offset(keys.data_ptr(), n_q, k, offset.data_ptr(), eng._stream()))
-        eng.launches += 1
+    index = LateFusionIndex(db_text, db_image, k, precision, max(int(q_text.shape[0]), 1), eng)
+    keys = index.search(q_text, q_image, text_weight, mode, k)
+    if keys is None:                              # rescore bound overflowed: the 3-pass arm is exact enough by itself
+        del index
+        index = LateFusionIndex(db_text, db_image, k, "bf16x3", max(int(q_text.shape[0]), 1), eng)
+        keys = index.search(q_text, q_image, text_weight, mode, k)
     return keys

@@ -367,8 +367,13 @@ class CVRetrievalEvaluator:
         eng = get_engine()
         n = len(labels)
         ids = list(patient_ids) if patient_ids is not None else None
-        label_list = labels.tolist() if isinstance(labels, np.ndarray) else list(labels)
-        classes, (codes,) = encode(label_list)
+        if isinstance(labels, np.ndarray) and labels.dtype.kind in "iub":
+            # integer class labels: classes = sorted(set(labels)) without a python pass over the cases
+            uniq, codes = np.unique(labels, return_inverse=True)
+            classes, codes, label_list = uniq.tolist(), codes.astype(np.int32), labels
+        else:
+            label_list = labels.tolist() if isinstance(labels, np.ndarray) else list(labels)
+            classes, (codes,) = encode(label_list)
         codes_t = eng.to_device(codes, torch.int32)
         mats = {}
         if need_img:

@@ -28,13 +28,14 @@ def _oracle_topk(oracle, db_t, db_i, q_t, q_i, w, mode, k):
     return np.array(idx), np.array(sc)
 
 
-@pytest.mark.parametrize("mode", ["zscore", "minmax", "none"])
+@pytest.mark.parametrize("mode,d_t,d_i", [("zscore", 72, 56), ("minmax", 72, 56), ("none", 72, 56),
+                                          ("minmax", 64, 128)])       # 64 | 128: min-max on column-sliced operands
 @pytest.mark.parametrize("prec", ["fp32", "bf16x3", "rescore"])
-def test_fused_late_search_matches_materialised_reference(oracle, mode, prec):
+def test_fused_late_search_matches_materialised_reference(oracle, mode, d_t, d_i, prec):
     from emr2a_b200.engine import get_engine, unpack_keys
     from emr2a_b200.late import late_fusion_search
     eng = get_engine()
-    db_t, db_i, q_t, q_i, _, _ = _data(6000, 150, 72, 56, seed=41)
+    db_t, db_i, q_t, q_i, _, _ = _data(6000, 150, d_t, d_i, seed=41)
     k, w = 5, 0.35
     keys = late_fusion_search(db_t, db_i, q_t, q_i, w, MODES[mode], k, precision=prec, engine=eng)
     sc, idx = unpack_keys(keys)
@@ -108,3 +109,22 @@ def test_scale_segments_and_key_offset_kernels():
     sc1, idx1 = unpack_keys(keys)
     assert np.array_equal(idx0, idx1) and np.all(idx1[:, 37:] == -1)
     assert np.array_equal(sc1[:, :37], sc0[:, :37] + off.cpu().numpy()[:, None])
+
+
+def test_resident_late_index_reuses_moments_and_matches_one_shot(oracle):
+    import torch
+    from emr2a_b200.engine import get_engine
+    from emr2a_b200.late import LateFusionIndex, late_fusion_search
+    eng = get_engine()
+    db_t, db_i, q_t, q_i, _, _ = _data(5000, 120, 40, 48, seed=8)
+    index = LateFusionIndex(db_t, db_i, k=5, precision="fp32", engine=eng)
+    first = index.search(q_t[:60], q_i[:60], 0.3, MODES["zscore"], 5)
+    cached = index._moments
+    second = index.search(q_t[60:], q_i[60:], 0.3, MODES["zscore"], 5)
+    assert index._moments is cached
+    whole = late_fusion_search(db_t, db_i, q_t, q_i, 0.3, MODES["zscore"], 5, precision="fp32", engine=eng)
+    assert torch.equal(torch.cat([first, second]), whole)
+    mm = index.search(q_t, q_i, 0.3, MODES["minmax"], 5)
+    assert torch.equal(mm, late_fusion_search(db_t, db_i, q_t, q_i, 0.3, MODES["minmax"], 5, precision="fp32", engine=eng))
+    with pytest.raises(ValueError):
+        LateFusionIndex(db_t, db_i[:10], engine=eng)

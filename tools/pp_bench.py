@@ -50,3 +50,8 @@ args = (dt[:n_db], di[:n_db], dt[n_db:], di[n_db:])
 for name, mode in (("none", native.SCORE_NONE), ("zscore", native.SCORE_ZSCORE), ("minmax", native.SCORE_MINMAX)):
     ms = timed(lambda: late_fusion_search(*args, 0.4, mode, k, engine=eng), reps=3, warm=1)
     print(f"late fusion '{name}' {n_db}x({dm}+{dm}), {n_q} queries, K={k}: {ms:.1f} ms/step = {n_q/ms*1e3:.0f} queries/s", flush=True)
+from emr2a_b200.late import LateFusionIndex
+index = LateFusionIndex(args[0], args[1], k=k, expected_queries=n_q, engine=eng)
+for name, mode in (("none", native.SCORE_NONE), ("zscore", native.SCORE_ZSCORE), ("minmax", native.SCORE_MINMAX)):
+    ms = timed(lambda: index.search(args[2], args[3], 0.4, mode, k), reps=3, warm=1)
+    print(f"resident LateFusionIndex '{name}': {ms:.1f} ms/step = {n_q/ms*1e3:.0f} queries/s", flush=True)
