@@ -88,7 +88,8 @@ def sharded_search_and_vote(eng, db_segs_local: Sequence, q_segs: Sequence, db_l
 def sharded_cv_search_and_vote(eng, segs_local: Sequence, labels_global, folds_global, n_classes: int, k: int,
                                row_offset: int, flags: int, q_weights=(1.0, 1.0), k_list=(1, 3, 5),
                                precision: str = "auto", n_folds: Optional[int] = None, q_block: int = 262144,
-                               fold_sorted: bool = True, want_lists: bool = False) -> Dict[str, torch.Tensor]:
+                               fold_sorted: bool = True, want_lists: bool = False,
+                               full_segs: Optional[Sequence] = None) -> Dict[str, torch.Tensor]:
     """The whole CV loop over a row-sharded cohort: EVERY case is a query against the cases of the OTHER folds
     (utils/cv_evaluator.py:349-376 builds exactly these train/test pairs, one fold at a time), database rows
     sharded over the ranks (``segs_local`` = this rank's rows ``[row_offset, row_offset + n_local)`` of every
@@ -100,6 +101,8 @@ def sharded_cv_search_and_vote(eng, segs_local: Sequence, labels_global, folds_g
     query block would make ranks whose shard lies in the block's own fold (nothing to do: all tiles skipped) wait
     for the others.  ``fold_sorted`` promises ``folds_global`` is non-decreasing (rows in fold order) so whole
     tiles of a single fold are skipped; pass False for arbitrary fold vectors (per-element mask only).
+
+    ``full_segs``: the rows of ALL cases, if this rank already holds them (then nothing is all-gathered).
 
     Returns per-fold counters (``hit_counts [F, nk]``, ``vote_counts [F, 3]``, ``confusion [F, 2, C, C]``,
     ``group_sizes [F]``), ``unverified`` and, with ``want_lists``, the per-query outputs of all N cases
@@ -116,7 +119,9 @@ def sharded_cv_search_and_vote(eng, segs_local: Sequence, labels_global, folds_g
     dim = sum(int(m.shape[1]) for m in mats)
     prec = eng.pick_precision(n, n, dim, k, precision)
     # (1) one all-gather of the raw rows (equal-sized, zero-padded shards)
-    if world > 1:
+    if full_segs is not None:
+        full = [eng._embedding(x)[0] for x in full_segs if x is not None]
+    elif world > 1:
         per = shard_range(n, 0, world)[1]
         full = []
         for m in mats:
@@ -158,7 +163,8 @@ def sharded_cv_search_and_vote(eng, segs_local: Sequence, labels_global, folds_g
         st = st.cpu()
         if int(st[1]):
             return sharded_cv_search_and_vote(eng, segs_local, labels_global, folds_global, n_classes, k, row_offset,
-                                              flags, q_weights, k_list, "bf16x3", n_folds, q_block, fold_sorted, want_lists)
+                                              flags, q_weights, k_list, "bf16x3", n_folds, q_block, fold_sorted, want_lists,
+                                              full_segs)
         unverified = int(st[0])
     res: Dict[str, torch.Tensor] = {}
     for name in ("hit_counts", "vote_counts", "confusion", "group_sizes"):

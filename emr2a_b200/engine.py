@@ -432,14 +432,17 @@ class Engine:
                            flags: int = native.NF_ROWNORM, q_weights=(1.0, 1.0),
                            k_list: Sequence[int] = (1, 3, 5), precision: str = "auto",
                            n_folds: Optional[int] = None, q_block: int = 1 << 20,
-                           want_lists: bool = True) -> Dict[str, torch.Tensor]:
+                           want_lists: bool = True, distributed: Optional[bool] = None) -> Dict[str, torch.Tensor]:
         """The whole CV loop in one pass: every row is a query against the rows of the OTHER folds
         (utils/cv_evaluator.py:349-376 builds exactly these train/test pairs, one fold at a time).
         Rows are brought into fold order so the search can skip whole tiles of the query's own fold;
         indices and per-query outputs are mapped back to the caller's row order.  Counters are
         per fold (``hit_counts[f]``, ``vote_counts[f]``, ``confusion[f]``, ``group_sizes[f]``).
         Equals the reference's per-fold evaluation whenever the preprocessing does not depend on
-        the fold (the rows passed in are the processed embeddings)."""
+        the fold (the rows passed in are the processed embeddings).
+        ``distributed`` (default: automatic): under ``torchrun`` with an NCCL process group, when every rank
+        calls this with the same arrays, each rank searches against its own shard of the rows and the Top-K
+        lists are exchanged over NCCL -- same results, bit for bit, in 1/world of the time."""
         folds_t = self.to_device(folds, torch.uint8)
         n = int(folds_t.shape[0])
         if n_folds is None:
@@ -455,6 +458,19 @@ class Engine:
             folds_t = folds_t.index_select(0, perm)
         dim = sum(int(m.shape[1]) for m in mats)
         prec = self.pick_precision(n, n, dim, k, precision)
+        import torch.distributed as tdist
+        if distributed is None:
+            distributed = (tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1
+                           and tdist.get_backend() == "nccl" and n >= 256 * tdist.get_world_size())
+        if distributed:
+            # one process per GPU (torchrun), every rank called with the same arrays: this rank searches all queries
+            # against ITS shard of the fold-ordered rows, Top-K lists are exchanged over NCCL (emr2a_b200/dist.py)
+            from .dist import shard_range, sharded_cv_search_and_vote
+            lo, hi = shard_range(n, tdist.get_rank(), tdist.get_world_size())
+            res = sharded_cv_search_and_vote(self, [m[lo:hi] for m in mats], labels_t, folds_t, n_classes, k, lo, flags,
+                                             q_weights, k_list, prec, n_folds, min(q_block, 1 << 18), True, want_lists,
+                                             full_segs=mats)
+            return self._cv_unpermute(res, perm, want_lists)
         seg1 = mats[1] if len(mats) > 1 else None
         db = self.prepare(mats[0], seg1, 1.0, 1.0, flags, prec)
         same_q = float(q_weights[0]) == 1.0 and float(q_weights[1]) == 1.0
@@ -473,7 +489,7 @@ class Engine:
                 u, overflow = self.consume_status()
                 if overflow:
                     return self.cv_search_and_vote(segs, labels, folds, n_classes, k, flags, q_weights, k_list,
-                                                   "bf16x3", n_folds, q_block, want_lists)
+                                                   "bf16x3", n_folds, q_block, want_lists, False)
                 unverified += u
         res: Dict[str, torch.Tensor] = {}
         for name in ("hit_counts", "vote_counts", "confusion", "group_sizes"):
@@ -482,19 +498,24 @@ class Engine:
                      if nm in outs[0]]
         for name in per_query:
             res[name] = torch.cat([o[name] for o in outs])
-        if perm is not None:                                   # back to the caller's row order / row numbers
-            if "top_idx" in res:
-                ti = res["top_idx"]
-                res["top_idx"] = torch.where(ti >= 0, perm[ti.clamp(min=0)], ti)
-            for name in per_query:
-                if name == "keys":
-                    continue
+        res["precision"] = prec
+        res["unverified"] = unverified
+        return self._cv_unpermute(res, perm, want_lists)
+
+    @staticmethod
+    def _cv_unpermute(res: Dict[str, torch.Tensor], perm: Optional[torch.Tensor], want_lists: bool) -> Dict[str, torch.Tensor]:
+        """Per-query outputs of a fold-ordered CV pass back to the caller's row order / row numbers."""
+        if perm is None:
+            return res
+        if "top_idx" in res:
+            ti = res["top_idx"]
+            res["top_idx"] = torch.where(ti >= 0, perm[ti.clamp(min=0)], ti)
+        for name in ("top_idx", "top_scores", "top_labels", "pred_top1", "pred_vote", "pred_weighted"):
+            if name in res:
                 out = torch.empty_like(res[name])
                 out[perm] = res[name]
                 res[name] = out
-            res.pop("keys", None)                              # packed keys carry fold-order indices: not exported
-        res["precision"] = prec
-        res["unverified"] = unverified
+        res.pop("keys", None)                                  # packed keys carry fold-order indices: not exported
         return res
 
     # ----------------------------------------------- host-buffer (end-to-end) path

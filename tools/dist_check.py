@@ -41,10 +41,19 @@ ft, _ = synth.device_block(0, n_cv, d, c, 20, dev, label_seed=19)
 for prec in ("rescore", "bf16x3"):
     r = sharded_cv_search_and_vote(eng, (xi, xt), lab, fold, c, 5, lo, flags, k_list=[1, 3, 5], precision=prec,
                                    n_folds=n_folds, q_block=65536, want_lists=True)
-    full = eng.cv_search_and_vote((fi, ft), lab, fold, c, 5, flags=flags, k_list=[1, 3, 5], precision=prec, n_folds=n_folds)
-    same = all(torch.equal(r[key], full[key]) for key in ("hit_counts", "vote_counts", "confusion", "group_sizes",
-                                                           "top_idx", "top_scores", "pred_vote", "pred_weighted"))
+    full = eng.cv_search_and_vote((fi, ft), lab, fold, c, 5, flags=flags, k_list=[1, 3, 5], precision=prec, n_folds=n_folds,
+                                  distributed=False)
+    names = ("hit_counts", "vote_counts", "confusion", "group_sizes", "top_idx", "top_scores", "pred_vote", "pred_weighted")
+    same = all(torch.equal(r[key], full[key]) for key in names)
     print(f"rank {rank}/{world} cv {prec}: sharded == single-GPU: {same} (unverified {r['unverified']})", flush=True)
+    ok = ok and same
+    # the engine call itself goes multi-GPU under torchrun (every rank passes the same arrays), here with UNSORTED folds
+    mixed = ((torch.arange(n_cv, device=dev, dtype=torch.int64) * 7919) % n_folds).to(torch.uint8)
+    auto = eng.cv_search_and_vote((fi, ft), lab, mixed, c, 5, flags=flags, k_list=[1, 3, 5], precision=prec, n_folds=n_folds)
+    single = eng.cv_search_and_vote((fi, ft), lab, mixed, c, 5, flags=flags, k_list=[1, 3, 5], precision=prec, n_folds=n_folds,
+                                    distributed=False)
+    same = all(torch.equal(auto[key], single[key]) for key in names)
+    print(f"rank {rank}/{world} cv {prec}: engine auto-distributed == single-GPU: {same}", flush=True)
     ok = ok and same
 dist.barrier(); dist.destroy_process_group()
 sys.exit(0 if ok else 1)
