@@ -98,3 +98,77 @@ def test_evaluate_processed_fold_matches_oracle(oracle, n_tr, n_te, d, top_k, fu
     if safe.all():
         for key in ("top1", "top3", "top5", "vote_acc", "weighted_vote_acc", "macro_precision", "macro_recall", "macro_f1"):
             assert abs(float(r[key]) - o[key]) < 1e-12, key
+
+
+@settings(max_examples=20, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(n=st.integers(2, 700), d=st.integers(1, 150), p=st.integers(1, 160), seed=st.integers(0, 10_000),
+       constant_col=st.booleans(), big_offset=st.booleans())
+def test_preprocessing_matches_oracle_on_random_shapes(eng, oracle, n, d, p, seed, constant_col, big_offset):
+    """StandardScaler + exact PCA on the device against the numpy oracle: random fold shapes incl. n <= d (rank
+    deficient), pca_dim beyond min(n - 1, d), constant features, large means relative to the spread."""
+    from sklearn.preprocessing import StandardScaler
+    from emr2a_b200 import preprocess as pp
+    rng = np.random.default_rng(seed)
+    basis, _ = np.linalg.qr(rng.standard_normal((d, d)))
+    x = (rng.standard_normal((n + 7, d)) * (0.9 ** np.arange(d))[None, :]) @ basis.T
+    x = x * rng.uniform(0.2, 5.0, d)[None, :] + (rng.uniform(-1000, 1000, d) if big_offset else rng.uniform(-3, 3, d))[None, :]
+    x = x.astype(np.float32)
+    if constant_col:
+        x[:, rng.integers(0, d)] = 1.75
+    tr, te = x[:n], x[n:]
+    tf = pp.fit(tr, p, eng)
+    sk = StandardScaler().fit(tr)
+    np.testing.assert_allclose(tf.mean.cpu().numpy(), sk.mean_, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(tf.scale.cpu().numpy(), sk.scale_, rtol=1e-9)
+    n_comp = min(p, n - 1, d)
+    assert tf.n_components == max(n_comp, 0)
+    got_tr = pp.transform(tf, tr, eng, normalize=False).cpu().numpy()
+    got_te = pp.transform(tf, te, eng, normalize=False).cpu().numpy()
+    if n_comp <= 0:
+        np.testing.assert_allclose(got_tr, sk.transform(tr), rtol=1e-6, atol=1e-6)
+        return
+    z_tr, z_te = sk.transform(tr), sk.transform(te)
+    comps, zmean = oracle.pca_exact_fit(z_tr, n_comp)
+    want_tr = (z_tr.astype(np.float64) - zmean) @ comps.T
+    want_te = (z_te.astype(np.float64) - zmean) @ comps.T
+    # principal axes whose eigenvalue is well separated from its neighbours are determined to fp32 accuracy; the
+    # others (rank-deficient tail, near-equal eigenvalues) may rotate inside their eigenspace -- compare the former
+    ev = np.linalg.eigvalsh(np.cov(z_tr.T.astype(np.float64)) if d > 1 else np.array([[z_tr.var(ddof=1)]]))[::-1]
+    ev = np.concatenate([ev, [0.0]])
+    sep = np.minimum(np.abs(np.diff(ev))[:n_comp], np.abs(np.diff(np.concatenate([[np.inf], ev])))[:n_comp])
+    good = (sep > 1e-2 * ev[0]) & (ev[:n_comp] > 1e-6 * ev[0])
+    scale = max(1.0, float(np.abs(want_tr).max()))
+    if good.any():
+        assert np.max(np.abs(got_tr[:, good] - want_tr[:, good])) < 2e-4 * scale
+        assert np.max(np.abs(got_te[:, good] - want_te[:, good])) < 2e-4 * scale
+    # whatever the basis inside degenerate eigenspaces, it is orthonormal and spans the same variance
+    w = tf.components.cpu().numpy().astype(np.float64)
+    assert np.max(np.abs(w @ w.T - np.eye(n_comp))) < 1e-5
+    np.testing.assert_allclose(tf.explained_variance.cpu().numpy(), np.clip(ev[:n_comp], 0, None), rtol=1e-6,
+                               atol=1e-9 * max(ev[0], 1e-30))
+
+
+@settings(max_examples=15, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(n=st.integers(8, 1500), q=st.integers(1, 60), d_t=st.integers(1, 90), d_i=st.integers(1, 90), k=st.integers(1, 8),
+       mode=st.sampled_from(["zscore", "minmax", "none"]), w=st.floats(0.05, 0.95), seed=st.integers(0, 10_000))
+def test_fused_late_fusion_matches_materialised_on_random_shapes(eng, oracle, n, q, d_t, d_i, k, mode, w, seed):
+    """Matrix-free z-score / min-max late fusion (emr2a_b200/late.py) against the reference's per-query arithmetic."""
+    from emr2a_b200.engine import unpack_keys
+    from emr2a_b200.late import late_fusion_search
+    rng = np.random.default_rng(seed)
+    db_t = rng.standard_normal((n, d_t)).astype(np.float32) * 2.0
+    db_i = rng.standard_normal((n, d_i)).astype(np.float32) + 0.3
+    q_t = rng.standard_normal((q, d_t)).astype(np.float32)
+    q_i = rng.standard_normal((q, d_i)).astype(np.float32) * 0.1
+    k = min(k, n)
+    keys = late_fusion_search(db_t, db_i, q_t, q_i, w, {"none": 0, "zscore": 1, "minmax": 2}[mode], k,
+                              precision="fp32", engine=eng)
+    sc, idx = unpack_keys(keys)
+    for j in range(q):
+        fused = oracle.fuse_late_scores(oracle.cosine_one_vs_db(q_t[j], db_t), oracle.cosine_one_vs_db(q_i[j], db_i), w, mode)
+        top = oracle.topk_desc(fused, k)
+        tol = 2e-5 * max(1.0, float(np.abs(fused).max()))
+        assert np.max(np.abs(sc[j] - fused[top])) < tol
+        srt = np.sort(fused)[::-1][:k + 1]
+        if len(srt) < 2 or np.abs(np.diff(srt)).min() > 4 * tol:
+            assert np.array_equal(idx[j], top)
