@@ -605,9 +605,9 @@ def main():
     passes = {"bf16x3": 3, "bf16x1": 1, "fp32": 1, "rescore": 1}[res["precision"]]
     achieved = flops / (k2_avg_ms / 1e3) / 1e12
     # DRAM bytes of the dominant kernel (tc2_topk_kernel<1,16,0>, full 1M-row shard) from the committed ncu
-    # --set full capture profiles/r01_ncu_step_c2_rescore.md: 3.574 GB read + 0.034 GB written per launch
+    # --set full capture profiles/r01_ncu_step_c2_head.md: 3.418 GB read + 0.036 GB written per launch
     # (algorithmic: 2.05 GB bf16 database plane + 20 MB query plane + 31 MB partial lists).
-    traffic = 3.608e9 if (res["precision"] == "rescore" and world == 1 and args.workload == "c2") else None
+    traffic = 3.453e9 if (res["precision"] == "rescore" and world == 1 and args.workload == "c2") else None
     t_peak, t_src = tensor_peak(pk, ms_per_step * args.steps / 1e3)
     roofline = {"bound": "tensor", "achieved": achieved, "peak": t_peak, "unit": "TFLOP/s",
                 "frac": achieved / t_peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
