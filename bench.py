@@ -317,7 +317,6 @@ def run_c1(args):
     import torch
     from emr2a_b200 import native, synth
     from emr2a_b200.engine import get_engine
-    from emr2a_b200.labels import encode
     from emr2a_b200.utils.cv_evaluator import CVRetrievalEvaluator
     sys.path.insert(0, os.path.join(REPO, "oracle"))
     import emr2a_oracle as oracle
@@ -448,7 +447,7 @@ def main():
     import torch.distributed as dist
     from emr2a_b200 import native, synth
     from emr2a_b200.dist import gather_keys, shard_range, sharded_search_and_vote
-    from emr2a_b200.engine import get_engine, unpack_keys
+    from emr2a_b200.engine import get_engine
 
     world = int(os.environ.get("WORLD_SIZE", 1))
     rank = int(os.environ.get("RANK", 0))

@@ -1,6 +1,6 @@
 """Whole reference pipeline at scale on one GPU: CVRetrievalEvaluator.run_cv_arrays = StratifiedKFold (host) +
 per-fold StandardScaler + exact PCA + fusion + Top-K + votes (device).  N x (512 + 512) -> pca_dim 128 each."""
-import os, sys, time, numpy as np, torch
+import os, sys, time, torch
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 import logging
