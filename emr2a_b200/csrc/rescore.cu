@@ -82,11 +82,22 @@ __device__ __forceinline__ void query_norms(const float* __restrict__ qrow, int 
   rq = fminf(sqrtf(r2) * 1.000002f, qs[1]);
 }
 
-template <bool VEC>
+// WPQ = warps per query.  1: a warp owns a query (throughput layout, 8 queries per block).  8: a BLOCK owns a query
+// and its 8 warps re-score 8 of the 64 candidates each -- for small batches (serving), where a single warp walking
+// 16 groups of dependent row gathers is pure latency (~90 us at D = 1024); selection and verification are then done
+// by warp 0 from the exact keys the warps exchanged through shared memory.
+template <bool VEC, int WPQ>
 __global__ void __launch_bounds__(256) rescore_select_kernel(const RescoreParams p) {
+  __shared__ uint64_t xkeys[WPQ == 1 ? 1 : 64];
   const int lane = threadIdx.x & 31;
-  const int64_t q = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int wq = WPQ == 1 ? 0 : (threadIdx.x >> 5);                      // this warp's share of the candidate groups
+  const int64_t q = WPQ == 1 ? (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5
+                             : static_cast<int64_t>(blockIdx.x);
   if (q >= p.Q) return;
+  if (WPQ > 1) {
+    if (threadIdx.x < 64) xkeys[threadIdx.x] = 0ull;
+    __syncthreads();
+  }
   // lane holds candidates lane and lane + 32
   uint64_t akey[2], ekey[2] = {0ull, 0ull};
   akey[0] = lane < p.KP ? p.approx[q * p.KP + lane] : 0ull;
@@ -113,6 +124,7 @@ __global__ void __launch_bounds__(256) rescore_select_kernel(const RescoreParams
         acc[c] = 0.f;
       }
       if (kk[0] == 0ull) { done = true; break; }      // lists are packed: nothing valid beyond the first empty slot
+      if (WPQ > 1 && (((h * 32 + g) >> 2) % WPQ) != wq) continue;      // another warp of the block takes this group
       if (VEC) {
         for (int e = lane * 4; e < p.D; e += 128) {
           const float4 x = __ldg(reinterpret_cast<const float4*>(qrow + e));
@@ -144,6 +156,14 @@ __global__ void __launch_bounds__(256) rescore_select_kernel(const RescoreParams
         if (lane == g + c && kk[c] != 0ull) ekey[h] = pack_key(s, key_index(kk[c]));
       }
     }
+  }
+  if (WPQ > 1) {                                     // gather the block's exact keys in warp 0
+    if (ekey[0] != 0ull) xkeys[lane] = ekey[0];
+    if (ekey[1] != 0ull) xkeys[32 + lane] = ekey[1];
+    __syncthreads();
+    if (wq != 0) return;
+    ekey[0] = xkeys[lane];
+    ekey[1] = xkeys[32 + lane];
   }
   // exact Top-K of the candidates
   uint64_t mine = 0ull;
@@ -314,9 +334,14 @@ int rescore_pipeline(const uint64_t* approx, int KP, const uint32_t* tau, const 
   p.q_fold = q_fold; p.db_fold = db_fold;
   auto al16 = [](const void* x) { return (reinterpret_cast<uintptr_t>(x) & 15) == 0; };
   const bool vec = (D % 4 == 0) && (ldq % 4 == 0) && (lddb % 4 == 0) && al16(q) && al16(db);
-  const unsigned blocks = static_cast<unsigned>((Q * 32 + 255) / 256);
-  if (vec) rescore_select_kernel<true><<<blocks, 256, 0, st>>>(p);
-  else rescore_select_kernel<false><<<blocks, 256, 0, st>>>(p);
+  if (Q <= 4 * static_cast<int64_t>(sm_count())) {        // small batch: a block per query (latency layout)
+    if (vec) rescore_select_kernel<true, 8><<<static_cast<unsigned>(Q), 256, 0, st>>>(p);
+    else rescore_select_kernel<false, 8><<<static_cast<unsigned>(Q), 256, 0, st>>>(p);
+  } else {
+    const unsigned blocks = static_cast<unsigned>((Q * 32 + 255) / 256);
+    if (vec) rescore_select_kernel<true, 1><<<blocks, 256, 0, st>>>(p);
+    else rescore_select_kernel<false, 1><<<blocks, 256, 0, st>>>(p);
+  }
   EMR2A_LAUNCH_CHECK("rescore_select_kernel");
   // exact re-scan of unverified queries; both kernels return at once when status[0] == 0
   const int Dp = (D + 3) & ~3;

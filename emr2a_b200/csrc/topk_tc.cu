@@ -251,7 +251,12 @@ static TcPlan tc_plan(int64_t Q, int64_t N, int K, bool has_fold, bool pairs, in
   const int sms = pairs ? sm_count() / 2 : sm_count();      // concurrent workers: CTAs or CTA pairs
   // pick the split count whose unit count fills whole waves of CTAs best
   int best_s = 1; double best_eff = -1.0;
-  const int64_t max_s = pl.n_tiles < 64 ? pl.n_tiles : 64;
+  // at most 64 splits -- except for small query batches: with fewer query tiles than 64 splits can spread over
+  // the workers, the cap rises to one unit per worker (148 CTAs / 74 pairs), so that a single-tile batch (serving,
+  // Q <= 256) streams the database with every SM instead of 64 of them
+  int64_t cap = 64;
+  if (pl.m_tiles * cap < sms) cap = sms;
+  const int64_t max_s = pl.n_tiles < cap ? pl.n_tiles : cap;
   int64_t first_s = min_splits < max_s ? min_splits : max_s;
   if (first_s < 1) first_s = 1;
   best_s = static_cast<int>(first_s);

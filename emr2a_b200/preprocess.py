@@ -13,7 +13,10 @@ Contract.  The scaler reproduces sklearn's ``StandardScaler`` (float64 statistic
 EXACT principal-component basis of the standardised train rows: float64 covariance, float64 symmetric
 eigen-decomposition, components ordered by decreasing eigenvalue, signs fixed by sklearn's
 ``svd_flip(u_based_decision=False)`` rule (largest-|.| entry of every component is positive).  That is what
-``PCA(svd_solver="full")`` / ``"covariance_eigh"`` compute up to their own fp32 rounding.  sklearn's ``"auto"``
+``PCA(svd_solver="full")`` / ``"covariance_eigh"`` compute up to their own fp32 rounding.  (The sign rule is
+ill-conditioned when the two largest entries of an axis tie -- every 2-feature fold has the axes (1, 1)/sqrt(2),
+(1, -1)/sqrt(2) -- and LAPACK / cuSOLVER may break such a tie differently; the sign of an axis flips train and test
+rows alike and leaves every cosine score unchanged.)  sklearn's ``"auto"``
 picks the *randomized* solver for mid-sized folds (e.g. 1600 x 512 -> 128) and the reference does not seed it, so
 the reference's own output there differs from run to run; the exact basis is deterministic.
 
