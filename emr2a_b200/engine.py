@@ -608,10 +608,9 @@ class DatabaseIndex:
     def rows(self) -> int:
         return self.operand.n
 
-    def search(self, q_segs: Sequence, q_labels=None, k: int = 10, q_weights=(1.0, 1.0), q_flags: Optional[int] = None,
-               k_list: Sequence[int] = (1, 3, 5), want_lists: bool = True) -> Dict[str, torch.Tensor]:
-        """K1 on the queries (host or device arrays) -> K2 against the resident rows -> K4 vote.  Without
-        ``q_labels`` the hit/vote counters are meaningless and only lists and predictions should be read."""
+    def _enqueue(self, q_segs: Sequence, q_labels, k: int, q_weights, q_flags: Optional[int], k_list: Sequence[int],
+                 want_lists: bool) -> Dict[str, torch.Tensor]:
+        """K1 (queries) -> K2 -> K4, stream-ordered, no host synchronisation; the rescore status stays on the device."""
         eng = self.engine
         prec = self.precision
         if prec == "rescore" and k > _RESCORE_MAX_K:
@@ -623,13 +622,83 @@ class DatabaseIndex:
         if q_labels is None:
             q_labels = torch.full((n_q,), -1, dtype=torch.int32, device=eng.device)
         res = eng.vote_metrics(keys, self.labels, q_labels, self.n_classes, k_list=k_list, want_lists=want_lists)
-        if prec == "rescore":
-            unverified, overflow = eng.consume_status()
-            if overflow:
-                raise Emr2aOverflow("rescore verification overflowed for this query batch; rebuild the index with "
-                                    "precision='bf16x3' for databases with very dense score neighbourhoods")
-            res["unverified"] = unverified
         res["keys"] = keys
+        if prec == "rescore":
+            res["status"] = eng.pop_status_tensor()
+        return res
+
+    @staticmethod
+    def _check_status(res: Dict[str, torch.Tensor]) -> None:
+        st = res.pop("status", None)
+        if st is None:
+            return
+        st = st.cpu()
+        if int(st[1]):
+            raise Emr2aOverflow("rescore verification overflowed for this query batch; rebuild the index with "
+                                "precision='bf16x3' for databases with very dense score neighbourhoods")
+        res["unverified"] = int(st[0])
+
+    def search(self, q_segs: Sequence, q_labels=None, k: int = 10, q_weights=(1.0, 1.0), q_flags: Optional[int] = None,
+               k_list: Sequence[int] = (1, 3, 5), want_lists: bool = True) -> Dict[str, torch.Tensor]:
+        """K1 on the queries (host or device arrays) -> K2 against the resident rows -> K4 vote.  Without
+        ``q_labels`` the hit/vote counters are meaningless and only lists and predictions should be read."""
+        res = self._enqueue(q_segs, q_labels, k, q_weights, q_flags, k_list, want_lists)
+        self._check_status(res)
+        return res
+
+    def capture(self, n_queries: int, k: int = 10, q_weights=(1.0, 1.0), q_flags: Optional[int] = None,
+                k_list: Sequence[int] = (1, 3, 5), want_lists: bool = True, seg_dims: Optional[Sequence[int]] = None
+                ) -> "GraphedSearch":
+        """Small-batch serving: the whole K1 -> K2 -> K4 sequence for batches of exactly ``n_queries`` queries captured
+        in ONE CUDA graph (the ~10 launches of a batch are launch-bound below a few hundred queries)."""
+        return GraphedSearch(self, n_queries, k, q_weights, q_flags, k_list, want_lists, seg_dims)
+
+
+class GraphedSearch:
+    """``DatabaseIndex.search`` for a fixed batch size as a CUDA graph.  Calling it copies the queries into the
+    graph's static input buffers, replays the graph and returns the graph's static output tensors (overwritten by
+    the next call)."""
+
+    def __init__(self, index: DatabaseIndex, n_queries: int, k: int, q_weights, q_flags, k_list, want_lists, seg_dims):
+        eng = index.engine
+        if seg_dims is None:
+            seg_dims = [index.operand.dim]
+        if sum(int(d) for d in seg_dims) != index.operand.dim or not 1 <= len(seg_dims) <= 2:
+            raise ValueError(f"capture: seg_dims {list(seg_dims)} do not add up to the index dimension {index.operand.dim}")
+        self.index, self.n_queries = index, int(n_queries)
+        self.q_in = [torch.zeros((self.n_queries, int(d)), dtype=torch.float32, device=eng.device) for d in seg_dims]
+        self.labels_in = torch.full((self.n_queries,), -1, dtype=torch.int32, device=eng.device)
+        args = (self.q_in, self.labels_in, k, q_weights, q_flags, list(k_list), want_lists)
+        side = torch.cuda.Stream(eng.device)                 # warm-up off the capture stream (lazy module loads etc.)
+        side.wait_stream(torch.cuda.current_stream(eng.device))
+        with torch.cuda.stream(side):
+            for t in self.q_in:
+                t.normal_()                                  # all-zero queries would tie every score
+            index._enqueue(*args)
+        torch.cuda.current_stream(eng.device).wait_stream(side)
+        eng._status_log.clear()
+        l0 = eng.launches
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = index._enqueue(*args)
+        self.launches_per_replay = eng.launches - l0
+        eng.launches = l0
+
+    def __call__(self, q_segs: Sequence, q_labels=None) -> Dict[str, torch.Tensor]:
+        eng = self.index.engine
+        if len(q_segs) != len(self.q_in):
+            raise ValueError("graphed search: number of query segments differs from the captured one")
+        for dst, src in zip(self.q_in, q_segs):
+            src_t = torch.from_numpy(np.ascontiguousarray(src, dtype=np.float32)) if isinstance(src, np.ndarray) else src
+            if tuple(src_t.shape) != tuple(dst.shape):
+                raise ValueError(f"graphed search: query block {tuple(src_t.shape)} != captured {tuple(dst.shape)}")
+            dst.copy_(src_t, non_blocking=True)
+        if q_labels is not None:
+            self.labels_in.copy_(eng.to_device(q_labels, torch.int32), non_blocking=True)
+        self.graph.replay()
+        eng.launches += self.launches_per_replay
+        res = dict(self.out)
+        self.index._check_status(res)
         return res
 
 

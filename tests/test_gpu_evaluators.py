@@ -258,3 +258,31 @@ def test_resident_index_matches_one_shot_search(oracle):
             assert np.array_equal(r["top_idx"].cpu().numpy(), one["top_idx"].cpu().numpy())
             assert np.array_equal(r["hit_counts"].cpu().numpy(), one["hit_counts"].cpu().numpy())
             assert np.array_equal(r["pred_weighted"].cpu().numpy(), one["pred_weighted"].cpu().numpy())
+
+
+@pytest.mark.parametrize("prec", ["rescore", "bf16x3", "fp32"])
+def test_graphed_small_batch_search_equals_eager(prec):
+    """DatabaseIndex.capture: the K1 -> K2 -> K4 sequence of a fixed-size batch as one CUDA graph, replayed on fresh
+    queries, gives exactly the eager results (and re-zeroes its counters on every replay)."""
+    import torch
+    from emr2a_b200 import native, synth
+    from emr2a_b200.engine import get_engine
+    eng = get_engine()
+    both = synth.two_modal(50_000 + 3 * 96, 64, 128, 3, seed=13)
+    db = {k: v[:50_000] for k, v in both.items()}
+    flags = native.NF_SEGNORM | native.NF_ROWNORM
+    index = eng.build_index((db["image"], db["text"]), db["labels"], 3, flags=flags, precision=prec, k=5)
+    graphed = index.capture(96, k=5, k_list=[1, 3, 5], seg_dims=[64, 128])
+    assert graphed.launches_per_replay >= 3
+    for b in range(3):
+        lo = 50_000 + b * 96
+        q = (both["image"][lo:lo + 96], both["text"][lo:lo + 96])
+        lab = both["labels"][lo:lo + 96]
+        eager = index.search(q, lab, k=5, k_list=[1, 3, 5])
+        got = graphed(q, lab)
+        for name in ("keys", "top_idx", "top_scores", "pred_vote", "pred_weighted", "hit_counts", "vote_counts", "confusion"):
+            assert torch.equal(got[name], eager[name]), (prec, b, name)
+    with pytest.raises(ValueError):
+        graphed((both["image"][:10], both["text"][:10]))
+    with pytest.raises(ValueError):
+        index.capture(8, seg_dims=[64, 64])

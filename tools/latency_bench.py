@@ -26,7 +26,19 @@ for prec in os.environ.get("PRECS", "rescore,bf16x3").split(","):
         e1.record(); torch.cuda.synchronize()
         wall = (time.perf_counter() - t0) / reps * 1e3
         ms = e0.elapsed_time(e1) / reps
+        g_ms = None
+        if q <= 1024:                                  # the same batch as one CUDA graph
+            graphed = index.capture(q, k=k, want_lists=False, seg_dims=[d, d])
+            for _ in range(3):
+                graphed((qi, qt), ql)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                graphed((qi, qt), ql)
+            torch.cuda.synchronize()
+            g_ms = (time.perf_counter() - t0) / reps * 1e3
+            del graphed
         plane_gb = n * 2 * d * 2 / 1e9 * (2 if prec == "bf16x3" else 1)
         print(f"[{prec}] Q={q:5d}: {ms:.3f} ms/batch (wall {wall:.3f}) = {q/ms*1e3:9.0f} queries/s; database plane stream "
-              f"{plane_gb/ms*1e3:.0f} GB/s; {2*q*n*2*d/ms/1e9:.0f} TFLOP/s", flush=True)
+              f"{plane_gb/ms*1e3:.0f} GB/s; {2*q*n*2*d/ms/1e9:.0f} TFLOP/s" + (f"; CUDA graph {g_ms:.3f} ms wall" if g_ms else ""), flush=True)
     del index
