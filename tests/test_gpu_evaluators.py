@@ -286,3 +286,26 @@ def test_graphed_small_batch_search_equals_eager(prec):
         graphed((both["image"][:10], both["text"][:10]))
     with pytest.raises(ValueError):
         index.capture(8, seg_dims=[64, 64])
+
+
+@pytest.mark.parametrize("n_q", [1, 48, 70])
+def test_resident_index_small_batches_are_padded_transparently(n_q):
+    """Batches of up to 256 queries are filled to a multiple of 64 rows inside DatabaseIndex.search (TMA loads of
+    partly out-of-bounds query tiles are slow); results and counters are those of the real queries only."""
+    import torch
+    from emr2a_b200 import native, synth
+    from emr2a_b200.engine import get_engine
+    eng = get_engine()
+    both = synth.two_modal(40_000 + n_q, 96, 32, 3, seed=21)
+    db = {k: v[:40_000] for k, v in both.items()}
+    qs = {k: v[40_000:] for k, v in both.items()}
+    flags = native.NF_SEGNORM | native.NF_ROWNORM
+    for prec in ("rescore", "bf16x3"):
+        one = eng.search_and_vote((db["image"], db["text"]), (qs["image"], qs["text"]), db["labels"], qs["labels"], 3, 5,
+                                  db_flags=flags, q_flags=flags, k_list=[1, 3, 5], precision=prec)
+        index = eng.build_index((db["image"], db["text"]), db["labels"], 3, flags=flags, precision=prec, k=5)
+        r = index.search((qs["image"], qs["text"]), qs["labels"], k=5, k_list=[1, 3, 5])
+        assert r["keys"].shape == (n_q, 5) and r["pred_vote"].shape == (n_q,)
+        for name in ("keys", "top_idx", "top_scores", "pred_vote", "pred_weighted", "hit_counts", "vote_counts",
+                     "confusion", "group_sizes"):
+            assert torch.equal(r[name], one[name]), (prec, name)
