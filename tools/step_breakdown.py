@@ -6,14 +6,14 @@ sys.path.insert(0, REPO)
 from emr2a_b200 import native, synth
 from emr2a_b200.engine import get_engine
 eng = get_engine(); dev = eng.device
-n, d, q, k, c = int(os.environ.get("N", 1_000_000)), 512, 10_000, 10, 3
+n, d, q, k, c = int(os.environ.get("N", 1_000_000)), 512, int(os.environ.get("Q", 10_000)), 10, 3
 flags = native.NF_SEGNORM | native.NF_ROWNORM
 di, _ = synth.device_block(0, n, d, c, 11, dev, label_seed=11); dt, _ = synth.device_block(0, n, d, c, 12, dev, label_seed=11)
 qi, ql = synth.device_block(50_003_968, q, d, c, 11, dev, label_seed=11); qt, _ = synth.device_block(50_003_968, q, d, c, 12, dev, label_seed=11)
 labels = synth.device_labels(0, n, c, 11, dev)
 prec = os.environ.get("PREC", "rescore")
 def ev(): return torch.cuda.Event(enable_timing=True)
-for it in range(4):
+for it in range(6):
     e = [ev() for _ in range(6)]
     e[0].record(); db = eng.prepare(di, dt, 1.0, 1.0, flags, prec)
     e[1].record(); qs = eng.prepare(qi, qt, 1.0, 1.0, flags, prec)
