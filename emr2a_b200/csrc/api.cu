@@ -133,8 +133,10 @@ static int topk_search_impl(const float* q_f32, int64_t ldq_f32, const uint16_t*
       // At least two splits so that the merged candidates of several lists back the verification; with >= 8
       // splits (or K <= 5) each split only keeps 16 (rows it drops are bounded by tau), which halves the
       // epilogue's insertion work.
+      // A single-tile batch on single CTAs gets one split per SM (148): 8 rows per split are 1184 candidates, more than
+      // the 64 that are re-scored, and keep the merge within its 2048-key register variant.
       const int planned = tc_planned_splits(Q, N, 2);
-      const int kp = (planned >= 8 || K <= 5) ? 16 : RESCORE_KP;
+      const int kp = planned > 128 ? 8 : ((planned >= 8 || K <= 5) ? 16 : RESCORE_KP);
       int rc = tc_topk_search(q_hi, nullptr, db_hi, nullptr, Q, N, D, ldq_bf16, lddb_bf16, q_fold, db_fold, idx_base,
                               kp, 1, nullptr, ws + a_bytes, t_bytes, debug_scores, st, &parts, fold_sorted, 2);
       if (rc != EMR2A_OK) return rc;

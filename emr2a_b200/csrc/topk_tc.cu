@@ -234,13 +234,18 @@ struct TcPlan {
 int tc2_dispatch(int passes, int kcap, bool has_fold, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
                  const CUtensorMap& d, const TcParams& p, int grid, cudaStream_t st);
 
-static bool use_cta_pairs() {
+// CTA pairs (M = 256 per tile, cta_group::2) or single CTAs (M = 128).  Pairs win whenever the tensor pipe is the
+// bound (one third less L2->SM traffic per FLOP).  A batch of up to 128 queries is HBM-bound -- the database plane is
+// streamed once whatever the batch size -- and the pair kernel would still compute a full M = 256 tile (tensor pipe
+// 77 % busy at Q = 64): there 148 single CTAs stream the plane faster (1M x 1024, Q = 64: 0.34 ms = 6.0 TB/s against
+// 0.40 ms).  EMR2A_TC2 = 0 / 1 forces the single-CTA / pair kernel.
+static bool use_cta_pairs(int64_t Q) {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("EMR2A_TC2");         // EMR2A_TC2=0 selects the single-CTA kernel
-    v = (e && e[0] == '0') ? 0 : 1;
+    const char* e = getenv("EMR2A_TC2");
+    v = !e ? 2 : (e[0] == '0' ? 0 : 1);
   }
-  return v == 1;
+  return v == 2 ? Q > T_BM : v == 1;
 }
 
 static TcPlan tc_plan(int64_t Q, int64_t N, int K, bool has_fold, bool pairs, int min_splits = 1) {
@@ -255,7 +260,11 @@ static TcPlan tc_plan(int64_t Q, int64_t N, int K, bool has_fold, bool pairs, in
   // the workers, the cap rises to one unit per worker (148 CTAs / 74 pairs), so that a single-tile batch (serving,
   // Q <= 256) streams the database with every SM instead of 64 of them
   int64_t cap = 64;
-  if (pl.m_tiles * cap < sms) cap = sms;
+  if (pl.m_tiles * cap < sms) {
+    const int kcap = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
+    cap = sms < 2048 / kcap ? sms : 2048 / kcap;       // the register merge (K3) takes up to 2048 keys per query
+    if (cap < 64) cap = 64;
+  }
   const int64_t max_s = pl.n_tiles < cap ? pl.n_tiles : cap;
   int64_t first_s = min_splits < max_s ? min_splits : max_s;
   if (first_s < 1) first_s = 1;
@@ -284,7 +293,7 @@ static TcPlan tc_plan(int64_t Q, int64_t N, int K, bool has_fold, bool pairs, in
 
 // number of database splits the search will use (the rescore arm sizes its candidate lists by it)
 int tc_planned_splits(int64_t Q, int64_t N, int min_splits) {
-  return tc_plan(Q, N, 1, false, use_cta_pairs(), min_splits).splits;
+  return tc_plan(Q, N, 1, false, use_cta_pairs(Q), min_splits).splits;
 }
 
 size_t tc_topk_workspace_bytes(int64_t Q, int64_t N, int K) {
@@ -333,7 +342,7 @@ int tc_topk_search(const uint16_t* q_hi, const uint16_t* q_lo, const uint16_t* d
   if (Q >= (1LL << 31) || N >= (1LL << 31) - T_BN) return fail(EMR2A_ERR_UNSUPPORTED, "topk_search(bf16): Q/N too large for one call");
   if (N + idx_base >= 0xFFFFFFFFLL) return fail(EMR2A_ERR_UNSUPPORTED, "topk_search: global index exceeds 32 bits");
   const bool has_fold = q_fold != nullptr;
-  const bool pairs = use_cta_pairs();
+  const bool pairs = use_cta_pairs(Q);
   TcPlan pl = tc_plan(Q, N, K, has_fold, pairs, min_splits);
   const size_t keys_off = 0;
   const size_t fold_off = (pl.keys_bytes + 255) & ~static_cast<size_t>(255);
