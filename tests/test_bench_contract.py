@@ -43,3 +43,31 @@ def test_b200_arm_line_small_workload():
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["value"] > 0 and c["parity_on_sample"]["topk_rows_identical"] == 1.0
     assert c["parity_on_sample"]["vote_identical"] == 1.0
+
+
+def test_roofline_denominator_rule():
+    """Burst peak for short runs, sustained peak once the GPU has been under load for 1.5 s (bench.tensor_peak)."""
+    sys.path.insert(0, REPO)
+    import bench
+    pk = {"tflops": 1382.1, "tflops_burst": 1657.8, "hbm_gbs": 6549.4, "src": "measured"}
+    assert bench.tensor_peak(pk, 0.2)[0] == 1657.8 and "burst" in bench.tensor_peak(pk, 0.2)[1]
+    assert bench.tensor_peak(pk, 1.9)[0] == 1382.1 and "sustained" in bench.tensor_peak(pk, 1.9)[1]
+    got = bench.peaks()
+    assert got["tflops_burst"] >= got["tflops"] > 0 and got["hbm_gbs"] > 0
+
+
+def test_ncu_summary_tool(tmp_path, capsys):
+    sys.path.insert(0, os.path.join(REPO, "tools"))
+    import ncu_summary
+    path = tmp_path / "launches.csv"
+    rows = ['"ID","Process ID","Process Name","Host Name","Kernel Name","Context","Stream","Block Size","Grid Size","Device","CC","Section Name","Metric Name","Metric Unit","Metric Value"']
+    for i, (name, ns) in enumerate([("void emr2a::normalize_fuse_vec_kernel<float, 8, 0, 1>(NfParams)", 1700000), ("void emr2a::normalize_fuse_vec_kernel<float, 8, 0, 1>(NfParams)", 19000),
+                                    ("void emr2a::tc2_topk_kernel<1, 16, 0>(CUtensorMap_st)", 13000000), ("emr2a::topk_merge_pway_kernel(const unsigned long *)", 60000),
+                                    ("void at::native::vectorized_elementwise_kernel<4>(int)", 5000), ("void emr2a::vote_metrics_kernel<16>(VoteParams)", 15000)] * 2):
+        rows.append(f'"{i}","1","python","box","{name}","1","7","(256, 1, 1)","(148, 1, 1)","0","10.0","Command line profiler metrics","gpu__time_duration.sum","ns","{ns}"')
+    path.write_text("\n".join(rows) + "\n")
+    ncu_summary.launches(str(path))
+    out = capsys.readouterr().out
+    assert "tc2_topk_kernel<1, 16, 0>" in out and "vectorized_elementwise" not in out
+    assert "| 4 |" in out and "| 5 |" not in out            # the last step only: 5 of our launches
+    assert "87.87%" in out and "= 88.3% of the step" in out   # tc2 share; filter + merge share
