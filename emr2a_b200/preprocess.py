@@ -5,8 +5,9 @@ sides (``CVRetrievalEvaluator.process_embeddings`` utils/cv_evaluator.py:73-93; 
 What runs where
     column mean / variance ........ ``emr2a_column_moments`` (hand-written, HBM-bound, float64 accumulators)
     (x - mean) / scale ............ ``emr2a_standardize``    (hand-written, HBM-bound, sklearn's fp32 arithmetic)
-    Z^T Z, eigh, Z W^T ............ library calls (cuBLAS DGEMM/SGEMM, cuSOLVER syevd through torch): plain GEMMs
-                                    and a D x D symmetric eigenproblem
+    Z^T Z, eigh ................... library calls (cuBLAS DGEMM, cuSOLVER syevd through torch): a plain GEMM and a
+                                    D x D symmetric eigenproblem, fit only
+    Z W^T ......................... ``emr2a_scores`` (hand-written fp32 FMA GEMM, fixed summation order)
     row normalisation ............. K1 (``emr2a_normalize_fuse``)
 
 Contract.  The scaler reproduces sklearn's ``StandardScaler`` (float64 statistics, fp32 transform).  The PCA is the
@@ -168,12 +169,14 @@ def transform(tf: FoldTransform, x, engine: Optional[Engine] = None, normalize: 
         p = tf.n_components
         y = torch.empty((n, p), dtype=torch.float32, device=eng.device)
         buf = torch.empty((min(n, _CHUNK_ROWS), d), dtype=torch.float32, device=eng.device)
-        wt = tf.components.t()
-        with _NoTF32():
-            for lo in range(0, n, _CHUNK_ROWS):
-                hi = min(lo + _CHUNK_ROWS, n)
-                z = standardize(eng, x[lo:hi], tf.mean_f32, tf.scale_f32, out=buf[:hi - lo])
-                torch.matmul(z, wt, out=y[lo:hi])
+        w = tf.components                                   # [P, D]: y[r, j] = <z_r, w_j>, the shape of emr2a_scores
+        for lo in range(0, n, _CHUNK_ROWS):
+            hi = min(lo + _CHUNK_ROWS, n)
+            z = standardize(eng, x[lo:hi], tf.mean_f32, tf.scale_f32, out=buf[:hi - lo])
+            with torch.cuda.device(eng.device):          # projection on our own fp32 FMA kernel (fixed summation order)
+                native.check(eng.lib.emr2a_scores(z.data_ptr(), w.data_ptr(), hi - lo, p, d, _ld(z), _ld(w),
+                                                  y[lo:hi].data_ptr(), p, eng._stream()))
+            eng.launches += 1
         y -= tf.bias
     if not normalize:
         return y
