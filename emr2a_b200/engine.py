@@ -22,6 +22,7 @@ from . import native
 _PREC = {"fp32": native.PREC_FP32, "bf16x3": native.PREC_BF16X3, "bf16x1": native.PREC_BF16X1,
          "rescore": native.PREC_BF16_RESCORE}
 _RESCORE_MAX_K = 10
+_QPAD_MAX = int(os.environ.get("EMR2A_QPAD_MAX", 256))     # resident-index batches up to this size are filled to 64-row multiples
 # tensor cores pay off once the contraction is large; below this the exact fp32 arm is used
 _TC_MIN_MACS = float(os.environ.get("EMR2A_TC_MIN_MACS", 2.0e9))
 
@@ -621,7 +622,7 @@ class DatabaseIndex:
         # filled to a multiple of 64 rows with copies of its last query; the copies' results are dropped before the vote.
         segs = [eng._embedding(x)[0] for x in q_segs if x is not None]
         n_q = int(segs[0].shape[0])
-        pad = (-n_q) % 64 if (0 < n_q <= 256 and prec != "fp32") else 0
+        pad = (-n_q) % 64 if (0 < n_q <= _QPAD_MAX and prec != "fp32") else 0
         if pad:
             segs = [torch.cat([t, t[-1:].expand(pad, int(t.shape[1]))]) for t in segs]
         qs = eng.prepare(segs[0], segs[1] if len(segs) > 1 else None, q_weights[0], q_weights[1],

@@ -12,7 +12,7 @@ di, _ = synth.device_block(0, n, d, c, 11, dev, label_seed=11); dt, _ = synth.de
 labels = synth.device_labels(0, n, c, 11, dev)
 for prec in os.environ.get("PRECS", "rescore,bf16x3").split(","):
     index = eng.build_index((di, dt), labels, c, flags=flags, precision=prec, k=k)
-    for q in (1, 8, 64, 128, 256, 1024, 4096):
+    for q in [int(v) for v in os.environ.get("QS", "1,8,64,128,256,1024,4096").split(",")]:
         qi, ql = synth.device_block(50_003_968, q, d, c, 11, dev, label_seed=11); qt, _ = synth.device_block(50_003_968, q, d, c, 12, dev, label_seed=11)
         for _ in range(3):
             r = index.search((qi, qt), ql, k=k, want_lists=False)
