@@ -226,3 +226,38 @@ def test_auto_mode_follows_sklearn_solver_choice():
     ho = RetrievalEvaluator(use_pca=False)
     ho.preprocess = "auto"
     assert ho._preprocess_on_gpu(1600, 512)          # scaler only: always deterministic
+
+
+def test_public_signatures_match_the_reference():
+    """Every public function / class / method of the reference's hot-path modules exists here under the same name with
+    the same parameter names, order and defaults (tests/golden/signatures.json, recorded from the reference by
+    tests/golden/make_signatures.py).  Extra methods and extra trailing keyword parameters with defaults are allowed."""
+    import importlib
+    import inspect
+    import json
+    with open(os.path.join(REPO, "tests", "golden", "signatures.json")) as fh:
+        ref = json.load(fh)
+
+    def check(where, fn, want):
+        got = [[p.name, p.kind.name, None if p.default is inspect.Parameter.empty else repr(p.default)]
+               for p in inspect.signature(fn).parameters.values()]
+        assert got[:len(want)] == want, f"{where}: {got} != {want}"
+        for extra in got[len(want):]:
+            assert extra[2] is not None, f"{where}: extra parameter {extra[0]} has no default"
+
+    import emr2a_b200.retrieval as ours_retrieval
+    for name in ref.pop("retrieval.__all__"):
+        assert callable(getattr(ours_retrieval, name)), name
+    checked = 0
+    for mod_name, api in ref.items():
+        mod = importlib.import_module("emr2a_b200." + mod_name)
+        for name, want in api.items():
+            obj = getattr(mod, name)
+            if isinstance(want, dict):
+                for meth, sig in want["methods"].items():
+                    check(f"{mod_name}.{name}.{meth}", getattr(obj, meth), sig)
+                    checked += 1
+            else:
+                check(f"{mod_name}.{name}", obj, want)
+                checked += 1
+    assert checked >= 35
