@@ -1,6 +1,7 @@
 """Pin the CPU oracle against vectors produced by running the reference itself
 (tests/golden/make_golden.py).  CPU only."""
 import numpy as np
+import pytest
 
 TOL = 2e-6   # oracle repeats the same numpy ops; only BLAS thread order may differ
 
@@ -163,3 +164,37 @@ def test_sklearn_solver_rule_matches_sklearn():
         x = rng.standard_normal((n, d)).astype(np.float32)
         sk = PCA(n_components=min(p, n - 1, d)).fit(x)
         assert sklearn_solver(n, d, min(p, n - 1, d)) == sk._fit_svd_solver, (n, d, p)
+
+
+@pytest.mark.parametrize("mode", ["zscore", "minmax"])
+def test_late_fusion_affine_identity_behind_the_matrix_free_path(oracle, mode):
+    """The derivation emr2a_b200/late.py relies on, checked in numpy: per query the reference's
+    w * norm(ts) + (1 - w) * norm(is) equals <[g_t Tq ; g_i Iq], [Td ; Id]> - c with the statistics taken from
+    database moments (z-score: column sums + Gram matrix) or from the extreme scores (min-max)."""
+    rng = np.random.default_rng(3)
+    n, d_t, d_i, w = 4000, 24, 40, 0.35
+    db_t = oracle.unit_rows(rng.standard_normal((n, d_t)).astype(np.float32) + 0.4)
+    db_i = oracle.unit_rows(rng.standard_normal((n, d_i)).astype(np.float32))
+    s_t, g_t = db_t.astype(np.float64).sum(axis=0), db_t.astype(np.float64).T @ db_t.astype(np.float64)
+    s_i, g_i = db_i.astype(np.float64).sum(axis=0), db_i.astype(np.float64).T @ db_i.astype(np.float64)
+    for _ in range(5):
+        q_t = oracle.unit_rows(rng.standard_normal((1, d_t)).astype(np.float32))[0]
+        q_i = oracle.unit_rows(rng.standard_normal((1, d_i)).astype(np.float32))[0]
+        ts, is_ = oracle.dot_one_vs_db(q_t, db_t), oracle.dot_one_vs_db(q_i, db_i)
+        want = oracle.fuse_late_scores(ts, is_, w, mode)
+        stats = []
+        for q, s, g, sc in ((q_t, s_t, g_t, ts), (q_i, s_i, g_i, is_)):
+            q64 = q.astype(np.float64)
+            if mode == "zscore":
+                mean = q64 @ s / n
+                std = np.sqrt(max(q64 @ g @ q64 / n - mean * mean, 0.0))
+                assert abs(mean - float(sc.mean())) < 1e-7 and abs(std - float(sc.std())) < 1e-7
+                stats.append((mean, std + 1e-8))
+            else:
+                stats.append((float(sc.min()), float(sc.max()) - float(sc.min()) + 1e-8))
+        (a_t, b_t), (a_i, b_i) = stats
+        gam_t, gam_i = w / b_t, (1 - w) / b_i
+        fused = np.concatenate([gam_t * q_t, gam_i * q_i]).astype(np.float64) @ np.concatenate([db_t, db_i], axis=1).astype(np.float64).T
+        fused -= gam_t * a_t + gam_i * a_i
+        assert np.max(np.abs(fused - want)) < 2e-5 * max(1.0, float(np.abs(want).max()))
+        assert np.array_equal(np.argsort(-fused)[:5], np.argsort(-want.astype(np.float64))[:5])
