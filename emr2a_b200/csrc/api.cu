@@ -31,7 +31,8 @@ size_t simt_topk_workspace_bytes(int64_t Q, int64_t N, int K);
 int simt_topk_search(const float* q, const float* db, int64_t Q, int64_t N, int D, int64_t ldq, int64_t lddb,
                      const uint8_t* q_fold, const uint8_t* db_fold, int64_t idx_base, int K, uint64_t* out_keys,
                      void* workspace, size_t ws_bytes, cudaStream_t st);
-size_t tc_topk_workspace_bytes(int64_t Q, int64_t N, int K);
+size_t tc_topk_workspace_bytes(int64_t Q, int64_t N, int K, int D);
+int tc_debug_unit_clocks(unsigned long long* host_out, int64_t cap_units, int64_t* plan_out);
 struct TcPartials {
   const uint64_t* parts;
   int splits;
@@ -81,14 +82,13 @@ extern "C" int emr2a_device_check(int* sms, int* cc_major, int* cc_minor) {
 }
 
 extern "C" size_t emr2a_topk_search_workspace_bytes(int64_t Q, int64_t N, int D, int K, int precision) {
-  (void)D;
   if (Q <= 0 || N <= 0 || K <= 0) return 256;
   if (precision == EMR2A_PREC_FP32) return simt_topk_workspace_bytes(Q, N, K) + 256;
   if (precision == EMR2A_PREC_BF16_RESCORE) {
     return align256(sizeof(uint64_t) * static_cast<size_t>(Q) * RESCORE_KPM) +
-           align256(tc_topk_workspace_bytes(Q, N, RESCORE_KP)) + align256(rescore_workspace_bytes(Q, K));
+           align256(tc_topk_workspace_bytes(Q, N, RESCORE_KP, D)) + align256(rescore_workspace_bytes(Q, K));
   }
-  return tc_topk_workspace_bytes(Q, N, K);
+  return tc_topk_workspace_bytes(Q, N, K, D);
 }
 
 static int topk_search_impl(const float* q_f32, int64_t ldq_f32, const uint16_t* q_hi, const uint16_t* q_lo,
@@ -124,7 +124,7 @@ static int topk_search_impl(const float* q_f32, int64_t ldq_f32, const uint16_t*
       if (ldq_f32 < D || lddb_f32 < D) return fail(EMR2A_ERR_INVALID, "topk_search(rescore): leading dimension smaller than D");
       if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255)) return fail(EMR2A_ERR_INVALID, "topk_search(rescore): workspace must be 256-byte aligned");
       const size_t a_bytes = align256(sizeof(uint64_t) * static_cast<size_t>(Q) * RESCORE_KPM);
-      const size_t t_bytes = align256(tc_topk_workspace_bytes(Q, N, RESCORE_KP));
+      const size_t t_bytes = align256(tc_topk_workspace_bytes(Q, N, RESCORE_KP, D));
       const size_t r_bytes = align256(rescore_workspace_bytes(Q, K));
       if (ws_bytes < a_bytes + t_bytes + r_bytes) return fail(EMR2A_ERR_WORKSPACE, "topk_search(rescore): workspace %zu < %zu", ws_bytes, a_bytes + t_bytes + r_bytes);
       uint8_t* ws = static_cast<uint8_t*>(workspace);
@@ -182,4 +182,11 @@ extern "C" int emr2a_debug_topk_search_dump(const uint16_t* q_hi, const uint16_t
   return topk_search_impl(nullptr, 0, q_hi, q_lo, ldq, nullptr, 0, db_hi, db_lo, lddb, Q, N, D, q_fold, db_fold, 0,
                           idx_base, K, precision, nullptr, nullptr, out_keys, nullptr, nullptr, workspace, ws_bytes,
                           debug_scores, stream);
+}
+
+// Diagnostics: globaltimer stamps (start, end) of every work unit of the last CTA-pair launch made with
+// EMR2A_TC_UNIT_CLOCK=1, plus its plan {m_tiles, n_tiles, splits, tiles_per_split, mg, sync_tiles, grid, n_units}.
+extern "C" int emr2a_debug_unit_clocks(uint64_t* host_out, int64_t cap_units, int64_t* plan_out) {
+  if (!host_out || !plan_out) return fail(EMR2A_ERR_INVALID, "debug_unit_clocks: null output");
+  return tc_debug_unit_clocks(reinterpret_cast<unsigned long long*>(host_out), cap_units, plan_out);
 }

@@ -4,12 +4,21 @@
 // Filter:   s~(q,d) = <bf16(q), bf16(d)> accumulated in fp32 on the tensor cores; per query the KP = 32
 //           rows with the largest s~ are kept (K <= 10: the slack below the K-th best must hold ~2E of scores).
 // Rescore:  s(q,d) = fp32 dot product of the fp32 rows K1 wrote (the same values the fp32 arm uses).
-// Bound:    |s~ - s| <= E = r_q * n_d + (n_q + r_q) * r_d + 1e-5 * n_q * n_d   for every pair, where
-//           n_d, r_d = max row norm and max ||row - bf16(row)|| over the database rows (K1 `stats`), n_q, r_q = the
-//           same two norms of THIS query (computed here, clamped by the batch maxima of K1 `stats`)
-//           (Cauchy-Schwarz on the two quantisation residuals; the last term covers
-//           the fp32 accumulation inside the tensor core).  bf16 keeps 8 significant bits, so r ~ 1.7e-3 for a
-//           unit row and E ~ 4e-3.
+// Bound:    |s~ - s| <= E = r_q * n_d + (n_q + r_q) * r_d + (1.02 D + 8) * 2^-23 * (n_q + r_q) * (n_d + r_d)
+//           for every pair, where n_d, r_d = max row norm and max ||row - bf16(row)|| over the database rows (K1
+//           `stats`), n_q, r_q = the same two norms of THIS query (computed here, clamped by the batch maxima of K1
+//           `stats`).  The first two terms are Cauchy-Schwarz on the two quantisation residuals (bf16 keeps 8
+//           significant bits, so r ~ 1.7e-3 for a unit row and E ~ 4e-3).  The last term covers the arithmetic:
+//             * tensor core: the D products of bf16 values are exact; they are summed in groups of 16 (UMMA_K) and
+//               added to the fp32 accumulator in TMEM.  Model: every one of the D additions loses at most one unit
+//               in the last place of a 24-bit significand aligned to the largest magnitude involved (truncation,
+//               no guard bits -- the worst any fp32-accumulating tensor pipe documents), and all partial sums are
+//               bounded by sum |x_i y_i| <= ||bf16(q)|| ||bf16(d)|| <= (n_q + r_q)(n_d + r_d):  D * 2^-23 * that;
+//             * the fp32 re-scoring the comparison is made against: D/32 round-to-nearest FMAs per lane plus the
+//               shuffle tree, <= (D/32 + 6) * 2^-24 * n_q n_d  (inside the 0.02 D + 8).
+//           D = 1024: 1.3e-4, D = 5120: 6.2e-4 per unit norms -- 3 % / 15 % on top of the quantisation terms.
+//           Measured tensor-core error on bf16-exact operands (tests/test_gpu_rescore_bound.py): 2-4e-7 at
+//           D = 5120, i.e. the model is ~3 orders of magnitude pessimistic, as a worst-case bound must be.
 // Verify:   every row outside the candidate list has s~ <= tau (the KP-th approximate score), hence
 //           s <= tau + E.  If the exact K-th best candidate score exceeds tau + E strictly, no
 //           outside row can enter the Top-K and the selection is exact.  Otherwise the query is
@@ -58,9 +67,13 @@ __device__ __forceinline__ float lane_dot(const float* __restrict__ a, const flo
   return acc;
 }
 
-__device__ __forceinline__ float error_bound(float nq, float rq, const float* ds) {
-  const float nd = ds[0], rd = ds[1];
-  return rq * nd + (nq + rq) * rd + 1e-5f * nq * nd + 1e-7f;
+__device__ __forceinline__ float error_bound(float nq, float rq, const float* ds, int D) {
+  // the four norms are fp32 sums of D squares (relative error of a norm <= D * 2^-25): widen them accordingly
+  const float up = 1.f + static_cast<float>(D) * 5.9604645e-8f;
+  const float nd = ds[0] * up, rd = ds[1] * up;
+  nq *= up; rq *= up;
+  const float arith = (1.02f * static_cast<float>(D) + 8.f) * 1.1920929e-7f * (nq + rq) * (nd + rd);
+  return (rq * nd + (nq + rq) * rd + arith) * 1.000001f + 1e-30f;      // rounded up: the bound must stay a bound
 }
 
 // The query side of the bound is taken per query: ||q|| and ||q - bf16(q)|| of THIS query's fp32 row (the hi plane
@@ -108,7 +121,7 @@ __global__ void __launch_bounds__(256) rescore_select_kernel(const RescoreParams
   // filter scores all have exact scores >= s~_K - E), so it is not re-scored: typically ~20 of 64 are.
   float nq, rq;
   query_norms(qrow, p.D, lane, p.q_stats, nq, rq);
-  const float E = error_bound(nq, rq, p.db_stats);
+  const float E = error_bound(nq, rq, p.db_stats, p.D);
   const uint64_t kth_approx = __shfl_sync(0xffffffffu, akey[0], p.K - 1);
   const float cut = kth_approx != 0ull ? key_score(kth_approx) - 2.0f * E : -INFINITY;
   bool done = false;

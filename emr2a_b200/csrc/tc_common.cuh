@@ -26,6 +26,13 @@ struct TcParams {
   uint64_t* keys_out;      // [splits][Q][K]
   uint32_t* tau;           // [Q] order-preserving image of a lower bound of the query's global KCAP-th best score
   float* debug_scores;     // optional [Q][N] dump of every score (bring-up / tests)
+  // ---- CTA-pair kernel: unit order and database-stream sharing (topk_tc2.cu) ----
+  int64_t mg;              // query tiles per group: units are ordered (group, split, tile-in-group); mg >= m_tiles = one group
+  int sync_tiles;          // cohort pacing: the pairs that stream the same database split meet every sync_tiles tiles; 0 = off
+  int sync_points;         // ceil(tiles_per_split / sync_tiles)
+  int sync_budget;         // SM cycles a pair waits at a meeting point at most (pacing only, never required for correctness)
+  uint32_t* sync_ctr;      // [cohort slots][sync_points], zeroed per launch
+  unsigned long long* unit_clock;  // optional [n_units][2] globaltimer at unit start / end (diagnostics)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------
@@ -219,6 +226,55 @@ __device__ __forceinline__ void scan_tile(const TcParams& p, RegTopK<KCAP>& top,
       }
     }
     __syncwarp();                                 // tcgen05.ld is warp-collective: reconverge before the next chunk
+  }
+}
+
+// ---- unit order of the CTA-pair kernel ----------------------------------------------------
+// A work unit is (query tile mt, database split).  Units are numbered group by group: a group is p.mg consecutive
+// query tiles; inside a group the split is the slow index, so the mg units of one (group, split) -- a COHORT: they
+// stream the same database tiles -- carry consecutive numbers and run concurrently on consecutive pairs.
+//   * mg bounds the query-plane working set of the concurrent pairs (mg tiles x 256 rows x ld x 2 B) so that it
+//     stays in L2 next to the database stream (D = 5120: a 10k-query plane is 102 MB -- ncu r2: 651 GB of DRAM reads
+//     per launch for a 20 GB plane before grouping);
+//   * cohort members pace each other (cohort_sync) so the stream is fetched from HBM once per cohort, not once per pair.
+__device__ __forceinline__ void unit_coords(const TcParams& p, int64_t u, int64_t& split, int64_t& mt) {
+  const int64_t per_group = p.mg * p.splits;
+  const int64_t g = u / per_group;
+  const int64_t r = u - g * per_group;
+  const int64_t left = p.m_tiles - g * p.mg;
+  const int64_t mg_eff = left < p.mg ? left : p.mg;
+  split = r / mg_eff;
+  mt = g * p.mg + (r - split * mg_eff);
+}
+// Cohort part of unit u among the units [step * n_workers, (step + 1) * n_workers) that run concurrently:
+// slot = unique id of (cohort, step), size = members of the cohort inside this step.
+__device__ __forceinline__ void unit_cohort(const TcParams& p, int64_t u, int64_t n_workers, int64_t n_units,
+                                            int64_t& slot, int& size) {
+  const int64_t per_group = p.mg * p.splits;
+  const int64_t g = u / per_group;
+  const int64_t r = u - g * per_group;
+  const int64_t left = p.m_tiles - g * p.mg;
+  const int64_t mg_eff = left < p.mg ? left : p.mg;
+  const int64_t split = r / mg_eff;
+  int64_t c0 = g * per_group + split * mg_eff, c1 = c0 + mg_eff;          // the cohort's units [c0, c1)
+  const int64_t step = u / n_workers;
+  const int64_t s0 = step * n_workers, s1 = (s0 + n_workers < n_units) ? s0 + n_workers : n_units;
+  c0 = c0 > s0 ? c0 : s0;
+  c1 = c1 < s1 ? c1 : s1;
+  size = static_cast<int>(c1 - c0);
+  slot = g * p.splits + split + step;                                     // strictly increasing over the parts
+}
+// Meeting point of a cohort (called by ONE thread of the pair).  Pure pacing: a pair that arrives early waits --
+// at most p.sync_budget cycles -- until the others have arrived, so that all members request a database tile
+// while it is in L2.  Nothing depends on the wait being complete.
+__device__ __forceinline__ void cohort_sync(const TcParams& p, int64_t slot, int point, int size) {
+  uint32_t* ctr = p.sync_ctr + slot * p.sync_points + point;
+  const uint32_t seen = atomicAdd(ctr, 1u) + 1u;
+  if (seen >= static_cast<uint32_t>(size)) return;
+  const long long t0 = clock64();
+  while (__ldcg(ctr) < static_cast<uint32_t>(size)) {
+    if (clock64() - t0 > p.sync_budget) break;
+    __nanosleep(40);
   }
 }
 

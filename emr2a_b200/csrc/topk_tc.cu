@@ -228,7 +228,21 @@ struct TcPlan {
   int splits;
   int grid;
   size_t keys_bytes, fold_bytes, tau_bytes;
+  // CTA pairs: unit grouping and cohort pacing (tc_common.cuh: unit_coords / cohort_sync)
+  int64_t mg;
+  int sync_tiles, sync_points, sync_budget;
+  size_t sync_bytes;
 };
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
+
+// diagnostics (emr2a_debug_unit_clocks): globaltimer at the start / end of every work unit of the last pair-kernel launch
+constexpr int64_t UNIT_CLOCK_MAX = 1 << 16;
+__device__ unsigned long long g_unit_clock[2 * UNIT_CLOCK_MAX];
+static int64_t g_last_plan[8];
 
 // CTA-pair kernel (topk_tc2.cu)
 int tc2_dispatch(int passes, int kcap, bool has_fold, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
@@ -248,7 +262,8 @@ static bool use_cta_pairs(int64_t Q) {
   return v == 2 ? Q > T_BM : v == 1;
 }
 
-static TcPlan tc_plan(int64_t Q, int64_t N, int K, bool has_fold, bool pairs, int min_splits = 1) {
+static TcPlan tc_plan(int64_t Q, int64_t N, int K, bool has_fold, bool pairs, int min_splits = 1, int64_t ld = 1024,
+                      int planes = 1) {
   TcPlan pl{};
   const int bm = pairs ? 2 * T_BM : T_BM;
   pl.m_tiles = (Q + bm - 1) / bm;
@@ -288,6 +303,34 @@ static TcPlan tc_plan(int64_t Q, int64_t N, int K, bool has_fold, bool pairs, in
   pl.keys_bytes = sizeof(uint64_t) * static_cast<size_t>(pl.splits) * Q * K;
   pl.fold_bytes = has_fold ? static_cast<size_t>(pl.n_tiles) * T_BN : 0;
   pl.tau_bytes = (sizeof(uint32_t) * static_cast<size_t>(Q) + 255) & ~static_cast<size_t>(255);
+  pl.mg = pl.m_tiles;
+  if (pairs) {
+    // Query tiles per group: the query planes of the concurrently running pairs (mg tiles of 256 rows) are re-read
+    // from L2 for every database tile and must stay there next to the database stream.  EMR2A_TC_A_MB = budget.
+    const double a_tile = 2.0 * T_BM * static_cast<double>(ld) * 2.0 * planes;
+    int64_t mg = static_cast<int64_t>(env_int("EMR2A_TC_A_MB", 40) * 1048576.0 / a_tile);
+    if (mg < 1) mg = 1;
+    if (mg < pl.m_tiles) {
+      const int64_t j = (sms + mg - 1) / mg;       // whole cohorts per wave of pairs where possible
+      mg = sms / j;
+      if (mg < 1) mg = 1;
+      pl.mg = mg;
+    }
+    // Cohort pacing: meeting points every ~2 MB of database stream (per cohort), budget in SM cycles.
+    const double b_tile = static_cast<double>(T_BN) * static_cast<double>(ld) * 2.0 * planes;
+    int st = static_cast<int>(2097152.0 / b_tile + 0.5);
+    st = st < 1 ? 1 : (st > 16 ? 16 : st);
+    st = env_int("EMR2A_TC_SYNC", st);
+    const int64_t cohort_max = pl.mg < pl.m_tiles ? pl.mg : pl.m_tiles;
+    if (st > 0 && cohort_max > 1 && units > 1) {
+      pl.sync_tiles = st;
+      pl.sync_points = static_cast<int>((pl.tiles_per_split + st - 1) / st);
+      pl.sync_budget = env_int("EMR2A_TC_SYNC_BUDGET", 12000);
+      const int64_t groups = (pl.m_tiles + pl.mg - 1) / pl.mg;
+      const int64_t slots = groups * pl.splits + (units + sms - 1) / sms + 2;
+      pl.sync_bytes = (sizeof(uint32_t) * static_cast<size_t>(slots) * pl.sync_points + 255) & ~static_cast<size_t>(255);
+    }
+  }
   return pl;
 }
 
@@ -296,14 +339,25 @@ int tc_planned_splits(int64_t Q, int64_t N, int min_splits) {
   return tc_plan(Q, N, 1, false, use_cta_pairs(Q), min_splits).splits;
 }
 
-size_t tc_topk_workspace_bytes(int64_t Q, int64_t N, int K) {
+size_t tc_topk_workspace_bytes(int64_t Q, int64_t N, int K, int D) {
   size_t need = 0;
-  for (int pairs = 0; pairs < 4; ++pairs) {
-    TcPlan pl = tc_plan(Q, N, K, true, (pairs & 1) != 0, (pairs & 2) ? 2 : 1);
-    const size_t b = ((pl.keys_bytes + 255) & ~static_cast<size_t>(255)) + pl.fold_bytes + pl.tau_bytes + 512;
+  const int64_t ld = (static_cast<int64_t>(D) + T_BK - 1) / T_BK * T_BK;
+  for (int v = 0; v < 8; ++v) {
+    TcPlan pl = tc_plan(Q, N, K, true, (v & 1) != 0, (v & 2) ? 2 : 1, ld, (v & 4) ? 2 : 1);
+    const size_t b = ((pl.keys_bytes + 255) & ~static_cast<size_t>(255)) + pl.fold_bytes + pl.tau_bytes + pl.sync_bytes + 1024;
     need = b > need ? b : need;
   }
   return need;
+}
+
+// diagnostics: plan and unit clocks of the last pair-kernel launch made with EMR2A_TC_UNIT_CLOCK=1
+int tc_debug_unit_clocks(unsigned long long* host_out, int64_t cap_units, int64_t* plan_out) {
+  for (int i = 0; i < 8; ++i) plan_out[i] = g_last_plan[i];
+  int64_t n = g_last_plan[7];
+  if (n > cap_units) n = cap_units;
+  if (n > UNIT_CLOCK_MAX) n = UNIT_CLOCK_MAX;
+  if (n > 0) EMR2A_CUDA_TRY(cudaMemcpyFromSymbol(host_out, g_unit_clock, sizeof(unsigned long long) * 2 * n));
+  return EMR2A_OK;
 }
 
 template <int PASSES, int KCAP, bool HAS_FOLD>
@@ -343,11 +397,12 @@ int tc_topk_search(const uint16_t* q_hi, const uint16_t* q_lo, const uint16_t* d
   if (N + idx_base >= 0xFFFFFFFFLL) return fail(EMR2A_ERR_UNSUPPORTED, "topk_search: global index exceeds 32 bits");
   const bool has_fold = q_fold != nullptr;
   const bool pairs = use_cta_pairs(Q);
-  TcPlan pl = tc_plan(Q, N, K, has_fold, pairs, min_splits);
+  TcPlan pl = tc_plan(Q, N, K, has_fold, pairs, min_splits, lddb > ldq ? lddb : ldq, passes == 3 ? 2 : 1);
   const size_t keys_off = 0;
   const size_t fold_off = (pl.keys_bytes + 255) & ~static_cast<size_t>(255);
   const size_t tau_off = (fold_off + pl.fold_bytes + 255) & ~static_cast<size_t>(255);
-  const size_t need = tau_off + pl.tau_bytes;
+  const size_t sync_off = tau_off + pl.tau_bytes;
+  const size_t need = sync_off + pl.sync_bytes;
   if (!workspace || ws_bytes < need) return fail(EMR2A_ERR_WORKSPACE, "topk_search(bf16): workspace %zu < %zu", ws_bytes, need);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return fail(EMR2A_ERR_INVALID, "topk_search(bf16): workspace must be 256-byte aligned");
@@ -371,6 +426,20 @@ int tc_topk_search(const uint16_t* q_hi, const uint16_t* q_lo, const uint16_t* d
   if (pl.splits > 1) {     // sharing only pays (and is only needed) when a query tile is searched by several units
     p.tau = reinterpret_cast<uint32_t*>(ws + tau_off);
     EMR2A_CUDA_TRY(cudaMemsetAsync(p.tau, 0, sizeof(uint32_t) * static_cast<size_t>(Q), st));
+  }
+  p.mg = pl.mg;
+  if (pairs && pl.sync_bytes) {
+    p.sync_tiles = pl.sync_tiles; p.sync_points = pl.sync_points; p.sync_budget = pl.sync_budget;
+    p.sync_ctr = reinterpret_cast<uint32_t*>(ws + sync_off);
+    EMR2A_CUDA_TRY(cudaMemsetAsync(p.sync_ctr, 0, pl.sync_bytes, st));
+  }
+  if (pairs && env_int("EMR2A_TC_UNIT_CLOCK", 0) && pl.m_tiles * pl.splits <= UNIT_CLOCK_MAX) {
+    void* sym = nullptr;
+    EMR2A_CUDA_TRY(cudaGetSymbolAddress(&sym, g_unit_clock));
+    p.unit_clock = static_cast<unsigned long long*>(sym);
+    const int64_t plan[8] = {pl.m_tiles, pl.n_tiles, pl.splits, pl.tiles_per_split, pl.mg, pl.sync_tiles, pl.grid,
+                             pl.m_tiles * pl.splits};
+    for (int i = 0; i < 8; ++i) g_last_plan[i] = plan[i];
   }
   if (has_fold) {
     uint8_t* fpad = ws + fold_off;

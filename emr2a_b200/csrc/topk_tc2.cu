@@ -105,12 +105,24 @@ tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_consta
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int64_t u = pair; u < n_units; u += n_pairs) {
-        const int64_t split = u / p.m_tiles, mt = u - split * p.m_tiles;
+        int64_t split, mt;
+        unit_coords(p, u, split, mt);
         const int m0 = static_cast<int>(mt * T2_BM + rank * T_BM);
         const int64_t t0 = split * p.tiles_per_split;
         const int64_t t1 = (t0 + p.tiles_per_split < p.n_tiles) ? t0 + p.tiles_per_split : p.n_tiles;
         const int ufold = HAS_FOLD ? unit_fold(p, mt, T2_BM) : -1;
+        int64_t slot = 0; int cohort = 1;
+        if (leader && p.sync_tiles > 0) unit_cohort(p, u, n_pairs, n_units, slot, cohort);
         for (int64_t t = t0; t < t1; ++t) {
+          // the leader's producer paces the pair (the peer's producer follows through the slot barriers); meeting
+          // points are counted in absolute tiles so that members that skip own-fold tiles still show up
+          if (leader && cohort > 1 && (t - t0) % p.sync_tiles == 0)
+            cohort_sync(p, slot, static_cast<int>((t - t0) / p.sync_tiles), cohort);
+          if (leader && p.unit_clock != nullptr && t == t0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            p.unit_clock[2 * u] = now;
+          }
           if (HAS_FOLD && tile_skipped(p, ufold, t)) continue;
           const int n0 = static_cast<int>(t * T_BN + rank * 128);
           for (int kc = 0; kc < p.k_chunks; ++kc) {
@@ -135,10 +147,11 @@ tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_consta
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int64_t u = pair; u < n_units; u += n_pairs) {
-        const int64_t split = u / p.m_tiles;
+        int64_t split, mt;
+        unit_coords(p, u, split, mt);
         const int64_t t0 = split * p.tiles_per_split;
         const int64_t t1 = (t0 + p.tiles_per_split < p.n_tiles) ? t0 + p.tiles_per_split : p.n_tiles;
-        const int ufold = HAS_FOLD ? unit_fold(p, u - split * p.m_tiles, T2_BM) : -1;
+        const int ufold = HAS_FOLD ? unit_fold(p, mt, T2_BM) : -1;
         for (int64_t t = t0; t < t1; ++t) {
           if (HAS_FOLD && tile_skipped(p, ufold, t)) continue;
           mbar_wait(smem_u32(&bar_tempty[acc]), acc_phase ^ 1u);
@@ -178,7 +191,8 @@ tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_consta
     int acc = 0; uint32_t acc_phase = 0;
     RegTopK<KCAP> top;
     for (int64_t u = pair; u < n_units; u += n_pairs) {
-      const int64_t split = u / p.m_tiles, mt = u - split * p.m_tiles;
+      int64_t split, mt;
+      unit_coords(p, u, split, mt);
       const int64_t q = mt * T2_BM + rank * T_BM + row;
       const int64_t t0 = split * p.tiles_per_split;
       const int64_t t1 = (t0 + p.tiles_per_split < p.n_tiles) ? t0 + p.tiles_per_split : p.n_tiles;
@@ -209,6 +223,11 @@ tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_consta
 #pragma unroll
         for (int j = 0; j < KCAP; ++j)
           if (j < p.K) dst[j] = (top.i[j] == 0xFFFFFFFFu) ? 0ull : pack_key(top.s[j], top.i[j]);
+      }
+      if (leader && p.unit_clock != nullptr && threadIdx.x == 128) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        p.unit_clock[2 * u + 1] = now;
       }
     }
   }

@@ -52,6 +52,7 @@ _SIGNATURES = {
     # diagnostics (not part of the reference-facing surface)
     "emr2a_debug_topk_search_dump": (_int, [_p, _p, _p, _p, _i64, _i64, _int, _i64, _i64, _p, _p, _i64, _int, _int,
                                             _p, _p, _sz, _p, _p]),
+    "emr2a_debug_unit_clocks": (_int, [_p, _i64, _p]),
 }
 
 

@@ -46,17 +46,19 @@ def label_names(codes: np.ndarray, n_classes: int) -> list:
 
 
 def device_block(row0: int, rows: int, dim: int, n_classes: int, seed: int, device,
-                 sep: float = SEP, label_seed: int | None = None):
+                 sep: float = SEP, label_seed: int | None = None, dtype=None):
     """Generate rows [row0, row0+rows) of a (virtually unbounded) class-structured
     database directly on ``device``.  Deterministic per (seed, 65536-row chunk): the
     generators are re-seeded per chunk so any shard layout reproduces the same rows.
     Labels come from ``label_seed`` (default ``seed``) so several modalities can share
-    one label vector.  Returns (float32 [rows, dim], int32 labels [rows])."""
+    one label vector.  Returns (float32 [rows, dim], int32 labels [rows]); ``dtype`` (e.g. torch.bfloat16)
+    rounds the fp32 values chunk by chunk into a pre-allocated result (no fp32 copy of the whole block)."""
     import torch
 
     chunk = 65536
     label_seed = seed if label_seed is None else label_seed
-    xs, ls = [], []
+    out = torch.empty((rows, dim), dtype=dtype or torch.float32, device=device)
+    ls = []
     g = torch.Generator(device=device)
     gl = torch.Generator(device=device)
     gc = torch.Generator(device=device)
@@ -72,10 +74,10 @@ def device_block(row0: int, rows: int, dim: int, n_classes: int, seed: int, devi
         x = torch.randn((chunk, dim), generator=g, device=device, dtype=torch.float32)
         x += sep * centres[lab.long()]
         lo, hi = r - c0, min(end, c0 + chunk) - c0
-        xs.append(x[lo:hi])
+        out[r - row0:r - row0 + (hi - lo)] = x[lo:hi]
         ls.append(lab[lo:hi])
         r = c0 + hi
-    return torch.cat(xs), torch.cat(ls)
+    return out, (torch.cat(ls) if ls else torch.empty((0,), dtype=torch.int32, device=device))
 
 
 def device_labels(row0: int, rows: int, n_classes: int, label_seed: int, device):

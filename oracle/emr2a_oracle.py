@@ -479,3 +479,202 @@ def process_embeddings_exact(train: np.ndarray, test: np.ndarray, pca_dim: Optio
         tr = tr @ w.T - bias
         te = te @ w.T - bias
     return unit_rows(tr), unit_rows(te)
+
+
+# --------------------------------------------------------------------------
+# full-size sample parity: the reference loop for a SAMPLE of queries against a
+# database that only exists in row chunks (C2-C5 of BASELINE.json: 1M-10M rows)
+# --------------------------------------------------------------------------
+class StreamedReferenceSample:
+    """The reference's per-query loop for a sample of queries against a database too large to keep on the host:
+    the database is fed in row chunks (``add_chunk``), each chunk is normalised and fused the way the reference
+    does it for the whole matrix (row-wise operations, so chunking changes nothing), every sample query is scored
+    against the chunk with one ``np.dot`` sgemv, and the scores land in a ``[sample, N]`` float32 matrix.
+    ``finish`` then runs the reference's ``np.argsort(scores)[-k:][::-1]`` over all N scores of each query,
+    followed by the python votes.
+
+    mode ``concat``: utils/cv_evaluator.py:99-105 + :122-123 (:269-300 is the loop);
+    mode ``late``:   utils/cv_evaluator.py:232-237 (``w*txt + (1-w)*img`` of two sgemv results, merge-then-Top-K);
+    mode ``single``: one modality (:186-195).
+    ``q_fold`` / chunk ``fold``: the CV rule of :349-376 -- a query is only scored against the rows of the
+    OTHER folds (the reference builds per-fold train matrices; here the own-fold rows get -inf).
+    Timings: ``prep_seconds`` (normalise + fuse of the database chunks), ``query_seconds`` (sgemv + argsort +
+    votes, all sample queries)."""
+
+    def __init__(self, mode: str, k: int, n_rows: int, q_img: np.ndarray, q_txt: Optional[np.ndarray] = None,
+                 w_text: float = 0.5, q_fold: Optional[np.ndarray] = None):
+        import time
+        self._clock = time.perf_counter
+        if mode not in ("concat", "late", "single"):
+            raise ValueError(f"unknown mode {mode!r}")
+        self.mode, self.k, self.n_rows, self.w_text = mode, int(k), int(n_rows), w_text
+        self.q_fold = None if q_fold is None else np.asarray(q_fold)
+        self.q = self._prepare(np.asarray(q_img, dtype=np.float32),
+                               None if q_txt is None else np.asarray(q_txt, dtype=np.float32))
+        self.n_q = (self.q[0] if isinstance(self.q, tuple) else self.q).shape[0]
+        self.scores = np.full((self.n_q, self.n_rows), -np.inf, dtype=np.float32)
+        self.prep_seconds = 0.0
+        self.query_seconds = 0.0
+        self.rows_seen = 0
+        self.rows_scored = 0          # (query, row) pairs actually scored
+        self.rows_timed = 0           # rows / pairs fed with timed=True (the bounded timing sample)
+        self.pairs_timed = 0
+        import threading
+        self._lock = threading.Lock()
+
+    def _prepare(self, img: np.ndarray, txt: Optional[np.ndarray]):
+        if self.mode == "concat":
+            return fuse_concat_cv(unit_rows(img), unit_rows(txt))
+        if self.mode == "late":
+            return unit_rows(img), unit_rows(txt)
+        return unit_rows(img)
+
+    def add_chunk(self, row0: int, img: np.ndarray, txt: Optional[np.ndarray] = None,
+                  fold: Optional[np.ndarray] = None, timed: bool = True) -> None:
+        """Feed database rows ``[row0, row0 + len(img))``.  ``timed=True``: the reference's way (one sgemv per query),
+        counted in the timings.  ``timed=False``: the same scores from one sgemm for all sample queries (summation
+        order differs by <= ~1e-7), not timed -- for the rows beyond the bounded timing sample; thread-safe, chunks
+        may be fed from several threads."""
+        t0 = self._clock()
+        db = self._prepare(np.asarray(img, dtype=np.float32), None if txt is None else np.asarray(txt, dtype=np.float32))
+        t1 = self._clock()
+        n = (db[0] if isinstance(db, tuple) else db).shape[0]
+        pieces = [(0, n, None)]
+        if fold is not None:
+            # contiguous runs of equal fold id (rows come fold-sorted or in a few runs); a query skips its own fold's runs
+            fold = np.asarray(fold)
+            cuts = np.flatnonzero(np.diff(fold.astype(np.int64))) + 1
+            edges = np.concatenate([[0], cuts, [n]])
+            pieces = [(int(a), int(b), int(fold[a])) for a, b in zip(edges[:-1], edges[1:])]
+        scored = 0
+        if timed:
+            for i in range(self.n_q):
+                for a, b, f in pieces:
+                    if f is not None and self.q_fold is not None and f == int(self.q_fold[i]):
+                        continue
+                    if self.mode == "late":
+                        s_img = np.dot(db[0][a:b], self.q[0][i])
+                        s_txt = np.dot(db[1][a:b], self.q[1][i])
+                        sims = self.w_text * s_txt + (1 - self.w_text) * s_img
+                    else:
+                        sims = np.dot(db[a:b], self.q[i])
+                    self.scores[i, row0 + a:row0 + b] = sims
+                    scored += b - a
+        else:
+            for a, b, f in pieces:
+                if self.mode == "late":
+                    sims = self.w_text * (self.q[1] @ db[1][a:b].T) + (1 - self.w_text) * (self.q[0] @ db[0][a:b].T)
+                else:
+                    sims = self.q @ db[a:b].T
+                if f is not None and self.q_fold is not None:
+                    own = self.q_fold == f
+                    sims[own] = -np.inf
+                    scored += (b - a) * int((~own).sum())
+                else:
+                    scored += (b - a) * self.n_q
+                self.scores[:, row0 + a:row0 + b] = sims
+        t2 = self._clock()
+        with self._lock:
+            if timed:
+                self.prep_seconds += t1 - t0
+                self.query_seconds += t2 - t1
+                self.rows_timed += n
+                self.pairs_timed += scored
+            self.rows_seen += n
+            self.rows_scored += scored
+
+    def finish(self, db_labels: np.ndarray, q_labels: Optional[np.ndarray] = None) -> Dict:
+        if self.rows_seen != self.n_rows:
+            raise ValueError(f"only {self.rows_seen} of {self.n_rows} database rows were fed")
+        k = self.k
+        top_idx = np.zeros((self.n_q, k), np.int64)
+        top_sc = np.zeros((self.n_q, k), np.float32)
+        nxt = np.full(self.n_q, -np.inf, np.float32)
+        top1 = np.zeros(self.n_q, np.int64)
+        vote = np.zeros(self.n_q, np.int64)
+        wvote = np.zeros(self.n_q, np.int64)
+        top_lab = np.zeros((self.n_q, k), np.int64)
+        t0 = self._clock()
+        ref_rows = []
+        for i in range(self.n_q):
+            ref_rows.append(np.argsort(self.scores[i])[-(k + 1):][::-1])      # the reference's ranking op (+ the runner-up)
+        rank_seconds = self._clock() - t0
+        for i in range(self.n_q):
+            s = self.scores[i]
+            ref = ref_rows[i]
+            # tie rule of this oracle (score descending, index ascending) over everything tied with the k-th score
+            cand = np.flatnonzero(s >= s[ref[k - 1]])
+            order = cand[np.argsort(-s[cand], kind="stable")][:k]
+            top_idx[i], top_sc[i] = order, s[order]
+            rest = s[ref[k]] if len(ref) > k else -np.inf
+            if len(cand) > k:
+                rest = s[ref[k - 1]]
+            nxt[i] = rest
+            t1 = self._clock()
+            labs = [int(db_labels[j]) for j in order]
+            scs = [float(s[j]) for j in order]
+            top1[i] = labs[0]
+            vote[i] = vote_majority(labs)
+            wvote[i] = vote_weighted(labs, scs, "f64")
+            rank_seconds += self._clock() - t1
+            top_lab[i] = labs
+        # timings: normalise/fuse and sgemv are linear in the rows, so the bounded timed sample scales to the database;
+        # argsort + votes were run (and timed) on all N scores of every sample query
+        prep_full = self.prep_seconds * self.n_rows / self.rows_timed if self.rows_timed else float("nan")
+        sgemv_full = self.query_seconds * self.rows_scored / self.pairs_timed if self.pairs_timed else float("nan")
+        out = {"top_idx": top_idx, "top_scores": top_sc, "next_score": nxt, "top_labels": top_lab, "pred_top1": top1, "pred_vote": vote,
+               "pred_weighted": wvote, "prep_seconds": prep_full, "query_seconds": sgemv_full + rank_seconds,
+               "seconds_per_query": (sgemv_full + rank_seconds) / max(self.n_q, 1), "rows_scored": self.rows_scored,
+               "timed_rows": self.rows_timed, "timed_prep_seconds": self.prep_seconds,
+               "timed_sgemv_seconds": self.query_seconds, "rank_seconds": rank_seconds}
+        if q_labels is not None:
+            q_labels = np.asarray(q_labels)
+            out.update(top1=float(np.mean(top1 == q_labels)), vote_acc=float(np.mean(vote == q_labels)),
+                       weighted_vote_acc=float(np.mean(wvote == q_labels)))
+        return out
+
+
+def sample_parity(ref: Dict, got_idx: np.ndarray, got_scores: np.ndarray, got_vote: Optional[np.ndarray] = None,
+                  got_weighted: Optional[np.ndarray] = None, tol: float = 1e-5) -> Dict:
+    """Compare a search result with ``StreamedReferenceSample.finish`` (or any dict with ``top_idx``,
+    ``top_scores`` and optionally ``next_score``) under the stated bar: scores within ``tol``; index rows, majority
+    vote and weighted vote identical wherever every adjacent gap among the k best scores and the runner-up
+    exceeds ``2 * tol``.  Returns counts; ``ok`` is the conjunction."""
+    ref_idx, ref_sc = np.asarray(ref["top_idx"]), np.asarray(ref["top_scores"], dtype=np.float64)
+    got_idx, got_scores = np.asarray(got_idx), np.asarray(got_scores, dtype=np.float64)
+    ladder = ref_sc
+    if "next_score" in ref:
+        ladder = np.concatenate([ref_sc, np.asarray(ref["next_score"], dtype=np.float64)[:, None]], axis=1)
+    with np.errstate(invalid="ignore"):
+        gaps = -np.diff(ladder, axis=1)
+    clear = np.all((gaps > 2 * tol) | ~np.isfinite(gaps), axis=1)
+    # score error: position-wise on clear rows, as sorted multisets otherwise (ties may swap neighbours)
+    err = float(np.max(np.abs(np.sort(got_scores, axis=1) - np.sort(ref_sc, axis=1)))) if len(ref_sc) else 0.0
+    rows_same = np.all(got_idx == ref_idx, axis=1)
+    out = {"queries": int(len(ref_idx)), "clear_rows": int(clear.sum()), "max_score_err": err,
+           "topk_rows_identical": float(np.mean(rows_same)) if len(rows_same) else 1.0,
+           "clear_rows_identical": bool(np.all(rows_same[clear])),
+           # as SETS: rows that are not clear may only differ by swaps / replacements within the tolerance
+           "unclear_rows_within_tol": bool(all(
+               np.max(np.abs(np.sort(got_scores[i]) - np.sort(ref_sc[i]))) <= 2 * tol for i in np.flatnonzero(~clear)))}
+    ok = err <= tol and out["clear_rows_identical"] and out["unclear_rows_within_tol"]
+    if got_vote is not None:
+        same = np.asarray(got_vote) == np.asarray(ref["pred_vote"])
+        out["vote_identical"] = float(np.mean(same))
+        ok = ok and bool(np.all(same[clear]))
+    if got_weighted is not None:
+        same = np.asarray(got_weighted) == np.asarray(ref["pred_weighted"])
+        out["weighted_vote_identical"] = float(np.mean(same))
+        # identical rows carry scores that may differ by tol each, so two label sums closer than 2*k*tol may swap:
+        # the weighted vote must be identical on clear rows whose two best label sums are further apart than that
+        wclear = clear.copy()
+        if "top_labels" in ref:
+            labs = np.asarray(ref["top_labels"])
+            for i in np.flatnonzero(clear):
+                sums = sorted((float(ref_sc[i][labs[i] == c].sum()) for c in set(labs[i].tolist())), reverse=True)
+                if len(sums) > 1 and sums[0] - sums[1] <= 2 * ref_sc.shape[1] * tol:
+                    wclear[i] = False
+        out["weighted_clear_rows"] = int(wclear.sum())
+        ok = ok and bool(np.all(same[wclear]))
+    out["ok"] = bool(ok)
+    return out

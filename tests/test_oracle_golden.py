@@ -198,3 +198,82 @@ def test_late_fusion_affine_identity_behind_the_matrix_free_path(oracle, mode):
         fused -= gam_t * a_t + gam_i * a_i
         assert np.max(np.abs(fused - want)) < 2e-5 * max(1.0, float(np.abs(want).max()))
         assert np.array_equal(np.argsort(-fused)[:5], np.argsort(-want.astype(np.float64))[:5])
+
+
+@pytest.mark.parametrize("fusion", ["concat", "late", "image_only"])
+def test_streamed_reference_sample_matches_reference_folds(golden, oracle, fusion):
+    """The chunk-streamed sample loop (used for parity at the 1M-10M row sizes of C2-C5) reproduces the reference's
+    own evaluate_fold outputs: Top-K rows, scores, labels, votes -- fed in ragged chunks."""
+    g = golden("cv_small.npz")
+    n_folds = 5
+    k = int(g["meta"][5])
+    for f in range(n_folds):
+        tr, te = g[f"f{f}_train_idx"], g[f"f{f}_test_idx"]
+        a_tr, a_te, b_tr, b_te = (g[f"f{f}_{nm}"] for nm in ("img_tr", "img_te", "txt_tr", "txt_te"))
+        mode = {"concat": "concat", "late": "late", "image_only": "single"}[fusion]
+        s = oracle.StreamedReferenceSample(mode, k, len(tr), a_te, None if mode == "single" else b_te,
+                                           w_text=0.3 if fusion == "late" else 0.5)      # make_golden.py:150
+        for r0 in range(0, len(tr), 37):
+            s.add_chunk(r0, a_tr[r0:r0 + 37], None if mode == "single" else b_tr[r0:r0 + 37])
+        r = s.finish(g["labels"][tr], g["labels"][te])
+        want_idx, want_sc = g[f"f{f}_{fusion}_top_idx"], g[f"f{f}_{fusion}_top_scores"]
+        par = oracle.sample_parity({"top_idx": want_idx, "top_scores": want_sc}, r["top_idx"], r["top_scores"])
+        assert par["ok"] and par["max_score_err"] < TOL, par
+        clear = np.abs(np.diff(want_sc, axis=1)).min(axis=1) > 1e-6
+        assert np.array_equal(r["top_idx"][clear], want_idx[clear])
+        assert np.array_equal(r["top_labels"][clear], g[f"f{f}_{fusion}_top_labels"][clear])
+        metrics = g[f"f{f}_{fusion}_metrics"]         # top1, top3, top5, vote_acc, weighted_vote_acc, ...
+        if clear.all():
+            assert abs(r["top1"] - metrics[0]) < 1e-12 and abs(r["vote_acc"] - metrics[3]) < 1e-12
+            assert abs(r["weighted_vote_acc"] - metrics[4]) < 1e-12
+
+
+def test_streamed_reference_sample_fold_rule(oracle):
+    """Own-fold rows are never scored (utils/cv_evaluator.py:349-376) and the result equals the brute-force masked
+    ranking; the parity helper flags a wrong row on a clear gap and tolerates a swap inside the tolerance."""
+    rng = np.random.default_rng(5)
+    n, d, k = 3000, 48, 5
+    img = rng.standard_normal((n, d), dtype=np.float32)
+    txt = rng.standard_normal((n, d), dtype=np.float32)
+    lab = rng.integers(0, 3, n)
+    fold = np.sort(rng.integers(0, 5, n)).astype(np.uint8)
+    qi = np.arange(7, n, 173)
+    s = oracle.StreamedReferenceSample("concat", k, n, img[qi], txt[qi], q_fold=fold[qi])
+    for r0 in range(0, n, 500):
+        s.add_chunk(r0, img[r0:r0 + 500], txt[r0:r0 + 500], fold[r0:r0 + 500])
+    r = s.finish(lab, lab[qi])
+    db = oracle.fuse_concat_cv(oracle.unit_rows(img), oracle.unit_rows(txt))
+    want_idx, want_sc = oracle.search_topk_batched(db[qi], db, k, q_fold=fold[qi], db_fold=fold)
+    assert np.array_equal(r["top_idx"], want_idx) and np.max(np.abs(r["top_scores"] - want_sc)) < TOL
+    assert not np.any(fold[r["top_idx"]] == fold[qi][:, None])
+    assert r["rows_scored"] == int(sum((fold != f).sum() for f in fold[qi]))
+    assert oracle.sample_parity(r, want_idx, want_sc, r["pred_vote"], r["pred_weighted"])["ok"]
+    bad = want_idx.copy(); bad[3, 0] = (bad[3, 0] + 1) % n
+    assert not oracle.sample_parity(r, bad, want_sc)["ok"]
+    with pytest.raises(ValueError):
+        oracle.StreamedReferenceSample("concat", k, n + 1, img[qi], txt[qi]).finish(lab)
+
+
+def test_streamed_feed_timed_and_untimed_chunks_agree(oracle):
+    """oracle/streamed_feed.feed: a bounded timed prefix (per-query sgemv) + thread-pooled sgemm chunks give the same
+    ranking as feeding everything the reference's way, and the timings are scaled to the whole database."""
+    import streamed_feed
+    rng = np.random.default_rng(9)
+    n, d, k = 4000, 32, 5
+    img = rng.standard_normal((n, d), dtype=np.float32)
+    txt = rng.standard_normal((n, d), dtype=np.float32)
+    fold = np.sort(rng.integers(0, 5, n)).astype(np.uint8)
+    lab = rng.integers(0, 3, n)
+    qi = np.arange(3, n, 211)
+
+    def fetch(r0, rows):
+        return img[r0:r0 + rows], txt[r0:r0 + rows], fold[r0:r0 + rows]
+    for mode in ("concat", "late"):
+        a = oracle.StreamedReferenceSample(mode, k, n, img[qi], txt[qi], w_text=0.25, q_fold=fold[qi])
+        streamed_feed.feed(a, n, fetch, chunk_rows=512, timed_rows=n)
+        b = oracle.StreamedReferenceSample(mode, k, n, img[qi], txt[qi], w_text=0.25, q_fold=fold[qi])
+        streamed_feed.feed(b, n, fetch, chunk_rows=512, timed_rows=1024, workers=3)
+        ra, rb = a.finish(lab, lab[qi]), b.finish(lab, lab[qi])
+        assert oracle.sample_parity(ra, rb["top_idx"], rb["top_scores"], rb["pred_vote"], rb["pred_weighted"], tol=1e-6)["ok"]
+        assert ra["rows_scored"] == rb["rows_scored"] and rb["timed_rows"] == 1024 and ra["timed_rows"] == n
+        assert rb["prep_seconds"] > rb["timed_prep_seconds"] > 0
