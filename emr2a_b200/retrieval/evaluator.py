@@ -106,13 +106,22 @@ class RetrievalEvaluator:
 
     # ------------------------------------------------------------------- GPU
     @staticmethod
-    def _family(eng, db_op, q_op, db_codes, q_codes, n_classes, top_k_list, prec):
+    def _family(eng, operands, db_codes, q_codes, n_classes, top_k_list, prec):
         """One search at K = max(k list, 5) serves every top-k accuracy and the
-        Top-5 weighted vote of a metric family."""
+        Top-5 weighted vote of a metric family.  ``operands(prec) -> (db_op, q_op)`` runs K1 for a precision arm:
+        when the rescore arm cannot verify more queries than its exact re-scan list holds (dense score
+        neighbourhoods, duplicated cases) the search is repeated with the 3-pass tensor-core arm, as every other
+        caller of ``topk_search`` does -- an unverified filter result is never reported."""
+        db_op, q_op = operands(prec)
         n_db = db_op.n
         k_max = max(max(top_k_list), _WEIGHTED_K)
         k_eff = min(k_max, n_db) if n_db > 0 else 1
         keys = eng.topk_search(q_op, db_op, k_eff, prec)
+        if prec == "rescore":
+            _, overflow = eng.consume_status()
+            if overflow:
+                db_op, q_op = operands("bf16x3")
+                keys = eng.topk_search(q_op, db_op, k_eff, "bf16x3")
         return RetrievalEvaluator._family_from_keys(eng, keys, db_codes, q_codes, n_classes, top_k_list)
 
     @staticmethod
@@ -132,9 +141,10 @@ class RetrievalEvaluator:
         """cosine (both sides re-normalised with epsilon, retrieval/similarity.py:4-7) -> metrics."""
         eng = get_engine()
         prec = eng.pick_precision(len(qs), len(db), db.shape[1], max(max(top_k_list), _WEIGHTED_K))
-        db_op = eng.prepare(db, flags=native.NF_ROWNORM, precision=prec)
-        q_op = eng.prepare(qs, flags=native.NF_ROWNORM, precision=prec)
-        return self._family(eng, db_op, q_op, db_codes, q_codes, n_classes, top_k_list, prec)
+
+        def operands(p):
+            return eng.prepare(db, flags=native.NF_ROWNORM, precision=p), eng.prepare(qs, flags=native.NF_ROWNORM, precision=p)
+        return self._family(eng, operands, db_codes, q_codes, n_classes, top_k_list, prec)
 
     def evaluate_retrieval(
         self,
@@ -185,10 +195,12 @@ class RetrievalEvaluator:
                 # w*cos_T + (1-w)*cos_I as ONE contraction: unit segments, weights folded into the query side
                 n_db, dim = len(train_labels), train_text.shape[1] + train_image.shape[1]
                 prec = eng.pick_precision(len(test_labels), n_db, dim, max(max(top_k_list), _WEIGHTED_K))
-                db_op = eng.prepare(train_text, train_image, 1.0, 1.0, native.NF_SEGNORM, prec)
-                q_op = eng.prepare(test_text, test_image, np.float32(text_weight), np.float32(1 - text_weight),
-                                   native.NF_SEGNORM, prec)
-                accs, weighted, top5 = self._family(eng, db_op, q_op, db_codes, q_codes, n_cls, top_k_list, prec)
+
+                def operands(p):
+                    return (eng.prepare(train_text, train_image, 1.0, 1.0, native.NF_SEGNORM, p),
+                            eng.prepare(test_text, test_image, np.float32(text_weight), np.float32(1 - text_weight),
+                                        native.NF_SEGNORM, p))
+                accs, weighted, top5 = self._family(eng, operands, db_codes, q_codes, n_cls, top_k_list, prec)
             elif self._late_fused(len(test_labels), len(train_labels)):
                 # z-score / min-max without the [Q, N] score matrix: per-query statistics from database moments /
                 # K = 1 searches, then the ordinary fused search with scaled query segments (emr2a_b200/late.py)

@@ -175,6 +175,13 @@ def main():
         cv[f"runcv_{fusion}_f0_scores"] = np.array(res["fold_results"][0]["all_top_scores"])
         cv[f"runcv_{fusion}_f0_ids"] = np.array(
             [[pid_idx[p] for p in row] for row in res["fold_results"][0]["all_top_patient_ids"]])
+        # every fold: Top-K scores / ids and the eight metrics (the drop-in must reproduce them exactly on clear rows)
+        cv[f"runcv_{fusion}_scores"] = np.array([r["all_top_scores"] for r in res["fold_results"]])
+        cv[f"runcv_{fusion}_ids"] = np.array(
+            [[[pid_idx[p] for p in row] for row in r["all_top_patient_ids"]] for r in res["fold_results"]])
+        cv[f"runcv_{fusion}_fold_metrics"] = np.array(
+            [[r[m] for m in ("top1", "top3", "top5", "vote_acc", "weighted_vote_acc",
+                             "macro_precision", "macro_recall", "macro_f1")] for r in res["fold_results"]])
         if fusion == "concat":
             keys = sorted(res["fold_results"][0].keys())
             with open(os.path.join(HERE, "cv_result_keys.json"), "w") as fh:
@@ -210,6 +217,18 @@ def main():
         ho[name + "_vals"] = np.array([sc[k] for k in sorted(sc.keys())], dtype=np.float64)
         if "all_top_labels_top5" in r:
             ho[name + "_top5"] = np.array([[code_of(x) for x in row] for row in r["all_top_labels_top5"]])
+    # the score matrices behind those metrics, from the reference's own primitives (retrieval/similarity.py:4-7,
+    # retrieval/fusion.py:4-28), so that the parity test can tell which queries sit on a near-tie
+    cos_t = np.array([retrieval.compute_cosine_similarity(te_txt[i], tr_txt) for i in range(len(tel))])
+    cos_i = np.array([retrieval.compute_cosine_similarity(te_img[i], tr_img) for i in range(len(tel))])
+    ho["scores_text"], ho["scores_image"] = cos_t, cos_i
+    f_db = retrieval.early_fusion(tr_txt, tr_img, 0.4, 1 - 0.4)
+    f_q = retrieval.early_fusion(te_txt, te_img, 0.4, 1 - 0.4)
+    ho["scores_early"] = np.array([retrieval.compute_cosine_similarity(f_q[i], f_db) for i in range(len(tel))])
+    for name, kw in runs.items():
+        if name != "early":
+            ho["scores_" + name] = np.array([retrieval.late_fusion(cos_t[i], cos_i[i], kw["text_weight"], kw["score_mode"])
+                                             for i in range(len(tel))])
     r = rev.evaluate_retrieval(None, None, tr_img, te_img, trl, tel, fusion_type="none", top_k_list=[1, 3, 5, 5])
     ho["imgonly_keys"] = np.array(sorted(r.keys()))
     ho["imgonly_vals"] = np.array([r[k] for k in sorted(r.keys())], dtype=np.float64)

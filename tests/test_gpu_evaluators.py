@@ -80,11 +80,31 @@ def test_run_cv_end_to_end_matches_reference(golden, fusion, w):
     got_ids = np.array([[pid_idx[p] for p in row] for row in f0["all_top_patient_ids"]])
     safe = np.abs(np.diff(g[f"runcv_{fusion}_f0_scores"], axis=1)).min(axis=1) > 2 * TOL
     assert np.array_equal(got_ids[safe], g[f"runcv_{fusion}_f0_ids"][safe])
-    np.testing.assert_allclose([r["top1"] for r in res["fold_results"]], g[f"runcv_{fusion}_fold_top1"], atol=1.5 / 60)
-    got = np.array([[res["summary"][m][s] for s in ("mean", "std", "min", "max")]
-                    for m in ("top1", "top3", "top5", "vote_acc", "weighted_vote_acc",
-                              "macro_precision", "macro_recall", "macro_f1")])
-    np.testing.assert_allclose(got, g[f"runcv_{fusion}_summary"], atol=0.02)
+    # Every fold: scores within 1e-5, rows identical where the reference's gaps are clear, and -- the run is seeded
+    # identically and the preprocessing is the reference's own sklearn calls -- the eight metrics EXACT whenever all
+    # rows of the fold are clear.  A metric may move only by the queries that sit on a near-tie (gap < 2e-5).
+    names = ("top1", "top3", "top5", "vote_acc", "weighted_vote_acc", "macro_precision", "macro_recall", "macro_f1")
+    unclear_total = 0
+    for f, r in enumerate(res["fold_results"]):
+        want_sc, want_ids = g[f"runcv_{fusion}_scores"][f], g[f"runcv_{fusion}_ids"][f]
+        got_sc = np.array(r["all_top_scores"])
+        got = np.array([[pid_idx[p] for p in row] for row in r["all_top_patient_ids"]])
+        assert np.max(np.abs(got_sc - want_sc)) < TOL, f
+        safe = np.abs(np.diff(want_sc, axis=1)).min(axis=1) > 2 * TOL
+        assert np.array_equal(got[safe], want_ids[safe]), f
+        unclear = int((~safe).sum())
+        unclear_total += unclear
+        got_m = np.array([r[m] for m in names])
+        if unclear == 0:
+            np.testing.assert_allclose(got_m, g[f"runcv_{fusion}_fold_metrics"][f], atol=1e-12, err_msg=f"fold {f}")
+        else:       # accuracies move by at most one query per near-tied row (macro P/R/F1 by a bounded multiple)
+            np.testing.assert_allclose(got_m[:5], g[f"runcv_{fusion}_fold_metrics"][f][:5], atol=unclear / len(safe) + 1e-12)
+    assert unclear_total <= 6                                   # the fixture is overwhelmingly clear: the test bites
+    got = np.array([[res["summary"][m][s] for s in ("mean", "std", "min", "max")] for m in names])
+    if unclear_total == 0:
+        np.testing.assert_allclose(got, g[f"runcv_{fusion}_summary"], atol=1e-12)
+    else:
+        np.testing.assert_allclose(got[:5], g[f"runcv_{fusion}_summary"][:5], atol=unclear_total / 60 + 1e-12)
     assert f0["fold"] == 1 and len(f0["train_ids"]) == 240
 
 
@@ -135,20 +155,52 @@ def test_holdout_evaluator_matches_reference(golden):
         "late_minmax": dict(fusion_type="late", text_weight=0.6, score_mode="minmax"),
     }
     n_q = len(tel)
+    tr_codes, te_codes = g["tr_labels"], g["te_labels"]
+
+    def unclear_queries(scores, depth, weighted=False):
+        """Queries whose metric may legitimately differ from the reference: an adjacent gap among the `depth` best
+        reference scores and the runner-up is inside 2 * tol (tol = 1e-5 relative to the score magnitude), or -- for
+        the weighted vote -- two label sums of the Top-5 are that close."""
+        s = np.sort(scores.astype(np.float64), axis=1)[:, ::-1][:, :depth + 1]
+        tol = TOL * max(1.0, float(np.abs(scores).max()))
+        bad = (-np.diff(s, axis=1)).min(axis=1) <= 2 * tol
+        if weighted:
+            order = np.argsort(-scores, axis=1, kind="stable")[:, :5]
+            for i in range(len(scores)):
+                labs = tr_codes[order[i]]
+                sums = sorted((float(scores[i, order[i]][labs == c].sum()) for c in set(labs.tolist())), reverse=True)
+                if len(sums) > 1 and sums[0] - sums[1] <= 2 * 5 * tol:
+                    bad[i] = True
+        return int(bad.sum()), bad
+
+    def check_metric(name, key, got, want):
+        prefix, _, metric = key.rpartition("_")
+        fam = {"text": "scores_text", "image": "scores_image"}.get(prefix, "scores_" + name)
+        if fam not in g:
+            fam = "scores_image"
+        depth = 5 if metric == "weighted" else int(metric[3:])
+        n_bad, _ = unclear_queries(g[fam], depth, weighted=(metric == "weighted"))
+        # exact unless queries sit on a near-tie; then at most that many queries may flip
+        assert abs(got - want) <= n_bad / n_q + 1e-12, (name, key, got, want, n_bad)
+        return n_bad
+
+    n_bad_per_check = []
     for name, kw in runs.items():
         r = ev.evaluate_retrieval(g["tr_txt"], g["te_txt"], g["tr_img"], g["te_img"], trl, tel, top_k_list=[1, 3, 5, 7], **kw)
         scalars = {k: v for k, v in r.items() if not isinstance(v, list)}
         assert sorted(scalars) == [str(k) for k in g[name + "_keys"]], name
         for k, v in zip(g[name + "_keys"], g[name + "_vals"]):
-            # a rank flip between near-equal scores may move at most one query
-            assert abs(scalars[str(k)] - v) <= 1.0 / n_q + 1e-12, (name, k, scalars[str(k)], v)
+            n_bad_per_check.append(check_metric(name, str(k), scalars[str(k)], float(v)))
         if name + "_top5" in g:
             got = np.array([[int(x.split("_")[1]) for x in row] for row in r["all_top_labels_top5"]])
-            assert (got == g[name + "_top5"]).mean() > 0.98
+            _, bad = unclear_queries(g["scores_" + name], 5)
+            assert np.array_equal(got[~bad], g[name + "_top5"][~bad]), name
+            assert bad.mean() < 0.1
+    assert np.mean(np.array(n_bad_per_check) == 0) > 0.6         # most comparisons above were exact ones (no near-tie)
     r = ev.evaluate_retrieval(None, None, g["tr_img"], g["te_img"], trl, tel, fusion_type="none", top_k_list=[1, 3, 5, 5])
     assert sorted(r) == [str(k) for k in g["imgonly_keys"]]
     for k, v in zip(g["imgonly_keys"], g["imgonly_vals"]):
-        assert abs(r[str(k)] - v) <= 1.0 / n_q + 1e-12
+        check_metric("image", str(k), r[str(k)], float(v))
     with pytest.raises(ValueError, match="Early fusion requires both"):
         ev.evaluate_retrieval(None, None, g["tr_img"], g["te_img"], trl, tel, fusion_type="early")
     sc = g["fs_scores"]
@@ -156,6 +208,42 @@ def test_holdout_evaluator_matches_reference(golden):
     assert ev._compute_weighted_accuracy_from_scores(sc, trl, tel) == float(g["fs_weighted"])
     got = np.array([[int(x.split("_")[1]) for x in row] for row in ev.get_all_top_labels(sc, trl, tel, 5)])
     assert np.array_equal(got, g["fs_top5_labels"])
+
+
+def test_holdout_evaluator_rescore_overflow_is_not_reported_as_exact(monkeypatch):
+    """A database of large tight clusters (near-duplicate cases) defeats the rescore bound for every query and
+    overflows the exact re-scan list: evaluate_retrieval must fall back to the 3-pass arm like every other caller
+    (never report the unverified filter result) and leave no stale status behind."""
+    import torch
+    from emr2a_b200.engine import get_engine
+    from emr2a_b200.retrieval import RetrievalEvaluator
+    eng = get_engine()
+    g = torch.Generator().manual_seed(3)
+    n_clusters, per, d = 30, 100, 128
+    centres = torch.randn((n_clusters, d), generator=g)
+    tr = (centres.repeat_interleave(per, dim=0) + 0.01 * torch.randn((n_clusters * per, d), generator=g)).numpy()
+    pick = torch.randint(0, n_clusters, (1500,), generator=g)
+    te = (centres[pick] + 0.01 * torch.randn((1500, d), generator=g)).numpy()
+    trl = [f"class_{(j // per) % 3}" for j in range(n_clusters * per)]       # neighbours of a cluster share one label
+    tel = [f"class_{int(c) % 3}" for c in pick]
+    ev = RetrievalEvaluator()
+    monkeypatch.setenv("EMR2A_PRECISION", "fp32")
+    want = ev.evaluate_retrieval(tr, te, tr[:, ::-1].copy(), te[:, ::-1].copy(), trl, tel, text_weight=0.4, top_k_list=[1, 3, 5])
+    monkeypatch.setenv("EMR2A_PRECISION", "rescore")
+    eng._status_log.clear()
+    flagged = []
+    real = eng.topk_search
+
+    def spy(q, db, k, precision="fp32", **kw):
+        flagged.append(precision)
+        return real(q, db, k, precision, **kw)
+    monkeypatch.setattr(eng, "topk_search", spy)
+    got = ev.evaluate_retrieval(tr, te, tr[:, ::-1].copy(), te[:, ::-1].copy(), trl, tel, text_weight=0.4, top_k_list=[1, 3, 5])
+    assert flagged.count("rescore") == 3 and flagged.count("bf16x3") == 3          # text, image, late: each fell back
+    assert not eng._status_log                                                     # nothing left for an unrelated caller
+    assert {k: v for k, v in got.items() if not isinstance(v, list)} == {k: v for k, v in want.items() if not isinstance(v, list)}
+    assert got["all_top_labels_top5"] == want["all_top_labels_top5"]
+    assert got["top1"] == 1.0
 
 
 def test_c1_full_size_against_oracle(oracle):

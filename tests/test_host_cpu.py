@@ -261,3 +261,54 @@ def test_public_signatures_match_the_reference():
                 check(f"{mod_name}.{name}", obj, want)
                 checked += 1
     assert checked >= 35
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "analysis")), reason="reference tree not present (GPU box)")
+def test_run_cv_experiments_script_reaches_the_dropin(tmp_path):
+    """analysis/run_cv_experiments.py launched UNCHANGED through emr2a_b200/run.py from the reference root
+    (--skip_encoding, the layout of :111-128): every import of the script resolves (encoders, utils.vlm_review through
+    the drop-in package's extended path, utils.cv_evaluator = ours) and the run gets as far as the first kernel call
+    of OUR CVRetrievalEvaluator -- which, without a GPU, stops with 'no CPU fallback' instead of running the
+    reference's numpy loop.  (With a GPU it completes and writes the experiment directory; the value-for-value check
+    of those files is tests/test_gpu_scripts_replay.py.)"""
+    import json
+    import subprocess
+    import sys
+    rng = np.random.default_rng(1)
+    n = 60
+    manifest = tmp_path / "manifest.jsonl"
+    with manifest.open("w") as fh:
+        for i in range(n):
+            fh.write(json.dumps({"patient_id": f"p{i:03d}", "label": f"class_{i % 3}", "slices": [], "meta": {}}) + "\n")
+    np.savez(tmp_path / "emb.npz", patient_ids=np.array([f"p{i:03d}" for i in range(n)], dtype=object),
+             image_matrix=rng.standard_normal((n, 2, 24)).astype(np.float32),
+             text_matrix=rng.standard_normal((n, 20)).astype(np.float32))
+    # modules the reference imports at module level but that this image lacks (SURVEY App. D): stubbed via sitecustomize
+    site = tmp_path / "site"
+    site.mkdir()
+    (site / "sitecustomize.py").write_text(
+        "import sys, types, importlib.machinery as im\n"
+        "def stub(name, **kw):\n"
+        "    m = types.ModuleType(name); m.__spec__ = im.ModuleSpec(name, None); m.__path__ = []; m.__dict__.update(kw)\n"
+        "    sys.modules[name] = m; return m\n"
+        "noop = lambda *a, **k: None\n"
+        "for name in ('qwen_vl_utils', 'timm', 'timm.data', 'open_clip'):\n"
+        "    try:\n"
+        "        __import__(name)\n"
+        "    except Exception:\n"
+        "        stub(name, process_vision_info=noop, create_transform=noop, resolve_data_config=noop, create_model=noop)\n")
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1", PYTHONPATH=str(site))
+    out = subprocess.run([sys.executable, os.path.join(REPO, "emr2a_b200", "run.py"), "analysis.run_cv_experiments",
+                          "--manifest_path", str(manifest), "--skip_encoding", "--embeddings_path", str(tmp_path / "emb.npz"),
+                          "--output_dir", str(tmp_path / "out"), "--experiment_id", "t", "--pca_dim", "8", "--top_k", "3",
+                          "--device", "cpu"], cwd=REFERENCE, env=env, capture_output=True, text=True)
+    import torch
+    if torch.cuda.is_available():
+        assert out.returncode == 0, out.stderr[-3000:]
+        m = json.load(open(tmp_path / "out" / "exp_t" / "fold_1" / "metrics.json"))
+        assert {"all_top_labels", "all_top_scores", "all_top_patient_ids", "test_patient_ids", "top1"} <= set(m)
+    else:
+        assert out.returncode != 0
+        assert "no CPU fallback" in out.stderr, out.stderr[-3000:]
+        assert "emr2a_b200/utils/cv_evaluator.py" in out.stderr.replace("\\", "/")      # it was OUR evaluator that ran
+        assert "Running experiment: t" in out.stderr                                      # the script's own driver code ran
