@@ -1,22 +1,29 @@
 """EMR2A retrieval hot path benchmark (BASELINE.json metric: queries/sec, cosine Top-K + vote).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c1|c2|c2k5|c3|c4|c5|small]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload ("c2", BASELINE.json configs[1]): 1M-case database, 512-d image + 512-d text
+Headline workload ("c2", BASELINE.json configs[1]): 1M-case database, 512-d image + 512-d text
 embeddings (fp32, synthetic class-structured Gaussians), concat fusion to 1024-d, 10k queries,
 K=10, 3 classes.  A STEP = the whole hot path over that batch:
     K1 normalise+fuse (database shard AND queries) -> K2 similarity + fused Top-K
     -> K3 merge -> [NCCL all-gather of local Top-K + K3 merge when N > 1] -> K4 vote + metrics.
-N > 1: the SAME 1M-row database is sharded row-wise over the ranks (strong scaling).
+N > 1: the SAME 1M-row database is sharded row-wise over the ranks (strong scaling), and the line carries a "c5"
+sub-record: BASELINE.json configs[4] (every case a query, 5-fold CV rule, K=5) on all N GPUs -- the full
+10M-case cohort at N = 8, sqrt(N/8)-scaled row counts below (same per-GPU time), see run_c5.
 
 value  : queries/sec with the raw embeddings resident in HBM.
 e2e    : queries/sec through Engine.search_and_vote_host with the inputs in PINNED HOST
          memory: every step copies the database shard + queries host->device (chunked,
          overlapped with compute) and the results device->host.
-roofline: the K2 kernel (tensor pipe): algorithmic FLOPs 2*D*Q*N_local / its CUDA-event time.
-cpu_baseline / --impl reference: the oracle's reference-style loop (np.dot sgemv + full
-         np.argsort + python votes, per query) on the host cores, on a bounded query sample.
+roofline: the K2 kernel (tensor pipe): algorithmic FLOPs 2*D*Q*N_local / its CUDA-event time; traffic = DRAM bytes
+         of that kernel from the committed ncu capture listed in profiles/k2_traffic.json.
+cpu_baseline: the reference's algorithm (oracle port: per-query np.dot sgemv over every admissible row + full np.argsort
+         + python votes, utils/cv_evaluator.py:232-300) on the host cores for a SAMPLE of queries against ALL database
+         rows, the database streamed from the GPU in chunks (oracle.StreamedReferenceSample), with the parity of the
+         GPU results on that sample (index rows / votes under the gap rule) -- every workload, C2 to C5.
+--impl reference: the same algorithm timed alone; inputs are the GPU arm's (synth.device_block on the box's GPU,
+         copied to the host).
 """
 import argparse
 import json
@@ -49,8 +56,10 @@ WORKLOADS = {
     # BASELINE.json configs[3]: Qwen3-VL-shaped 4096-d image + 1024-d text, bf16 INPUTS, fp32 accumulation, 2M cases
     "c4": (2_000_000, 4096, 1024, 10_000, 10, 3, 17),
     # BASELINE.json configs[4]: every case is a query against the other folds (n_q == n_db); multi-GPU workload
-    "c5": (int(os.environ.get("EMR2A_C5_N", 10_000_000)), 512, 512, -1, 5, 3, 19),
+    "c5": (10_000_000, 512, 512, -1, 5, 3, 19),
 }
+C3_W_TEXT = 0.25
+Q_ROW0 = 50_003_968          # first synthetic row of the query block (far outside any database)
 
 
 def parse():
@@ -61,10 +70,21 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("EMR2A_BENCH_WORKLOAD", "c2"), choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default=os.environ.get("EMR2A_BENCH_PRECISION", "rescore"))
-    ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("EMR2A_BENCH_CPU_SAMPLE", 48)))
+    ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("EMR2A_BENCH_CPU_SAMPLE", 32)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="N > 1: skip the C5 sub-record next to the C2 headline")
     return ap.parse_args()
+
+
+def workload_string(name, n_db=None):
+    n, d_img, d_txt, n_q, k, n_cls, _ = WORKLOADS[name]
+    n_db = n if n_db is None else n_db
+    if name == "c5":
+        return f"c5: {n_db}-case {d_img + d_txt}-d fused database, every case a query, 5-fold CV rule, K={k}"
+    fusion = f"late fusion (w_text={C3_W_TEXT}, merge-then-Top-K)" if name == "c3" else "concat fusion"
+    dtype = " (bf16 in)" if name == "c4" else " (fp32 in)"
+    return f"{name}: {n_db}-case database, {d_img}+{d_txt}-d {fusion}{dtype}, {n_q} queries, K={k}, {n_cls} classes"
 
 
 def peaks():
@@ -86,6 +106,21 @@ def tensor_peak(pk, load_seconds):
     if load_seconds >= 1.5:
         return pk["tflops"], f"bf16 sustained (continuous load {load_seconds:.1f} s >= 1.5 s)"
     return pk["tflops_burst"], f"bf16 burst (continuous load {load_seconds:.1f} s < 1.5 s)"
+
+
+def k2_traffic(workload, precision, world):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture for this workload
+    (profiles/k2_traffic.json names the capture each figure comes from); None when there is no capture of it."""
+    path = os.path.join(REPO, "profiles", "k2_traffic.json")
+    try:
+        with open(path) as fh:
+            table = json.load(fh)
+    except Exception:
+        return None, None
+    rec = table.get(f"{workload}/{precision}/{world}gpu")
+    if not rec:
+        return None, None
+    return rec.get("dram_bytes_per_launch"), rec.get("source")
 
 
 class ClockSampler:
@@ -111,15 +146,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self, windows=None):
-        """Summary of the samples that arrived inside the given (t0, t1) wall-clock windows (the timed regions)."""
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+    def summary(self, windows=None):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, r in self.rows:
+        for ts, r in list(self.rows):
             if windows and not any(a <= ts <= b + 0.12 for a, b in windows):
                 continue
             try:
@@ -131,129 +161,188 @@ class ClockSampler:
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm),
-                "window": "timed regions (device-resident loop + e2e loop), nvidia-smi -lms 100"}
+                "window": "timed regions, nvidia-smi -lms 100"}
+
+    def stop(self, windows=None):
+        """Summary of the samples that arrived inside the given (t0, t1) wall-clock windows (the timed regions)."""
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        return self.summary(windows)
 
 
-def cpu_reference_leg(db_img, db_txt, q_img, q_txt, db_labels, q_labels, k, sample, full_q):
-    """The reference's algorithm on the host cores (oracle port): normalise + fuse the database
-    once (utils/cv_evaluator.py:95-105), then per query sgemv + argsort + votes (:269-300)."""
+def _oracle():
     sys.path.insert(0, os.path.join(REPO, "oracle"))
     import emr2a_oracle as oracle
+    import streamed_feed
+    return oracle, streamed_feed
+
+
+def _blas_threads():
     try:
         from threadpoolctl import threadpool_info
-        threads = max([i.get("num_threads", 1) for i in threadpool_info()] or [1])
+        return int(max([i.get("num_threads", 1) for i in threadpool_info()] or [1]))
     except Exception:
-        threads = os.cpu_count() or 1
+        return int(os.cpu_count() or 1)
+
+
+def cpu_sample_leg(mode, k, n_db, fetch, q_img, q_txt, db_labels, q_labels, full_q, w_text=0.5, q_fold=None,
+                   chunk_rows=65536, timed_rows=131072, prep_passes=1.0, got=None):
+    """The reference's loop on the host cores for a sample of queries against ALL ``n_db`` rows (streamed through
+    ``fetch``), its throughput extrapolated to the full workload, and the parity of the GPU results ``got``
+    (dict of top_idx / top_scores / pred_vote / pred_weighted rows for the same queries) under the gap rule.
+    ``prep_passes``: how many times the reference normalises/fuses an n_db-row matrix for the whole workload (1 for
+    C2-C4; 5 for the 5-fold CV, whose train + test matrices add up to the cohort once per fold)."""
+    oracle, feed = _oracle()
+    s = oracle.StreamedReferenceSample(mode, k, n_db, q_img, q_txt, w_text=w_text, q_fold=q_fold)
     t0 = time.perf_counter()
-    db = oracle.fuse_concat_cv(oracle.unit_rows(db_img), oracle.unit_rows(db_txt))
-    t_prep = time.perf_counter() - t0
-    rng = np.random.default_rng(0)
-    pick = np.sort(rng.choice(len(q_labels), size=min(sample, len(q_labels)), replace=False))
-    qs = oracle.fuse_concat_cv(oracle.unit_rows(q_img[pick]), oracle.unit_rows(q_txt[pick]))
-    t0 = time.perf_counter()
-    res = oracle.reference_style_search_and_vote(qs, db, db_labels, q_labels[pick], k)
-    t_q = (time.perf_counter() - t0) / len(pick)
+    feed.feed(s, n_db, fetch, chunk_rows=chunk_rows, timed_rows=timed_rows)
+    ref = s.finish(db_labels, q_labels)
+    wall = time.perf_counter() - t0
+    t_prep, t_q = ref["prep_seconds"] * prep_passes, ref["seconds_per_query"]
     qps = full_q / (t_prep + full_q * t_q)
-    info = {"value": qps, "unit": "queries/s", "cores": int(threads), "kind": "port",
-            "sample": f"{len(pick)} of {full_q} queries against the full {len(db)}-row database "
-                      f"({t_q * 1e3:.1f} ms/query) + one database normalise/fuse pass ({t_prep:.1f} s), "
-                      f"extrapolated to the full step; host has {os.cpu_count()} logical cores"}
-    return info, pick, res
+    info = {"value": qps, "unit": "queries/s", "cores": _blas_threads(), "kind": "port",
+            "sample": f"{len(q_labels)} of {full_q} queries, each scored against every admissible row of the {n_db}-row "
+                      f"database (sgemv timed on the first {ref['timed_rows']} rows and scaled by rows; np.argsort over all "
+                      f"{n_db} scores + python votes timed per query: {t_q * 1e3:.1f} ms/query) + database normalise/fuse "
+                      f"({t_prep:.1f} s, from {ref['timed_prep_seconds']:.2f} s on the timed rows), extrapolated to the "
+                      f"full step; {wall:.0f} s of host time; host has {os.cpu_count()} logical cores"}
+    if got is not None:
+        par = oracle.sample_parity(ref, got["top_idx"], got["top_scores"], got.get("pred_vote"), got.get("pred_weighted"))
+        info["parity_on_sample"] = par
+    return info, ref
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port; the reference is pure Python and
-    /root/reference does not exist on the GPU box), every host thread BLAS can use."""
+    """--impl reference: the reference's CPU path (oracle port; the reference is pure Python and /root/reference does
+    not exist on the GPU box), every host thread BLAS can use.  Inputs: the GPU arm's own generator
+    (``synth.device_block`` on the box's GPU, copied to the host) -- identical arrays.  A step = a bounded, proportional
+    sample of the workload: ``sample`` of the n_q queries through the reference loop against the full prepared
+    database (sgemv over all rows + full argsort + votes, utils/cv_evaluator.py:269-300) PLUS the same fraction of the
+    database normalise/fuse pass (utils/cv_evaluator.py:95-105; n_db * sample / n_q rows re-done inside the step).
+    ``value`` = sample / measured step time; ``ms_per_step`` is that measured time."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    from emr2a_b200 import synth
-    n_db, d_img, d_txt, n_q, k, n_cls, seed = WORKLOADS[args.workload]
     import torch
-    g = torch.Generator().manual_seed(seed)
-    lab = torch.randint(0, n_cls, (n_db + n_q,), generator=g).numpy().astype(np.int32)
-    cen_i = torch.randn((n_cls, d_img), generator=g).numpy()
-    cen_t = torch.randn((n_cls, d_txt), generator=g).numpy()
-    img = torch.randn((n_db + n_q, d_img), generator=g).numpy()
-    txt = torch.randn((n_db + n_q, d_txt), generator=g).numpy()
-    img += np.float32(synth.SEP) * cen_i[lab]
-    txt += np.float32(synth.SEP) * cen_t[lab]
-    sys.path.insert(0, os.path.join(REPO, "oracle"))
-    import emr2a_oracle as oracle
-    try:
-        from threadpoolctl import threadpool_info
-        threads = max([i.get("num_threads", 1) for i in threadpool_info()] or [1])
-    except Exception:
-        threads = 1
+    from emr2a_b200 import synth
+    oracle, _ = _oracle()
+    name = args.workload if args.workload != "c5" else "c2"
+    n_db, d_img, d_txt, n_q, k, n_cls, seed = WORKLOADS[name]
+    dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+    mode = "late" if name == "c3" else "concat"
+    dt = torch.bfloat16 if name == "c4" else None
+
+    def host_block(row0, rows, dim, s):
+        out = np.empty((rows, dim), dtype=np.float32)
+        for r0 in range(0, rows, 262144):
+            r1 = min(r0 + 262144, rows)
+            out[r0:r1] = synth.device_block(row0 + r0, r1 - r0, dim, n_cls, s, dev, label_seed=seed, dtype=dt)[0].float().cpu().numpy()
+        return out
+    img, txt = host_block(0, n_db, d_img, seed), host_block(0, n_db, d_txt, seed + 1)
+    q_img, q_txt = host_block(Q_ROW0, n_q, d_img, seed), host_block(Q_ROW0, n_q, d_txt, seed + 1)
+    db_lab = synth.device_labels(0, n_db, n_cls, seed, dev).cpu().numpy()
+    q_lab = synth.device_labels(Q_ROW0, n_q, n_cls, seed, dev).cpu().numpy()
+
+    def prep(a, b):
+        if mode == "late":
+            return oracle.unit_rows(a), oracle.unit_rows(b)
+        return oracle.fuse_concat_cv(oracle.unit_rows(a), oracle.unit_rows(b))
     t0 = time.perf_counter()
-    db = oracle.fuse_concat_cv(oracle.unit_rows(img[:n_db]), oracle.unit_rows(txt[:n_db]))
-    t_prep = time.perf_counter() - t0
+    db = prep(img, txt)
+    t_prep_full = time.perf_counter() - t0
     sample = max(4, min(args.cpu_sample, 16))
-    qs_all = oracle.fuse_concat_cv(oracle.unit_rows(img[n_db:]), oracle.unit_rows(txt[n_db:]))
+    share = max(1, n_db * sample // n_q)                       # database rows whose preparation belongs to one step
     times = []
     for s in range(args.warmup + args.steps):
         lo = (s * sample) % (n_q - sample)
+        r0 = (s * share) % (n_db - share)
         t0 = time.perf_counter()
-        oracle.reference_style_search_and_vote(qs_all[lo:lo + sample], db, lab[:n_db], lab[n_db + lo:n_db + lo + sample], k)
-        dt = time.perf_counter() - t0
+        prep(img[r0:r0 + share], txt[r0:r0 + share])            # this step's share of the normalise/fuse pass
+        qs = prep(q_img[lo:lo + sample], q_txt[lo:lo + sample])
+        if mode == "late":
+            for i in range(sample):
+                sims = C3_W_TEXT * np.dot(db[1], qs[1][i]) + (1 - C3_W_TEXT) * np.dot(db[0], qs[0][i])
+                idx = np.argsort(sims)[-k:][::-1]
+                labs = [int(db_lab[j]) for j in idx]
+                oracle.vote_majority(labs), oracle.vote_weighted(labs, [float(sims[j]) for j in idx], "f64")
+        else:
+            oracle.reference_style_search_and_vote(qs, db, db_lab, q_lab[lo:lo + sample], k)
+        dt_s = time.perf_counter() - t0
         if s >= args.warmup:
-            times.append(dt)
-    t_q = sum(times) / (len(times) * sample)
-    qps = n_q / (t_prep + n_q * t_q)
+            times.append(dt_s)
+    t_step = sum(times) / len(times)
+    qps = sample / t_step
+    threads = _blas_threads()
     line = {"impl": "reference", "metric": "queries/sec (cosine Top-K + vote)", "value": qps, "unit": "queries/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * (t_prep + n_q * t_q), "higher_is_better": True, "scaling": "strong",
+            "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {n_db}-case database, {d_img}+{d_txt}-d concat fusion, {n_q} queries, K={k}",
-                       "parallelism": "cpu"},
-            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": int(threads), "kind": "port",
-                             "sample": f"each step = {sample} queries against the full database ({t_q * 1e3:.1f} ms/query) "
-                                       f"+ amortised database normalise/fuse ({t_prep:.1f} s per {n_q} queries); "
-                                       f"{os.cpu_count()} logical cores"},
+            "config": {"workload": workload_string(name), "parallelism": "cpu",
+                       "step": f"{sample} of the {n_q} queries (reference loop against the full {n_db}-row database) + the same "
+                               f"fraction of the database normalise/fuse pass ({share} rows)",
+                       "inputs": "synth.device_block on " + ("the box's GPU, copied to the host (the GPU arm's arrays)"
+                                                             if dev.type == "cuda" else "the CPU generator (no GPU present)")},
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
+                             "sample": f"each step = {sample} queries against the full database + {share} database rows "
+                                       f"normalised/fused; {os.cpu_count()} logical cores"},
+            "extrapolated_full_step_ms": 1e3 * t_step * n_q / sample,
+            "full_database_prepare_s": t_prep_full,
             "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
 
 
-def run_c5(args):
-    """BASELINE.json configs[4]: N-case 1024-d fused database, EVERY case a query, 5-fold CV rule (a case
-    is never retrieved from its own fold), K=5, database row-sharded over the ranks.  Rows are in fold
-    order (fold = contiguous fifths of the synthetic, label-shuffled rows).  Per step and rank: K1 on the
-    shard; one all-gather of the raw rows (every case is a query); for every query block: K1, fold-masked K2
-    against the local shard (whole own-fold tiles skipped); then all-gather of the local Top-K, K3 merge, K4 vote
-    with per-fold counters."""
+def c5_rows_for(world):
+    """Cohort size of the C5 record: the full 10M cases at 8 GPUs (and for an explicit EMR2A_C5_N); sqrt(world/8) of
+    it below, which keeps the per-GPU work -- the pair count N^2 / world -- the same at every GPU count."""
+    if "EMR2A_C5_N" in os.environ:
+        return int(os.environ["EMR2A_C5_N"])
+    n = WORKLOADS["c5"][0]
+    if world >= 8:
+        return n
+    return int(round(n * (world / 8.0) ** 0.5 / 100_000.0)) * 100_000
+
+
+def c5_record(args, eng, dev, world, rank, local_rank, n, steps, warm_full, cpu_sample):
+    """BASELINE.json configs[4]: N-case 1024-d fused database, EVERY case a query, 5-fold CV rule (a case is never
+    retrieved from its own fold), K=5.  Rows are in fold order (fold = contiguous fifths of the synthetic,
+    label-shuffled rows) and sharded FOLD-BALANCED: rank r holds piece r of every fold.  Per step and
+    rank: K1 once on the shard; query blocks walked owner by owner, the owner's prepared rows broadcast over NVLink
+    (double-buffered, block b+1 in flight while block b is searched); fold-masked K2 against the local shard (whole
+    own-fold tiles skipped); all-gather of the local Top-K, K3 merge, K4 vote with per-fold counters
+    (emr2a_b200/dist.py: sharded_cv_search_and_vote)."""
     import torch
     import torch.distributed as dist
     from emr2a_b200 import native, synth
-    from emr2a_b200.dist import shard_range, sharded_cv_search_and_vote
-    from emr2a_b200.engine import get_engine
+    from emr2a_b200.dist import fold_balanced_ranges, ranges_to_rows, sharded_cv_search_and_vote
 
-    world = int(os.environ.get("WORLD_SIZE", 1)); rank = int(os.environ.get("RANK", 0))
-    local_rank = int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local_rank); dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    eng = get_engine(dev)
-    n, d_img, d_txt, _, k, n_cls, seed = WORKLOADS["c5"]
+    _, d_img, d_txt, _, k, n_cls, seed = WORKLOADS["c5"]
     n_folds, dim = 5, d_img + d_txt
     q_block = int(os.environ.get("EMR2A_C5_QBLOCK", 262144))
-    lo, hi = shard_range(n, rank, world)
     flags = native.NF_SEGNORM | native.NF_ROWNORM
-    db_img, _ = synth.device_block(lo, hi - lo, d_img, n_cls, seed, dev, label_seed=seed)
-    db_txt, _ = synth.device_block(lo, hi - lo, d_txt, n_cls, seed + 1, dev, label_seed=seed)
-    labels = synth.device_labels(0, n, n_cls, seed, dev)
-    fold = (torch.arange(n, device=dev, dtype=torch.int64) * n_folds // n).to(torch.uint8)
     prec = args.precision
-    torch.cuda.synchronize()
 
-    def step():
-        # the library path: one all-gather of the raw rows, communication-free local search of every query block,
-        # exchange of the local Top-K keys, K3 merge, K4 vote with per-fold counters (emr2a_b200/dist.py)
-        r = sharded_cv_search_and_vote(eng, (db_img, db_txt), labels, fold, n_cls, k, lo, flags, k_list=[1, 3, 5],
-                                       precision=prec, n_folds=n_folds, q_block=q_block, fold_sorted=True)
+    def fold_vector(m):
+        return (torch.arange(m, device=dev, dtype=torch.int64) * n_folds // m).to(torch.uint8)
+
+    def build(m):
+        fold = fold_vector(m)
+        counts = torch.bincount(fold.long(), minlength=n_folds).cpu().tolist()
+        ranges = fold_balanced_ranges(counts, rank, world)
+        img = torch.cat([synth.device_block(g0, c, d_img, n_cls, seed, dev, label_seed=seed)[0] for g0, c in ranges])
+        txt = torch.cat([synth.device_block(g0, c, d_txt, n_cls, seed + 1, dev, label_seed=seed)[0] for g0, c in ranges])
+        return img, txt, synth.device_labels(0, m, n_cls, seed, dev), fold, ranges_to_rows(ranges, dev)
+
+    def step(data, want_lists):
+        img, txt, labels, fold, rows = data
+        r = sharded_cv_search_and_vote(eng, (img, txt), labels, fold, n_cls, k, 0, flags, k_list=[1, 3, 5],
+                                       precision=prec, n_folds=n_folds, q_block=q_block, fold_sorted=True,
+                                       want_lists=want_lists, row_ids=rows)
         if r["precision"] != prec:
             raise RuntimeError("rescore re-scan list overflowed on this workload; run with --precision bf16x3")
-        return r["hit_counts"], r["vote_counts"], r["group_sizes"], r["unverified"]
+        return r
 
     def barrier():
         torch.cuda.synchronize()
@@ -261,49 +350,97 @@ def run_c5(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(1, min(args.warmup, 1))):
-        out = step()
+    if not warm_full:                                   # sub-record: load the fold-masked kernels on a small cohort
+        step(build(200_000), False)
+    data = build(n)
+    if warm_full:
+        step(data, True)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)
     l0 = eng.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    steps = max(1, args.steps)
+    w0 = time.time()
     e0.record()
     for _ in range(steps):
-        out = step()
+        out = step(data, True)
     e1.record()
     barrier()
+    windows = [(w0, time.time())]
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0]) / steps
-    clocks = sampler.stop() if rank == 0 else None
-    hits, votes, sizes, unverified = out
+    clocks = sampler.stop(windows) if rank == 0 else None
+    launches = eng.launches - l0
+    peak_mem = torch.cuda.max_memory_allocated(dev)
+    rec = None
     if rank == 0:
         pk = peaks()
+        hits, votes, sizes = out["hit_counts"], out["vote_counts"], out["group_sizes"]
         pairs = float(n) * float(n) * (1.0 - 1.0 / n_folds)          # same-fold pairs are not counted
         tf = 2.0 * dim * pairs / (ms / 1e3) / 1e12
-        line = {"metric": "queries/sec (cosine Top-K + vote)", "value": n / (ms / 1e3), "unit": "queries/s", "n_gpus": world,
-                "steps": steps, "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": prec, "data": "synthetic",
-                "config": {"workload": f"c5: {n}-case {dim}-d fused database, every case a query, {n_folds}-fold CV rule, K={k}",
-                           "parallelism": f"database row-sharded x{world}; raw rows all-gathered once per step (every case is a "
-                                          f"query), query blocks of {q_block} searched locally, NCCL all-gather of local Top-K",
-                           "l2": "inputs larger than L2"},
-                "clocks": clocks, "e2e": None, "gpu_launches": eng.launches - l0,
-                "roofline": {"bound": "tensor", "achieved": tf / world, "peak": tensor_peak(pk, ms * (steps + 1) / 1e3)[0],
-                             "unit": "TFLOP/s per GPU", "frac": tf / world / tensor_peak(pk, ms * (steps + 1) / 1e3)[0],
-                             "peak_source": pk["src"] + " " + tensor_peak(pk, ms * (steps + 1) / 1e3)[1],
-                             "frac_of_burst": tf / world / pk["tflops_burst"], "frac_of_sustained": tf / world / pk["tflops"],
-                             "traffic": None,
-                             "note": "whole step (row all-gather + K1 + K2 + key gather + K3 + K4) over admissible pairs only"},
-                "cpu_baseline": None, "unverified_queries": int(unverified),
-                "accuracy": {"top1": float(hits[:, 0].sum()) / n, "top5": float(hits[:, 2].sum()) / n,
-                             "vote_acc": float(votes[:, 1].sum()) / n,
-                             "per_fold_top1": [float(hits[f, 0]) / max(float(sizes[f]), 1.0) for f in range(n_folds)]}}
-        emit(line)
+        load = ms * (steps + (1 if warm_full else 0)) / 1e3
+        t_peak, t_src = tensor_peak(pk, load)
+        cpu = None
+        if cpu_sample > 0:
+            # oracle sample: `cpu_sample` cases spread over the folds, each against ALL cases of the other folds; the
+            # cohort is regenerated chunk by chunk on this rank's GPU (the shards of the other ranks never leave them)
+            _, feed = _oracle()
+            pick = torch.linspace(0, n - 1, cpu_sample, device=dev).long()
+            fold = data[3]
+            q_img = torch.cat([synth.device_block(int(r), 1, d_img, n_cls, seed, dev, label_seed=seed)[0] for r in pick])
+            q_txt = torch.cat([synth.device_block(int(r), 1, d_txt, n_cls, seed + 1, dev, label_seed=seed)[0] for r in pick])
+            fetch = feed.generated_fetcher(lambda r0, m: synth.device_block(r0, m, d_img, n_cls, seed, dev, label_seed=seed)[0],
+                                           lambda r0, m: synth.device_block(r0, m, d_txt, n_cls, seed + 1, dev, label_seed=seed)[0],
+                                           lambda r0, m: fold[r0:r0 + m].cpu().numpy())
+            got = {nm: out[nm][pick].cpu().numpy() for nm in ("top_idx", "top_scores", "pred_vote", "pred_weighted")}
+            labels_h = data[2].cpu().numpy()
+            cpu, _ = cpu_sample_leg("concat", k, n, fetch, q_img.cpu().numpy(), q_txt.cpu().numpy(), labels_h,
+                                    labels_h[pick.cpu().numpy()], n, q_fold=fold[pick].cpu().numpy(), prep_passes=float(n_folds),
+                                    got=got)
+        rec = {"metric": "queries/sec (cosine Top-K + vote)", "value": n / (ms / 1e3), "unit": "queries/s", "n_gpus": world,
+               "steps": steps, "warmup": 1 if warm_full else 0, "ms_per_step": ms, "higher_is_better": True,
+               "scaling": "strong", "vs_baseline": None, "dtype": {"rescore": "bf16+f32"}.get(prec, prec), "data": "synthetic",
+               "config": {"workload": workload_string("c5", n),
+                          "parallelism": f"fold-balanced row shards x{world} (a slice of every fold per GPU); K1 once per shard; "
+                                         f"query blocks of {q_block} prepared rows broadcast from their owner over NVLink "
+                                         f"(double-buffered), searched locally; NCCL all-gather of local Top-K",
+                          "l2": "inputs larger than L2"},
+               "clocks": clocks, "e2e": None, "gpu_launches": launches,
+               "roofline": {"bound": "tensor", "achieved": tf / world, "peak": t_peak, "unit": "TFLOP/s per GPU",
+                            "frac": tf / world / t_peak, "peak_source": pk["src"] + " " + t_src,
+                            "frac_of_burst": tf / world / pk["tflops_burst"], "frac_of_sustained": tf / world / pk["tflops"],
+                            "traffic": None,
+                            "note": "whole step (K1 + query-block broadcasts + K2 + key gather + K3 + K4) over admissible pairs only"},
+               "cpu_baseline": cpu, "unverified_queries": int(out["unverified"]),
+               "peak_memory_gb_rank0": peak_mem / 1e9,
+               "accuracy": {"top1": float(hits[:, 0].sum()) / n, "top5": float(hits[:, 2].sum()) / n,
+                            "vote_acc": float(votes[:, 1].sum()) / n,
+                            "per_fold_top1": [float(hits[f, 0]) / max(float(sizes[f]), 1.0) for f in range(n_folds)]}}
+    barrier()
+    del data, out
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_c5(args):
+    import torch
+    import torch.distributed as dist
+    from emr2a_b200.engine import get_engine
+    world = int(os.environ.get("WORLD_SIZE", 1)); rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank); dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    eng = get_engine(dev)
+    n = int(os.environ.get("EMR2A_C5_N", WORKLOADS["c5"][0]))
+    rec = c5_record(args, eng, dev, world, rank, local_rank, n, max(1, args.steps), warm_full=args.warmup > 0,
+                    cpu_sample=0 if args.no_cpu_baseline else min(args.cpu_sample, 16))
+    if rank == 0:
+        emit(rec)
     if world > 1:
         dist.destroy_process_group()
 
@@ -318,8 +455,7 @@ def run_c1(args):
     from emr2a_b200 import native, synth
     from emr2a_b200.engine import get_engine
     from emr2a_b200.utils.cv_evaluator import CVRetrievalEvaluator
-    sys.path.insert(0, os.path.join(REPO, "oracle"))
-    import emr2a_oracle as oracle
+    oracle, _ = _oracle()
     torch.cuda.set_device(0)
     eng = get_engine()
     n, d, n_cls, k = 2000, 512, 3, 5
@@ -328,6 +464,7 @@ def run_c1(args):
     labels = synth.label_names(data["labels"], n_cls)
     emb = {pid: {"image": data["image"][j], "text": data["text"][j]} for j, pid in enumerate(ids)}
     ev = CVRetrievalEvaluator(cv_folds=5, pca_dim=128, top_k=k, seed=42)
+    ev.preprocess = "host"
     # processed arrays per fold (host, sklearn) -- shared by the device-resident leg and the CPU leg
     np.random.seed(0)
     t0 = time.perf_counter()
@@ -359,15 +496,21 @@ def run_c1(args):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     launches = eng.launches - l0
-    # e2e: the public run_cv
+    # e2e: the public run_cv, host preprocessing (the reference's own sklearn calls)
     np.random.seed(0)
     t0 = time.perf_counter()
     full = ev.run_cv(ids, labels, emb, fusion="concat", top_k_list=[1, 3, 5, 5])
     t_e2e = time.perf_counter() - t0
+    # the same public call as a user gets it by default (preprocess = "auto": scaler + exact PCA on the device
+    # wherever sklearn's own solver choice is deterministic; otherwise sklearn on the host)
+    ev_def = CVRetrievalEvaluator(cv_folds=5, pca_dim=128, top_k=k, seed=42)
+    t0 = time.perf_counter()
+    ev_def.run_cv(ids, labels, emb, fusion="concat", top_k_list=[1, 3, 5, 5])
+    t_e2e_default = time.perf_counter() - t0
     # the same public call with the per-fold scaler + PCA on the device (deterministic exact basis)
     ev_gpu = CVRetrievalEvaluator(cv_folds=5, pca_dim=128, top_k=k, seed=42)
     ev_gpu.preprocess = "gpu"
-    ev_gpu.run_cv(ids, labels, emb, fusion="concat", top_k_list=[1, 3, 5, 5])          # warm-up (cuSOLVER/cuBLAS handles)
+    ev_gpu.run_cv(ids, labels, emb, fusion="concat", top_k_list=[1, 3, 5, 5])          # warm-up (cuSOLVER handles)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     full_gpu = ev_gpu.run_cv(ids, labels, emb, fusion="concat", top_k_list=[1, 3, 5, 5])
@@ -394,13 +537,13 @@ def run_c1(args):
             "clocks": None, "gpu_launches": launches,
             "e2e": {"value": n / t_e2e, "unit": "queries/s", "seconds": t_e2e,
                     "h2d_bytes_per_step": int(sum(x.numel() * 4 for f in dev for x in f)), "d2h_bytes_per_step": n * k * 16,
-                    "api": "CVRetrievalEvaluator.run_cv (host StratifiedKFold + StandardScaler + PCA as in the reference, "
-                           f"~{t_prep:.2f} s; GPU hot path; python list outputs)",
+                    "api": "CVRetrievalEvaluator.run_cv, preprocess='host' (StratifiedKFold + StandardScaler + PCA by sklearn "
+                           f"as in the reference, ~{t_prep:.2f} s; GPU hot path; python list outputs)",
                     "api_hot_path_seconds": t_api, "api_hot_path_qps": n / t_api,
+                    "default_preprocess": {"mode": ev_def.preprocess, "value": n / t_e2e_default, "seconds": t_e2e_default},
                     "gpu_preprocess": {"value": n / t_e2e_gpu, "unit": "queries/s", "seconds": t_e2e_gpu,
                                        "api": "CVRetrievalEvaluator.run_cv with preprocess='gpu' (StandardScaler + exact "
-                                              "PCA on the device: emr2a_column_moments / emr2a_standardize + float64 "
-                                              "covariance/eigh), python list outputs",
+                                              "PCA on the device), python list outputs",
                                        "top1": float(np.mean([r["top1"] for r in full_gpu["fold_results"]])),
                                        "vote_acc": float(np.mean([r["vote_acc"] for r in full_gpu["fold_results"]]))}},
             "roofline": None,
@@ -465,23 +608,20 @@ def main():
     q_weights = (1.0, 1.0)
     in_dtype = torch.float32
     if args.workload == "c3":                              # late fusion: unit modalities, weights folded into the queries
-        w_text = 0.25
         flags = native.NF_SEGNORM
-        q_weights = (np.float32(1 - w_text), np.float32(w_text))
+        q_weights = (np.float32(1 - C3_W_TEXT), np.float32(C3_W_TEXT))
     if args.workload == "c4":
         in_dtype = torch.bfloat16
     k_list = [1, 3, 5, k]
 
     # ---- synthetic inputs, generated on the device (per shard; same rows for any N) ----
-    db_img, _ = synth.device_block(lo, hi - lo, d_img, n_cls, seed, dev, label_seed=seed)
-    db_txt, _ = synth.device_block(lo, hi - lo, d_txt, n_cls, seed + 1, dev, label_seed=seed)
+    gen_dt = None if in_dtype == torch.float32 else in_dtype
+    db_img, _ = synth.device_block(lo, hi - lo, d_img, n_cls, seed, dev, label_seed=seed, dtype=gen_dt)
+    db_txt, _ = synth.device_block(lo, hi - lo, d_txt, n_cls, seed + 1, dev, label_seed=seed, dtype=gen_dt)
     # labels must be global (the vote gathers labels by global row index)
     db_labels = synth.device_labels(0, n_db, n_cls, seed, dev)
-    q_row0 = 50_003_968
-    q_img, q_labels = synth.device_block(q_row0, n_q, d_img, n_cls, seed, dev, label_seed=seed)
-    q_txt, _ = synth.device_block(q_row0, n_q, d_txt, n_cls, seed + 1, dev, label_seed=seed)
-    if in_dtype != torch.float32:
-        db_img, db_txt, q_img, q_txt = (t.to(in_dtype) for t in (db_img, db_txt, q_img, q_txt))
+    q_img, q_labels = synth.device_block(Q_ROW0, n_q, d_img, n_cls, seed, dev, label_seed=seed, dtype=gen_dt)
+    q_txt, _ = synth.device_block(Q_ROW0, n_q, d_txt, n_cls, seed + 1, dev, label_seed=seed, dtype=gen_dt)
     torch.cuda.synchronize()
 
     timers = {"k2_start": torch.cuda.Event(enable_timing=True), "k2_end": torch.cuda.Event(enable_timing=True)}
@@ -593,24 +733,23 @@ def main():
             r_ms = (time.perf_counter() - t0) / e_steps * 1e3
             assert torch.equal(lists[0], res["top_idx"].cpu())
             e2e["resident_index"] = {"value": n_q / (r_ms / 1e3), "unit": "queries/s", "ms_per_step": r_ms,
-                                     "h2d_bytes_per_step": int(hq_img.numel() * 4 + hq_txt.numel() * 4 + hq_lab.numel() * 4),
+                                     "h2d_bytes_per_step": int(hq_img.numel() * hq_img.element_size() + hq_txt.numel() * hq_txt.element_size()
+                                                               + hq_lab.numel() * 4),
                                      "api": "Engine.build_index once + DatabaseIndex.search per step (queries from pinned host memory)"}
             del index
 
-    clocks = sampler.stop(windows) if rank == 0 else None
+    clocks = sampler.summary(windows) if rank == 0 else None
 
     # ---- roofline of the dominant kernel (K2, tensor pipe) ----
     pk = peaks()
     flops = 2.0 * dim * n_q * (hi - lo)
     passes = {"bf16x3": 3, "bf16x1": 1, "fp32": 1, "rescore": 1}[res["precision"]]
     achieved = flops / (k2_avg_ms / 1e3) / 1e12
-    # DRAM bytes of the dominant kernel (tc2_topk_kernel<1,16,0>, full 1M-row shard) from the committed ncu
-    # --set full capture profiles/r01_ncu_step_c2_head.md: 3.418 GB read + 0.036 GB written per launch
-    # (algorithmic: 2.05 GB bf16 database plane + 20 MB query plane + 31 MB partial lists).
-    traffic = 3.453e9 if (res["precision"] == "rescore" and world == 1 and args.workload == "c2") else None
+    traffic, traffic_src = k2_traffic(args.workload, res["precision"], world)
     t_peak, t_src = tensor_peak(pk, ms_per_step * (args.steps + max(args.warmup, 3)) / 1e3)
     roofline = {"bound": "tensor", "achieved": achieved, "peak": t_peak, "unit": "TFLOP/s",
                 "frac": achieved / t_peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
+                "traffic_source": traffic_src,
                 "peak_source": pk["src"] + " " + t_src,
                 "frac_of_burst": achieved / pk["tflops_burst"], "frac_of_sustained": achieved / pk["tflops"],
                 "kernel": "emr2a_topk_search = tc2_topk_kernel (tcgen05 cta_group::2, TMA, fused Top-K) + K3 merge of partial lists"
@@ -619,19 +758,19 @@ def main():
                 "issued_tflops": achieved * passes, "issued_frac": achieved * passes / t_peak,
                 "share_of_step": k2_avg_ms / ms_per_step}
 
-    # ---- CPU baseline + parity on the sample (rank 0, N = 1) ----
+    # ---- CPU baseline + parity on the sample (rank 0, N = 1): the reference loop against ALL database rows ----
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload in ("c2", "c2k5", "small"):
-        cpu, pick, ref = cpu_reference_leg(db_img.cpu().numpy(), db_txt.cpu().numpy(), q_img.cpu().numpy(),
-                                           q_txt.cpu().numpy(), db_labels.cpu().numpy(), q_labels.cpu().numpy(),
-                                           k, args.cpu_sample, n_q)
-        got_idx = res["top_idx"].cpu().numpy()[pick]
-        got_sc = res["top_scores"].cpu().numpy()[pick]
-        same_rows = float(np.mean(np.all(got_idx == ref["top_idx"], axis=1)))
-        cpu["parity_on_sample"] = {"topk_rows_identical": same_rows,
-                                   "vote_identical": float(np.mean(res["pred_vote"].cpu().numpy()[pick] == ref["pred_vote"])),
-                                   "weighted_vote_identical": float(np.mean(res["pred_weighted"].cpu().numpy()[pick] == ref["pred_weighted"]))}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        _, feed = _oracle()
+        pick = torch.linspace(0, n_q - 1, min(args.cpu_sample, n_q), device=dev).long()
+        got = {nm: res[nm][pick].cpu().numpy() for nm in ("top_idx", "top_scores", "pred_vote", "pred_weighted")}
+        wide = args.workload == "c4"
+        cpu, _ = cpu_sample_leg("late" if args.workload == "c3" else "concat", k, n_db, feed.device_fetcher(db_img, db_txt),
+                                q_img[pick].float().cpu().numpy(), q_txt[pick].float().cpu().numpy(),
+                                db_labels.cpu().numpy(), q_labels[pick].cpu().numpy(), n_q, w_text=C3_W_TEXT,
+                                chunk_rows=16384 if wide else 65536, timed_rows=32768 if wide else 131072, got=got)
 
+    line = None
     if rank == 0:
         hits = res["hit_counts"][0].cpu().numpy()
         line = {"metric": "queries/sec (cosine Top-K + vote)", "value": qps, "unit": "queries/s", "n_gpus": world,
@@ -639,10 +778,7 @@ def main():
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": {"bf16x3": "bf16x3", "bf16x1": "bf16", "fp32": "f32", "rescore": "bf16+f32"}[res["precision"]],
                 "data": "synthetic",
-                "config": {"workload": f"{args.workload}: {n_db}-case database, {d_img}+{d_txt}-d "
-                                       + ("late fusion (w_text=0.25, merge-then-Top-K)" if args.workload == "c3" else "concat fusion")
-                                       + (" (bf16 in)" if in_dtype != torch.float32 else " (fp32 in)")
-                                       + f", {n_q} queries, K={k}, {n_cls} classes",
+                "config": {"workload": workload_string(args.workload),
                            "parallelism": f"database row-sharded x{world}, NCCL all-gather of local Top-K" if world > 1 else "single GPU",
                            "arithmetic": {"bf16x3": "tcgen05 bf16 2-way split (hi*lo + lo*hi + hi*hi), fp32 accumulate",
                                           "bf16x1": "tcgen05 bf16 operands, fp32 accumulate", "fp32": "CUDA-core fp32 FMA",
@@ -654,6 +790,17 @@ def main():
                 "unverified_queries": int(unverified_total),
                 "accuracy": {"top1": float(hits[0]) / n_q, f"top{k}": float(hits[3]) / n_q,
                              "vote_acc": float(res["vote_counts"][0, 1]) / n_q}}
+
+    # ---- N > 1: BASELINE.json configs[4] on all N GPUs next to the C2 headline ----
+    if world > 1 and args.workload == "c2" and not args.no_c5 and os.environ.get("EMR2A_BENCH_C5", "1") != "0":
+        del db_img, db_txt, res
+        torch.cuda.empty_cache()
+        rec = c5_record(args, eng, dev, world, rank, local_rank, c5_rows_for(world), 1, warm_full=False,
+                        cpu_sample=0 if args.no_cpu_baseline else min(args.cpu_sample, 16))
+        if rank == 0:
+            line["c5"] = rec
+    if rank == 0:
+        sampler.stop()
         emit(line)
     if world > 1:
         dist.destroy_process_group()

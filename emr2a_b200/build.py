@@ -35,14 +35,34 @@ def _stamp() -> str:
     return h.hexdigest()
 
 
+def _up_to_date(stamp_file: str, stamp: str) -> bool:
+    if os.path.exists(OUT) and os.path.exists(stamp_file):
+        with open(stamp_file) as fh:
+            return fh.read().strip() == stamp
+    return False
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile + link if a source changed since the library was linked.  Safe under ``torchrun``: the ranks of one
+    node serialise on a file lock (the first one builds, the others find the stamp up to date), the library is linked
+    under a temporary name and moved into place atomically, and the stamp is written last."""
+    import fcntl
     stamp_file = os.path.join(OBJ, "stamp")
     stamp = _stamp()
-    if not force and os.path.exists(OUT) and os.path.exists(stamp_file):
-        with open(stamp_file) as fh:
-            if fh.read().strip() == stamp:
-                return OUT
+    if not force and _up_to_date(stamp_file, stamp):
+        return OUT
     os.makedirs(OBJ, exist_ok=True)
+    with open(os.path.join(OBJ, "lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and _up_to_date(stamp_file, stamp):      # another rank built it while this one waited
+                return OUT
+            return _build_locked(stamp_file, stamp, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(stamp_file: str, stamp: str, verbose: bool) -> str:
 
     def compile_one(src: str) -> str:
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
@@ -58,12 +78,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    r = subprocess.run([NVCC, "-shared", "-o", OUT, *objs, "-gencode", "arch=compute_100a,code=sm_100a"],
+    tmp_out = f"{OUT}.{os.getpid()}.tmp"
+    r = subprocess.run([NVCC, "-shared", "-o", tmp_out, *objs, "-gencode", "arch=compute_100a,code=sm_100a"],
                        capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    with open(stamp_file, "w") as fh:
+    os.replace(tmp_out, OUT)                       # a process that dlopens concurrently sees the old or the new file, never half of one
+    with open(stamp_file + ".tmp", "w") as fh:
         fh.write(stamp)
+    os.replace(stamp_file + ".tmp", stamp_file)
     return OUT
 
 

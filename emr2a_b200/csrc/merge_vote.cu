@@ -286,6 +286,30 @@ extern "C" int emr2a_topk_merge(const uint64_t* keys_in, int parts, int64_t Q, i
   return EMR2A_OK;
 }
 
+namespace emr2a {
+__global__ void __launch_bounds__(256) keys_map_rows_kernel(uint64_t* __restrict__ keys, int64_t total,
+                                                            const uint32_t* __restrict__ row_ids, int64_t n_rows,
+                                                            int64_t idx_base) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const uint64_t k = keys[i];
+  if (k == 0ull) return;
+  const int64_t local = static_cast<int64_t>(key_index(k)) - idx_base;
+  if (local < 0 || local >= n_rows) return;                  // not an index of this shard: left as it is
+  keys[i] = (k & 0xFFFFFFFF00000000ull) | static_cast<uint64_t>(0xFFFFFFFFu - row_ids[local]);
+}
+}  // namespace emr2a
+
+extern "C" int emr2a_keys_map_rows(uint64_t* keys, int64_t n_keys, const uint32_t* row_ids, int64_t n_rows,
+                                   int64_t idx_base, void* stream) {
+  if (!keys || !row_ids || n_keys < 0 || n_rows < 0 || idx_base < 0) return fail(EMR2A_ERR_INVALID, "keys_map_rows: bad arguments");
+  if (n_keys == 0) return EMR2A_OK;
+  keys_map_rows_kernel<<<static_cast<unsigned>((n_keys + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      keys, n_keys, row_ids, n_rows, idx_base);
+  EMR2A_LAUNCH_CHECK("keys_map_rows_kernel");
+  return EMR2A_OK;
+}
+
 extern "C" int emr2a_vote_metrics(const uint64_t* keys, int64_t Q, int K, const int32_t* db_labels,
                                   int64_t label_base, const int32_t* q_labels, const uint8_t* q_group,
                                   int n_groups, int C, const int32_t* k_list, int nk, int wacc_f32,

@@ -5,10 +5,12 @@ inside the keys, and ties break on the global index, so results are bit-identica
 GPU count."""
 from __future__ import annotations
 
-from typing import Dict, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
+
+from .engine import Operand
 
 
 def shard_range(n_rows: int, rank: int, world: int, align: int = 256) -> Tuple[int, int]:
@@ -85,29 +87,76 @@ def sharded_search_and_vote(eng, db_segs_local: Sequence, q_segs: Sequence, db_l
     return res
 
 
+def fold_balanced_ranges(fold_counts: Sequence[int], rank: int, world: int, align: int = 256) -> List[Tuple[int, int]]:
+    """Rows of ``rank`` in a FOLD-BALANCED sharding of a fold-ordered cohort ("each shard holds
+    ~N/(5G) rows of every fold so fold-skipping stays balanced"): every fold's row range is cut into ``world``
+    contiguous, ``align``-row-aligned pieces and rank r takes piece r of every fold.  Returns [(first global row,
+    count)] per fold, ascending.  With such shards every rank has the same amount of admissible work for ANY query
+    block (it skips its piece of the block's own fold), so the per-block exchange of query rows costs no waiting."""
+    out, start = [], 0
+    for n_f in fold_counts:
+        n_f = int(n_f)
+        per = (n_f + world - 1) // world
+        per = (per + align - 1) // align * align
+        lo = min(rank * per, n_f)
+        hi = min(lo + per, n_f)
+        out.append((start + lo, hi - lo))
+        start += n_f
+    return out
+
+
+def ranges_to_rows(ranges: Sequence[Tuple[int, int]], device) -> torch.Tensor:
+    parts = [torch.arange(g0, g0 + cnt, dtype=torch.int32, device=device) for g0, cnt in ranges if cnt > 0]
+    return torch.cat(parts) if parts else torch.empty((0,), dtype=torch.int32, device=device)
+
+
+def _gather_varlen(t: torch.Tensor, world: int) -> List[torch.Tensor]:
+    """All-gather 1-D / 2-D tensors whose first dimension differs per rank."""
+    if world == 1:
+        return [t]
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(x.item()) for x in sizes]
+    cap = max(max(sizes), 1)
+    pad = torch.zeros((cap,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[:t.shape[0]] = t
+    out = torch.empty((world, cap) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    if t.is_cuda:
+        dist.all_gather_into_tensor(out.view(-1), pad.view(-1))
+    else:
+        dist.all_gather([out[r] for r in range(world)], pad)
+    return [out[r, :sizes[r]] for r in range(world)]
+
+
 def sharded_cv_search_and_vote(eng, segs_local: Sequence, labels_global, folds_global, n_classes: int, k: int,
                                row_offset: int, flags: int, q_weights=(1.0, 1.0), k_list=(1, 3, 5),
                                precision: str = "auto", n_folds: Optional[int] = None, q_block: int = 262144,
                                fold_sorted: bool = True, want_lists: bool = False,
-                               full_segs: Optional[Sequence] = None) -> Dict[str, torch.Tensor]:
+                               full_segs: Optional[Sequence] = None, row_ids=None) -> Dict[str, torch.Tensor]:
     """The whole CV loop over a row-sharded cohort: EVERY case is a query against the cases of the OTHER folds
-    (utils/cv_evaluator.py:349-376 builds exactly these train/test pairs, one fold at a time), database rows
-    sharded over the ranks (``segs_local`` = this rank's rows ``[row_offset, row_offset + n_local)`` of every
-    modality; shards as ``shard_range`` cuts them: equal, 256-aligned, the last one shorter).
+    (utils/cv_evaluator.py:349-376 builds exactly these train/test pairs, one fold at a time).  The rows are sharded
+    over the ranks: ``segs_local`` = this rank's rows of every modality, ``row_ids`` (int32, ascending) their global
+    indices -- or the contiguous range ``[row_offset, row_offset + n_local)`` when ``row_ids`` is None.  Shards that
+    hold an equal slice of every fold (``fold_balanced_ranges``) keep all ranks equally busy on every query block.
 
-    Every rank needs every case as a query, so the raw rows are all-gathered ONCE over NVLink; after that each
-    rank searches all query blocks against its own shard without communication, and only the local Top-K keys
-    are exchanged (one all-gather + K3 merge per block) before K4 votes with per-fold counters.  A collective per
-    query block would make ranks whose shard lies in the block's own fold (nothing to do: all tiles skipped) wait
-    for the others.  ``fold_sorted`` promises ``folds_global`` is non-decreasing (rows in fold order) so whole
-    tiles of a single fold are skipped; pass False for arbitrary fold vectors (per-element mask only).
-
-    ``full_segs``: the rows of ALL cases, if this rank already holds them (then nothing is all-gathered).
+    Data movement (queries ARE database rows, so nothing is prepared twice and nothing is replicated):
+      1. every rank runs K1 ONCE on its own shard (fp32 rows and/or bf16 planes, as the precision arm needs);
+      2. query blocks are walked owner by owner; the owner's PREPARED rows of the block are broadcast to the other
+         ranks over NVLink (NCCL broadcast, double-buffered: block b+1 travels while block b is searched), so a rank
+         holds its shard plus two query blocks -- never the cohort;
+      3. each rank searches the block against its shard (fold rule: own-fold tiles skipped / masked), global row ids
+         go into the keys (``emr2a_keys_map_rows``);
+      4. the local Top-K keys are all-gathered, merged by K3, and K4 votes with per-fold counters.
+    ``fold_sorted`` promises ``folds_global`` is non-decreasing (rows in fold order) so whole tiles of a single fold
+    are skipped; pass False for arbitrary fold vectors (per-element mask only).  ``full_segs`` is accepted for
+    backward compatibility and ignored.
 
     Returns per-fold counters (``hit_counts [F, nk]``, ``vote_counts [F, 3]``, ``confusion [F, 2, C, C]``,
-    ``group_sizes [F]``), ``unverified`` and, with ``want_lists``, the per-query outputs of all N cases
-    (identical on every rank).  Results are bit-identical for every GPU count."""
+    ``group_sizes [F]``), ``unverified`` and, with ``want_lists``, the per-query outputs of all N cases in global row
+    order (identical on every rank).  Results are bit-identical for every GPU count and every sharding."""
     world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
     dev = eng.device
     mats = [eng._embedding(x)[0] for x in segs_local if x is not None]
     n_local = int(mats[0].shape[0])
@@ -118,44 +167,74 @@ def sharded_cv_search_and_vote(eng, segs_local: Sequence, labels_global, folds_g
         n_folds = int(folds.max().item()) + 1 if n else 1
     dim = sum(int(m.shape[1]) for m in mats)
     prec = eng.pick_precision(n, n, dim, k, precision)
-    # (1) one all-gather of the raw rows (equal-sized, zero-padded shards)
-    if full_segs is not None:
-        full = [eng._embedding(x)[0] for x in full_segs if x is not None]
-    elif world > 1:
-        per = shard_range(n, 0, world)[1]
-        full = []
-        for m in mats:
-            buf = torch.empty((world * per, int(m.shape[1])), dtype=m.dtype, device=dev)
-            src = m
-            if n_local < per:
-                src = torch.zeros((per, int(m.shape[1])), dtype=m.dtype, device=dev)
-                src[:n_local] = m
-            dist.all_gather_into_tensor(buf, src.contiguous())
-            full.append(buf)
+    contiguous = row_ids is None
+    if contiguous:
+        my_rows = torch.arange(row_offset, row_offset + n_local, dtype=torch.int32, device=dev)
     else:
-        full = mats
-    # (2) local work, no communication
+        my_rows = eng.to_device(row_ids, torch.int32)
+        if int(my_rows.shape[0]) != n_local:
+            raise ValueError(f"sharded_cv_search_and_vote: {int(my_rows.shape[0])} row ids for {n_local} local rows")
+    rows_of = _gather_varlen(my_rows, world)                   # every rank's global row ids
+    # (1) K1 once per rank
     seg1 = mats[1] if len(mats) > 1 else None
     db = eng.prepare(mats[0], seg1, 1.0, 1.0, flags, prec)
-    db_fold = folds[row_offset:row_offset + n_local]
+    same_q = float(q_weights[0]) == 1.0 and float(q_weights[1]) == 1.0
+    qsrc = db if same_q else eng.prepare(mats[0], seg1, q_weights[0], q_weights[1], flags, prec)
+    planes = [nm for nm in ("f32", "hi", "lo") if getattr(db, nm) is not None]
+    q_stats = None
+    if qsrc.stats is not None:                                 # the owner's maxima are valid clamps for its rows
+        q_stats = torch.stack(_gather_varlen(qsrc.stats.reshape(1, 2), world)).reshape(world, 2) if world > 1 \
+            else qsrc.stats.reshape(1, 2)
+    db_fold = folds[my_rows.long()]
+    db_ids = None if contiguous else my_rows
+    blocks = [(r, b0, min(b0 + q_block, int(rows_of[r].shape[0])))
+              for r in range(world) for b0 in range(0, int(rows_of[r].shape[0]), q_block)]
+    bufs = [None, None]
+    if world > 1:
+        cap = min(q_block, max(int(x.shape[0]) for x in rows_of))
+        bufs = [{nm: torch.empty((cap, int(getattr(db, nm).shape[1])), dtype=getattr(db, nm).dtype, device=dev)
+                 for nm in planes} for _ in range(2)]
+
+    def post(i):
+        """Start the broadcast of block i's prepared rows from its owner (asynchronous, NCCL's own stream)."""
+        r, b0, b1 = blocks[i]
+        if world == 1:
+            return []
+        works = []
+        for nm in planes:
+            t = getattr(qsrc, nm)[b0:b1] if r == rank else bufs[i % 2][nm][:b1 - b0]
+            works.append(dist.broadcast(t, src=r, async_op=True))
+        return works
+
+    # (2)+(3) local searches, block b+1 in flight while block b is searched
     local = []
-    for b0 in range(0, n, q_block):
-        b1 = min(b0 + q_block, n)
-        qs = eng.prepare(full[0][b0:b1], full[1][b0:b1] if len(full) > 1 else None, q_weights[0], q_weights[1], flags, prec)
-        local.append(eng.topk_search(qs, db, k, prec, q_fold=folds[b0:b1], db_fold=db_fold, fold_sorted=fold_sorted,
-                                     idx_base=row_offset))
-    # (3) exchange + merge + vote
+    pending = post(0) if blocks else []
+    for i, (r, b0, b1) in enumerate(blocks):
+        nxt = post(i + 1) if i + 1 < len(blocks) else []
+        for w in pending:
+            w.wait()
+        pending = nxt
+        src = qsrc if r == rank else None
+        qs = Operand(n=b1 - b0, dim=dim,
+                     f32=(src.f32[b0:b1] if src is not None else bufs[i % 2]["f32"][:b1 - b0]) if "f32" in planes else None,
+                     hi=(src.hi[b0:b1] if src is not None else bufs[i % 2]["hi"][:b1 - b0]) if "hi" in planes else None,
+                     lo=(src.lo[b0:b1] if src is not None else bufs[i % 2]["lo"][:b1 - b0]) if "lo" in planes else None,
+                     stats=None if q_stats is None else q_stats[r])
+        q_rows = rows_of[r][b0:b1].long()
+        local.append(eng.topk_search(qs, db, k, prec, q_fold=folds[q_rows], db_fold=db_fold, fold_sorted=fold_sorted,
+                                     idx_base=row_offset if contiguous else 0, row_ids=db_ids))
+    # (4) exchange + merge + vote
     outs = []
-    for i, b0 in enumerate(range(0, n, q_block)):
-        b1 = min(b0 + q_block, n)
+    for i, (r, b0, b1) in enumerate(blocks):
         keys = local[i]
         if world > 1:
             keys = eng.topk_merge(gather_keys(keys), k)
-        outs.append(eng.vote_metrics(keys, labels, labels[b0:b1], n_classes, k_list=k_list, q_group=folds[b0:b1],
+        q_rows = rows_of[r][b0:b1].long()
+        outs.append(eng.vote_metrics(keys, labels, labels[q_rows], n_classes, k_list=k_list, q_group=folds[q_rows],
                                      n_groups=n_folds, per_query=want_lists, want_lists=want_lists))
         local[i] = None
     unverified = 0
-    if prec == "rescore":
+    if prec == "rescore" and blocks:
         st = eng.pop_status_tensor()
         if world > 1:
             st = st.to(torch.int64)
@@ -164,14 +243,18 @@ def sharded_cv_search_and_vote(eng, segs_local: Sequence, labels_global, folds_g
         if int(st[1]):
             return sharded_cv_search_and_vote(eng, segs_local, labels_global, folds_global, n_classes, k, row_offset,
                                               flags, q_weights, k_list, "bf16x3", n_folds, q_block, fold_sorted, want_lists,
-                                              full_segs)
+                                              None, row_ids)
         unverified = int(st[0])
     res: Dict[str, torch.Tensor] = {}
     for name in ("hit_counts", "vote_counts", "confusion", "group_sizes"):
-        res[name] = torch.stack([o[name] for o in outs]).sum(dim=0)
-    if want_lists:
+        res[name] = torch.stack([o[name] for o in outs]).sum(dim=0) if outs else None
+    if want_lists and outs:
+        order = torch.cat([rows_of[r][b0:b1] for r, b0, b1 in blocks]).long()      # global row of every block position
         for name in ("top_idx", "top_scores", "top_labels", "pred_top1", "pred_vote", "pred_weighted"):
-            res[name] = torch.cat([o[name] for o in outs])
+            cat = torch.cat([o[name] for o in outs])
+            out = torch.empty_like(cat)
+            out[order] = cat
+            res[name] = out
     res["precision"] = prec
     res["unverified"] = unverified          # this rank's count (max over ranks when sharded)
     return res

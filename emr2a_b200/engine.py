@@ -239,8 +239,10 @@ class Engine:
 
     def topk_search(self, q: Operand, db: Operand, k: int, precision: str = "fp32",
                     q_fold: Optional[torch.Tensor] = None, db_fold: Optional[torch.Tensor] = None,
-                    fold_sorted: bool = False, idx_base: int = 0) -> torch.Tensor:
-        """Packed Top-K keys [Q, k] (int64 storage of the uint64 keys), best first."""
+                    fold_sorted: bool = False, idx_base: int = 0, row_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Packed Top-K keys [Q, k] (int64 storage of the uint64 keys), best first.  ``row_ids`` (int32 [N],
+        ASCENDING): global index of every database row of this operand, for shards that are not one contiguous
+        range (``emr2a_keys_map_rows``); default: ``idx_base + local row``."""
         if q.dim != db.dim:
             raise ValueError(f"topk_search: query dim {q.dim} != database dim {db.dim}")
         prec = _PREC[precision]
@@ -281,6 +283,14 @@ class Engine:
         self.launches += 2 if status is None else 6
         if status is not None:
             self._status_log.append(status)
+        if row_ids is not None:
+            row_ids = self.to_device(row_ids, torch.int32)
+            if int(row_ids.shape[0]) != N:
+                raise ValueError(f"topk_search: row_ids has {int(row_ids.shape[0])} entries for {N} database rows")
+            with torch.cuda.device(self.device):
+                native.check(self.lib.emr2a_keys_map_rows(keys.data_ptr(), Q * k, row_ids.data_ptr(), N, int(idx_base),
+                                                          self._stream()))
+            self.launches += 1
         return keys
 
     def pop_status_tensor(self) -> Optional[torch.Tensor]:
@@ -441,9 +451,10 @@ class Engine:
         per fold (``hit_counts[f]``, ``vote_counts[f]``, ``confusion[f]``, ``group_sizes[f]``).
         Equals the reference's per-fold evaluation whenever the preprocessing does not depend on
         the fold (the rows passed in are the processed embeddings).
-        ``distributed`` (default: automatic): under ``torchrun`` with an NCCL process group, when every rank
-        calls this with the same arrays, each rank searches against its own shard of the rows and the Top-K
-        lists are exchanged over NCCL -- same results, bit for bit, in 1/world of the time."""
+        ``distributed=True`` (or ``EMR2A_CV_DISTRIBUTED=1`` with the default ``None``): under ``torchrun`` with an
+        NCCL process group, when every rank calls this with the same arrays (verified with a checksum), each rank
+        searches against its own fold-balanced shard of the rows and the Top-K lists are exchanged over NCCL --
+        same results, bit for bit, in 1/world of the time."""
         folds_t = self.to_device(folds, torch.uint8)
         n = int(folds_t.shape[0])
         if n_folds is None:
@@ -461,16 +472,30 @@ class Engine:
         prec = self.pick_precision(n, n, dim, k, precision)
         import torch.distributed as tdist
         if distributed is None:
-            distributed = (tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1
-                           and tdist.get_backend() == "nccl" and n >= 256 * tdist.get_world_size())
+            # sharding is opt-in: an NCCL group alone does not say that every rank holds the same cohort (ordinary
+            # data-parallel callers pass different data per rank).  EMR2A_CV_DISTRIBUTED=1 turns the automatic mode on.
+            distributed = (os.environ.get("EMR2A_CV_DISTRIBUTED") == "1" and tdist.is_available() and tdist.is_initialized()
+                           and tdist.get_world_size() > 1 and tdist.get_backend() == "nccl")
         if distributed:
             # one process per GPU (torchrun), every rank called with the same arrays: this rank searches all queries
-            # against ITS shard of the fold-ordered rows, Top-K lists are exchanged over NCCL (emr2a_b200/dist.py)
-            from .dist import shard_range, sharded_cv_search_and_vote
-            lo, hi = shard_range(n, tdist.get_rank(), tdist.get_world_size())
-            res = sharded_cv_search_and_vote(self, [m[lo:hi] for m in mats], labels_t, folds_t, n_classes, k, lo, flags,
-                                             q_weights, k_list, prec, n_folds, min(q_block, 1 << 18), True, want_lists,
-                                             full_segs=mats)
+            # against ITS fold-balanced shard of the fold-ordered rows, query blocks travel from their owners and the
+            # Top-K lists are exchanged over NCCL (emr2a_b200/dist.py)
+            from .dist import fold_balanced_ranges, ranges_to_rows, sharded_cv_search_and_vote
+            world, rank = tdist.get_world_size(), tdist.get_rank()
+            # cheap guard against ranks that were handed different cohorts: (n, fold / label checksums) must agree
+            sig = torch.stack([torch.tensor(float(n), device=self.device, dtype=torch.float64),
+                               folds_t.double().sum(), (labels_t.double() * (torch.arange(n, device=self.device) % 8191 + 1)).sum()])
+            lo_sig, hi_sig = sig.clone(), sig.clone()
+            tdist.all_reduce(lo_sig, op=tdist.ReduceOp.MIN)
+            tdist.all_reduce(hi_sig, op=tdist.ReduceOp.MAX)
+            if not torch.equal(lo_sig, hi_sig):
+                raise ValueError("cv_search_and_vote(distributed=True): the ranks were called with different cohorts "
+                                 "(row count / fold / label checksums differ); every rank must pass the same arrays")
+            counts = torch.bincount(folds_t.long(), minlength=n_folds).cpu().tolist()
+            rows = ranges_to_rows(fold_balanced_ranges(counts, rank, world), self.device)
+            res = sharded_cv_search_and_vote(self, [m.index_select(0, rows.long()) for m in mats], labels_t, folds_t,
+                                             n_classes, k, 0, flags, q_weights, k_list, prec, n_folds,
+                                             min(q_block, 1 << 18), True, want_lists, None, rows)
             return self._cv_unpermute(res, perm, want_lists)
         seg1 = mats[1] if len(mats) > 1 else None
         db = self.prepare(mats[0], seg1, 1.0, 1.0, flags, prec)

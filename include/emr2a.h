@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define EMR2A_ABI_VERSION 7
+#define EMR2A_ABI_VERSION 8
 
 enum emr2a_status {
   EMR2A_OK = 0,
@@ -181,6 +181,18 @@ int emr2a_topk_search(const float* q_f32, int64_t ldq_f32,
 int emr2a_topk_merge(const uint64_t* keys_in, int parts, int64_t Q, int K_in,
                      int64_t part_stride, int64_t q_stride, int K_out,
                      uint64_t* keys_out, void* stream);
+
+/*
+ * Row-id mapping for shards that are not one contiguous range of the database (fold-balanced shards of the
+ * all-queries CV, SURVEY 8e: "each shard holds ~N/(5G) rows of every fold"): K2 numbers the rows of the operand it is
+ * given as idx_base + local row; this rewrites the index field of every non-empty key to row_ids[index - idx_base]
+ * (scores untouched).  row_ids must be ASCENDING in the local row order so that the tie rule (score descending,
+ * GLOBAL index ascending) -- and with it the order inside every list -- is preserved; then sharded results stay
+ * bit-identical to the single-GPU ones.  The reference's equivalent is the train_ids list that turns a position in
+ * the fold's train matrix back into a patient (utils/cv_evaluator.py:124-129, 366-371).
+ */
+int emr2a_keys_map_rows(uint64_t* keys, int64_t n_keys, const uint32_t* row_ids, int64_t n_rows,
+                        int64_t idx_base, void* stream);
 
 /*
  * K4 -- unpack Top-K, gather labels, vote and count.

@@ -72,11 +72,6 @@ def test_gather_and_merge_world2():
 # dist.sharded_cv_search_and_vote (the multi-GPU all-queries CV, BASELINE config 5) under gloo with a numpy stand-in
 # for the CUDA engine: checks the host-side plumbing -- shard padding and the all-gather of the raw rows, row
 # offsets / global indices, fold slices per query block, key exchange and merge order, per-fold counters.
-class _Rows:
-    def __init__(self, mat):
-        self.mat, self.n = mat, mat.shape[0]
-
-
 class _StubEngine:
     device = torch.device("cpu")
     launches = 0
@@ -94,17 +89,20 @@ class _StubEngine:
     def prepare(self, s0, s1, w0, w1, flags, prec):
         mats = [np.asarray(s0, dtype=np.float32) * np.float32(w0)] + ([np.asarray(s1, dtype=np.float32) * np.float32(w1)] if s1 is not None else [])
         rows = np.concatenate(mats, axis=1)
-        return _Rows(rows / (np.linalg.norm(rows, axis=1, keepdims=True) + 1e-8))
+        from emr2a_b200.engine import Operand
+        rows = rows / (np.linalg.norm(rows, axis=1, keepdims=True) + 1e-8)
+        return Operand(n=rows.shape[0], dim=rows.shape[1], f32=torch.from_numpy(np.ascontiguousarray(rows, dtype=np.float32)))
 
-    def topk_search(self, qs, db, k, prec, q_fold=None, db_fold=None, fold_sorted=False, idx_base=0):
-        sc = (qs.mat.astype(np.float64) @ db.mat.astype(np.float64).T).astype(np.float32)
+    def topk_search(self, qs, db, k, prec, q_fold=None, db_fold=None, fold_sorted=False, idx_base=0, row_ids=None):
+        sc = (qs.f32.numpy().astype(np.float64) @ db.f32.numpy().astype(np.float64).T).astype(np.float32)
         if q_fold is not None:
             sc = np.where(q_fold.numpy()[:, None] == db_fold.numpy()[None, :], -np.inf, sc)
         kk = min(k, sc.shape[1])
         order = np.argsort(-sc, axis=1, kind="stable")[:, :kk]
         top = np.take_along_axis(sc, order, axis=1)
         keys = np.zeros((sc.shape[0], k), dtype=np.int64)
-        keys[:, :kk] = np.where(np.isfinite(top), _pack(top, order + idx_base), 0)
+        gidx = order + idx_base if row_ids is None else row_ids.numpy().astype(np.int64)[order]
+        keys[:, :kk] = np.where(np.isfinite(top), _pack(top, gidx), 0)
         return torch.from_numpy(keys)
 
     def topk_merge(self, parts, k):
@@ -144,21 +142,47 @@ def _cv_case():
     return a, b, labels, folds, n_folds
 
 
-def _cv_run(world, rank):
-    from emr2a_b200.dist import shard_range, sharded_cv_search_and_vote
+def _cv_run(world, rank, balanced=False):
+    """contiguous shards (row_offset) or fold-balanced shards (row_ids: a slice of every fold per rank)"""
+    from emr2a_b200.dist import fold_balanced_ranges, ranges_to_rows, shard_range, sharded_cv_search_and_vote
     a, b, labels, folds, n_folds = _cv_case()
-    lo, hi = shard_range(len(labels), rank, world)
-    r = sharded_cv_search_and_vote(_StubEngine(), (a[lo:hi], b[lo:hi]), labels, folds, 3, 4, lo, 0, q_weights=(0.7, 0.3),
-                                   k_list=(1, 3), precision="fp32", n_folds=n_folds, q_block=256, want_lists=True)
-    return {k: r[k].numpy() for k in ("hit_counts", "vote_counts", "group_sizes", "top_idx")}
+    if balanced:
+        rows = ranges_to_rows(fold_balanced_ranges(np.bincount(folds, minlength=n_folds), rank, world, align=64), "cpu")
+        sel = rows.numpy()
+        r = sharded_cv_search_and_vote(_StubEngine(), (a[sel], b[sel]), labels, folds, 3, 4, 0, 0, q_weights=(0.7, 0.3),
+                                       k_list=(1, 3), precision="fp32", n_folds=n_folds, q_block=100, want_lists=True,
+                                       row_ids=rows)
+    else:
+        lo, hi = shard_range(len(labels), rank, world)
+        r = sharded_cv_search_and_vote(_StubEngine(), (a[lo:hi], b[lo:hi]), labels, folds, 3, 4, lo, 0, q_weights=(0.7, 0.3),
+                                       k_list=(1, 3), precision="fp32", n_folds=n_folds, q_block=256, want_lists=True)
+    return {k: r[k].numpy() for k in ("hit_counts", "vote_counts", "group_sizes", "top_idx", "top_labels")}
 
 
 def _cv_worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    out = _cv_run(world, rank)
+    out = {"contiguous": _cv_run(world, rank), "balanced": _cv_run(world, rank, balanced=True)}
     q.put((rank, out))
     dist.destroy_process_group()
+
+
+def test_fold_balanced_ranges_partition_every_fold():
+    from emr2a_b200.dist import fold_balanced_ranges
+    for counts in ([2_000_000] * 5, [10, 300, 7], [0, 5, 0], [1999999, 2000001, 2000000, 2000000, 2000000]):
+        for world in (1, 2, 4, 8):
+            per_rank = [fold_balanced_ranges(counts, r, world) for r in range(world)]
+            start = 0
+            for f, n_f in enumerate(counts):
+                pieces = [pr[f] for pr in per_rank]
+                assert pieces[0][0] == start and sum(c for _, c in pieces) == n_f
+                for (a0, c0), (a1, _) in zip(pieces, pieces[1:]):
+                    assert a0 + c0 == a1
+                assert all((g0 - start) % 256 == 0 or c == 0 for g0, c in pieces)
+                start += n_f
+            sizes = [sum(c for _, c in pr) for pr in per_rank]
+            if min(counts) >= 256 * world:
+                assert max(sizes) - min(sizes) <= 256 * world * len(counts)     # shards of (nearly) equal size
 
 
 def test_sharded_cv_world2_equals_single_process():
@@ -175,6 +199,8 @@ def test_sharded_cv_world2_equals_single_process():
     outs = dict(q.get(timeout=180) for _ in procs)
     for p in procs:
         p.join(timeout=60)
+    assert all(np.array_equal(_cv_run(1, 0, balanced=True)[key], want) for key, want in single.items())
     for rank in (0, 1):
-        for key, want in single.items():
-            assert np.array_equal(outs[rank][key], want), (rank, key)
+        for layout in ("contiguous", "balanced"):                                 # any sharding, same result
+            for key, want in single.items():
+                assert np.array_equal(outs[rank][layout][key], want), (rank, layout, key)

@@ -5,7 +5,7 @@ import torch, torch.distributed as dist
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 from emr2a_b200 import native, synth
-from emr2a_b200.dist import shard_range, sharded_cv_search_and_vote, sharded_search_and_vote
+from emr2a_b200.dist import fold_balanced_ranges, ranges_to_rows, shard_range, sharded_cv_search_and_vote, sharded_search_and_vote
 from emr2a_b200.engine import get_engine
 
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -47,9 +47,19 @@ for prec in ("rescore", "bf16x3"):
     same = all(torch.equal(r[key], full[key]) for key in names)
     print(f"rank {rank}/{world} cv {prec}: sharded == single-GPU: {same} (unverified {r['unverified']})", flush=True)
     ok = ok and same
+    # fold-balanced shards (a slice of every fold per rank; the C5 layout of bench.py), rows generated per range
+    ranges = fold_balanced_ranges([int((fold == f).sum()) for f in range(n_folds)], rank, world)
+    bi = torch.cat([synth.device_block(g0, cnt, d, c, 19, dev, label_seed=19)[0] for g0, cnt in ranges])
+    bt = torch.cat([synth.device_block(g0, cnt, d, c, 20, dev, label_seed=19)[0] for g0, cnt in ranges])
+    r = sharded_cv_search_and_vote(eng, (bi, bt), lab, fold, c, 5, 0, flags, k_list=[1, 3, 5], precision=prec,
+                                   n_folds=n_folds, q_block=16384, want_lists=True, row_ids=ranges_to_rows(ranges, dev))
+    same = all(torch.equal(r[key], full[key]) for key in names)
+    print(f"rank {rank}/{world} cv {prec}: fold-balanced shards == single-GPU: {same}", flush=True)
+    ok = ok and same
     # the engine call itself goes multi-GPU under torchrun (every rank passes the same arrays), here with UNSORTED folds
     mixed = ((torch.arange(n_cv, device=dev, dtype=torch.int64) * 7919) % n_folds).to(torch.uint8)
-    auto = eng.cv_search_and_vote((fi, ft), lab, mixed, c, 5, flags=flags, k_list=[1, 3, 5], precision=prec, n_folds=n_folds)
+    auto = eng.cv_search_and_vote((fi, ft), lab, mixed, c, 5, flags=flags, k_list=[1, 3, 5], precision=prec, n_folds=n_folds,
+                                  distributed=True)
     single = eng.cv_search_and_vote((fi, ft), lab, mixed, c, 5, flags=flags, k_list=[1, 3, 5], precision=prec, n_folds=n_folds,
                                     distributed=False)
     same = all(torch.equal(auto[key], single[key]) for key in names)
