@@ -197,12 +197,22 @@ def cpu_sample_leg(mode, k, n_db, fetch, q_img, q_txt, db_labels, q_labels, full
     oracle, feed = _oracle()
     s = oracle.StreamedReferenceSample(mode, k, n_db, q_img, q_txt, w_text=w_text, q_fold=q_fold)
     t0 = time.perf_counter()
-    feed.feed(s, n_db, fetch, chunk_rows=chunk_rows, timed_rows=timed_rows)
-    ref = s.finish(db_labels, q_labels)
+    try:        # torchrun pins every rank to OMP_NUM_THREADS=1; the CPU leg (rank 0 only) may use every host thread
+        from threadpoolctl import threadpool_limits
+        limit = threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        limit = None
+    try:
+        feed.feed(s, n_db, fetch, chunk_rows=chunk_rows, timed_rows=timed_rows)
+        ref = s.finish(db_labels, q_labels)
+        threads = _blas_threads()
+    finally:
+        if limit is not None:
+            limit.restore_original_limits()
     wall = time.perf_counter() - t0
     t_prep, t_q = ref["prep_seconds"] * prep_passes, ref["seconds_per_query"]
     qps = full_q / (t_prep + full_q * t_q)
-    info = {"value": qps, "unit": "queries/s", "cores": _blas_threads(), "kind": "port",
+    info = {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
             "sample": f"{len(q_labels)} of {full_q} queries, each scored against every admissible row of the {n_db}-row "
                       f"database (sgemv timed on the first {ref['timed_rows']} rows and scaled by rows; np.argsort over all "
                       f"{n_db} scores + python votes timed per query: {t_q * 1e3:.1f} ms/query) + database normalise/fuse "

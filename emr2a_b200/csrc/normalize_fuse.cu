@@ -8,6 +8,7 @@
 // (L1::no_allocate).  The arithmetic mirrors the reference op for op -- true IEEE
 // divisions by (sqrt(sum x^2) + 1e-8f) in fp32 -- so the fp32 output differs from
 // numpy only through the summation order of the norm (<= ~1e-7 relative).
+#include <type_traits>
 #include "common.cuh"
 
 namespace emr2a {
@@ -27,6 +28,7 @@ struct NfParams {
   int64_t ld_bf16;
   float* inv_norm;
   float* stats;     // [0] = max row norm, [1] = max ||row - bf16(row)||  (atomic max on the float bits)
+  const float* col_std;   // EMR2A_NF_STANDARDIZE: [3][d0 + d1] = per-column mean | scale | RN(1 / scale)
 };
 
 __device__ __forceinline__ void stats_flush(float* stats, float max_norm2, float max_res2) {
@@ -114,7 +116,23 @@ __device__ __forceinline__ void load_row(const NfParams& p, int64_t row, int lan
   }
 }
 
-template <typename InT, int MAXC, bool WANT_LO, bool STATS>
+// StandardScaler.transform on the loaded chunk: (x - mean) / scale per column, both IEEE fp32 -- the division as the
+// correctly rounded Markstein sequence with the per-column reciprocal the host precomputed (see RowDiv).
+__device__ __forceinline__ float std1(float x, float m, float s, float r) {
+  const float t = __fsub_rn(x, m);
+  const float q0 = t * r;
+  const float rem = fmaf(-q0, s, t);
+  return fmaf(rem, r, q0);
+}
+__device__ __forceinline__ void standardize4(float4& v, const float* __restrict__ col_std, int dtot, int col) {
+  const float4 m = __ldg(reinterpret_cast<const float4*>(col_std + col));
+  const float4 s = __ldg(reinterpret_cast<const float4*>(col_std + dtot + col));
+  const float4 r = __ldg(reinterpret_cast<const float4*>(col_std + 2 * dtot + col));
+  v.x = std1(v.x, m.x, s.x, r.x); v.y = std1(v.y, m.y, s.y, r.y);
+  v.z = std1(v.z, m.z, s.z, r.z); v.w = std1(v.w, m.w, s.w, r.w);
+}
+
+template <typename InT, int MAXC, bool WANT_LO, bool STATS, bool STD = false>
 __global__ void __launch_bounds__(256, (MAXC <= 8 ? 2 : 1)) normalize_fuse_vec_kernel(const NfParams p) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -136,6 +154,13 @@ __global__ void __launch_bounds__(256, (MAXC <= 8 ? 2 : 1)) normalize_fuse_vec_k
       if (row + nwarps < p.n) load_row<InT, MAXC>(p, row + nwarps, lane, c0, ctot, reinterpret_cast<float4 (&)[MAXC]>(nxt));
     } else {
       load_row<InT, MAXC>(p, row, lane, c0, ctot, v);
+    }
+    if (STD) {                              // per-fold StandardScaler fused into this pass (utils/cv_evaluator.py:78-80)
+#pragma unroll
+      for (int j = 0; j < MAXC; ++j) {
+        const int c = lane + 32 * j;
+        if (c < ctot) standardize4(v[j], p.col_std, p.d0 + p.d1, 4 * c);
+      }
     }
     float ss0 = 0.f, ss1 = 0.f;
     if (p.flags & EMR2A_NF_SEGNORM) {
@@ -434,6 +459,10 @@ __global__ void __launch_bounds__(256) normalize_fuse_scalar_kernel(const NfPara
 template <typename InT, int MAXC>
 static void launch_vec(const NfParams& p, unsigned blocks, int threads, cudaStream_t st) {
   const bool lo = p.out_lo != nullptr, stats = p.stats != nullptr;
+  if (p.flags & EMR2A_NF_STANDARDIZE) {       // fp32 rows in, fp32 rows out (checked by the entry point)
+    if constexpr (std::is_same<InT, float>::value) normalize_fuse_vec_kernel<InT, MAXC, false, false, true><<<blocks, threads, 0, st>>>(p);
+    return;
+  }
   if (lo && stats) normalize_fuse_vec_kernel<InT, MAXC, true, true><<<blocks, threads, 0, st>>>(p);
   else if (lo) normalize_fuse_vec_kernel<InT, MAXC, true, false><<<blocks, threads, 0, st>>>(p);
   else if (stats) normalize_fuse_vec_kernel<InT, MAXC, false, true><<<blocks, threads, 0, st>>>(p);
@@ -481,7 +510,8 @@ using namespace emr2a;
 extern "C" int emr2a_normalize_fuse(const void* seg0, const void* seg1, int64_t n, int d0, int d1,
                                     int64_t ld0, int64_t ld1, float w0, float w1, int flags, int in_dtype,
                                     float* out_f32, int64_t ld_f32, uint16_t* out_hi, uint16_t* out_lo,
-                                    int64_t ld_bf16, float* inv_norm_out, float* stats_out, void* stream) {
+                                    int64_t ld_bf16, float* inv_norm_out, float* stats_out, const float* col_std,
+                                    void* stream) {
   if (n < 0 || d0 <= 0 || d1 < 0) return fail(EMR2A_ERR_INVALID, "normalize_fuse: bad shape n=%lld d0=%d d1=%d", (long long)n, d0, d1);
   if (!seg0 || (d1 > 0 && !seg1)) return fail(EMR2A_ERR_INVALID, "normalize_fuse: null segment pointer");
   if (ld0 < d0 || (d1 > 0 && ld1 < d1)) return fail(EMR2A_ERR_INVALID, "normalize_fuse: leading dimension smaller than row");
@@ -492,13 +522,20 @@ extern "C" int emr2a_normalize_fuse(const void* seg0, const void* seg1, int64_t 
   if (out_hi && ld_bf16 < d0 + d1) return fail(EMR2A_ERR_INVALID, "normalize_fuse: ld_bf16 too small");
   if (n == 0) return EMR2A_OK;
   NfParams p{seg0, seg1, n, d0, d1, ld0, d1 > 0 ? ld1 : 0, w0, w1, flags,
-             out_f32, ld_f32, out_hi, out_lo, ld_bf16, inv_norm_out, stats_out};
+             out_f32, ld_f32, out_hi, out_lo, ld_bf16, inv_norm_out, stats_out, col_std};
   const size_t in_align = in_dtype == EMR2A_F32 ? 16 : 8;
   auto aligned = [](const void* q, size_t a) { return (reinterpret_cast<uintptr_t>(q) % a) == 0; };
   bool vec_ok = (d0 % 4 == 0) && (d1 % 4 == 0) && (ld0 % 4 == 0) && (d1 == 0 || ld1 % 4 == 0) &&
                 aligned(seg0, in_align) && (d1 == 0 || aligned(seg1, in_align));
   if (out_f32) vec_ok = vec_ok && (ld_f32 % 4 == 0) && aligned(out_f32, 16);
   if (out_hi) vec_ok = vec_ok && (ld_bf16 % 4 == 0) && aligned(out_hi, 8) && (!out_lo || aligned(out_lo, 8));
+  if (flags & EMR2A_NF_STANDARDIZE) {
+    if (!col_std) return fail(EMR2A_ERR_INVALID, "normalize_fuse: EMR2A_NF_STANDARDIZE needs col_std");
+    const int cmax = (d0 + d1) >> 2;
+    if (in_dtype != EMR2A_F32 || out_hi || !out_f32 || !vec_ok || !aligned(col_std, 16) || cmax > 32 * 16)
+      return fail(EMR2A_ERR_UNSUPPORTED, "normalize_fuse: the fused standardisation takes aligned fp32 rows of up to 2048 "
+                                         "columns (multiple of 4) and writes fp32 rows only");
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (in_dtype == EMR2A_F32) return launch_nf<float>(p, vec_ok, st);
   return launch_nf<__nv_bfloat16>(p, vec_ok, st);

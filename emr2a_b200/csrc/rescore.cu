@@ -17,8 +17,9 @@
 //             * the fp32 re-scoring the comparison is made against: D/32 round-to-nearest FMAs per lane plus the
 //               shuffle tree, <= (D/32 + 6) * 2^-24 * n_q n_d  (inside the 0.02 D + 8).
 //           D = 1024: 1.3e-4, D = 5120: 6.2e-4 per unit norms -- 3 % / 15 % on top of the quantisation terms.
-//           Measured tensor-core error on bf16-exact operands (tests/test_gpu_rescore_bound.py): 2-4e-7 at
-//           D = 5120, i.e. the model is ~3 orders of magnitude pessimistic, as a worst-case bound must be.
+//           Measured tensor-core error on bf16-exact operands (tests/test_gpu_rescore_bound.py, D = 5120): up to
+//           1.4e-5 * n_q n_d when all products have one sign (the accumulator truncates) -- above the constant
+//           1e-5 the first version of this bound used, 45x below this term.
 // Verify:   every row outside the candidate list has s~ <= tau (the KP-th approximate score), hence
 //           s <= tau + E.  If the exact K-th best candidate score exceeds tau + E strictly, no
 //           outside row can enter the Top-K and the selection is exact.  Otherwise the query is

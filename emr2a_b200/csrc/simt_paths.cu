@@ -26,6 +26,11 @@ struct SimtParams {
   // scores mode
   float* out;
   int64_t ld_out;
+  // projection mode (emr2a_project): q rows are standardised on load, (q - a_mean) / a_scale in IEEE fp32, and
+  // out_bias[c] is subtracted from column c of the result
+  const float* a_mean;
+  const float* a_scale;
+  const float* out_bias;
   // top-k mode
   const uint8_t* q_fold;
   const uint8_t* db_fold;
@@ -53,7 +58,10 @@ __device__ __forceinline__ void simt_tile_mma(const SimtParams& p, int64_t m0, i
       const int r = e >> 4, k = e & 15;
       const int64_t gr = m0 + r;
       float v = 0.f;
-      if (gr < p.Q && k0 + k < p.D) v = __ldg(p.q + gr * p.ldq + k0 + k);
+      if (gr < p.Q && k0 + k < p.D) {
+        v = __ldg(p.q + gr * p.ldq + k0 + k);
+        if (p.a_mean != nullptr) v = __fdiv_rn(__fsub_rn(v, __ldg(p.a_mean + k0 + k)), __ldg(p.a_scale + k0 + k));
+      }
       As[k][r] = v;
     }
 #pragma unroll
@@ -99,7 +107,7 @@ __global__ void __launch_bounds__(S_THREADS) simt_scores_kernel(const SimtParams
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int64_t c = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
-      if (c < p.N) p.out[r * p.ld_out + c] = acc[i][j];
+      if (c < p.N) p.out[r * p.ld_out + c] = p.out_bias != nullptr ? __fsub_rn(acc[i][j], __ldg(p.out_bias + c)) : acc[i][j];
     }
   }
 }
@@ -381,6 +389,27 @@ extern "C" int emr2a_scores(const float* q, const float* db, int64_t Q, int64_t 
   dim3 grid(static_cast<unsigned>((N + S_BN - 1) / S_BN), static_cast<unsigned>(gy));
   simt_scores_kernel<<<grid, S_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
   EMR2A_LAUNCH_CHECK("simt_scores_kernel");
+  return EMR2A_OK;
+}
+
+extern "C" int emr2a_project(const float* x, int64_t ld, int64_t n, int D, const float* mean, const float* scale,
+                             const float* w, int64_t ldw, int P, const float* bias, float* out, int64_t ld_out,
+                             void* stream) {
+  if (n < 0 || D <= 0 || P <= 0 || !x || !w || !out || ld < D || ldw < D || ld_out < P || ((mean == nullptr) != (scale == nullptr)))
+    return fail(EMR2A_ERR_INVALID, "project: bad arguments");
+  if (n == 0) return EMR2A_OK;
+  SimtParams p{};
+  p.q = x; p.db = w; p.Q = n; p.N = P; p.D = D; p.ldq = ld; p.lddb = ldw; p.out = out; p.ld_out = ld_out;
+  p.a_mean = mean; p.a_scale = scale; p.out_bias = bias;
+  const int64_t gy = (n + S_BM - 1) / S_BM;
+  for (int64_t y0 = 0; y0 < gy; y0 += 65535) {                 // the row-tile index lives in gridDim.y
+    const int64_t rows0 = y0 * S_BM;
+    SimtParams c = p;
+    c.q = x + rows0 * ld; c.out = out + rows0 * ld_out; c.Q = n - rows0 < 65535LL * S_BM ? n - rows0 : 65535LL * S_BM;
+    dim3 grid(static_cast<unsigned>((P + S_BN - 1) / S_BN), static_cast<unsigned>((c.Q + S_BM - 1) / S_BM));
+    simt_scores_kernel<<<grid, S_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(c);
+    EMR2A_LAUNCH_CHECK("simt_scores_kernel(project)");
+  }
   return EMR2A_OK;
 }
 

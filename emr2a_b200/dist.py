@@ -203,6 +203,8 @@ def sharded_cv_search_and_vote(eng, segs_local: Sequence, labels_global, folds_g
         works = []
         for nm in planes:
             t = getattr(qsrc, nm)[b0:b1] if r == rank else bufs[i % 2][nm][:b1 - b0]
+            if t.dtype == torch.int16:                 # bf16 planes are stored as int16; NCCL has no 16-bit integer type
+                t = t.view(torch.uint8)
             works.append(dist.broadcast(t, src=r, async_op=True))
         return works
 

@@ -102,7 +102,10 @@ class Engine:
     # --------------------------------------------------------------------- K1
     def normalize_fuse(self, seg0, seg1=None, w0: float = 1.0, w1: float = 1.0, flags: int = native.NF_ROWNORM,
                        want_f32: bool = True, want_planes: bool = False, want_lo: bool = True,
-                       want_inv_norm: bool = False, want_stats: bool = False) -> Operand:
+                       want_inv_norm: bool = False, want_stats: bool = False,
+                       col_std: Optional[torch.Tensor] = None) -> Operand:
+        """K1.  ``col_std`` (float32 [3, d0 + d1]: per-column mean | scale | 1/scale of a fitted StandardScaler) with
+        ``native.NF_STANDARDIZE`` in ``flags`` standardises the raw rows inside the same pass."""
         a, code = self._embedding(seg0)
         n, d0 = a.shape
         b = None
@@ -135,7 +138,7 @@ class Engine:
                 a.data_ptr(), native.ptr(b), n, d0, d1, _ld(a), _ld(b) if b is not None else 0,
                 float(w0), float(w1), int(flags), code,
                 native.ptr(out.f32), dim, native.ptr(out.hi), native.ptr(out.lo), ld_planes,
-                native.ptr(out.inv_norm), native.ptr(out.stats), self._stream()))
+                native.ptr(out.inv_norm), native.ptr(out.stats), native.ptr(col_std), self._stream()))
         self.launches += 1
         return out
 

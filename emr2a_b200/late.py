@@ -41,13 +41,18 @@ def _query_operand(eng: Engine, rows: torch.Tensor, prec: str) -> Operand:
 
 
 def database_moments(eng: Engine, unit_rows: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """float64 column sums [D] and Gram matrix [D, D] of a (column slice of a) row-major fp32 matrix."""
+    """float64 column sums [D] and Gram matrix [D, D] of a (column slice of a) row-major fp32 matrix: one pass of the
+    hand-written float64 contraction ``emr2a_gram_f64`` (no standardisation here: the rows are used as they are)."""
     n, d = int(unit_rows.shape[0]), int(unit_rows.shape[1])
-    s, _ = pp.column_moments(eng, unit_rows)
-    gram = torch.zeros((d, d), dtype=torch.float64, device=eng.device)
-    for lo in range(0, n, _CHUNK_ROWS):
-        z64 = unit_rows[lo:min(lo + _CHUNK_ROWS, n)].double()
-        gram.addmm_(z64.t(), z64)
+    gram = torch.empty((d, d), dtype=torch.float64, device=eng.device)
+    s = torch.empty((d,), dtype=torch.float64, device=eng.device)
+    ws_bytes = int(eng.lib.emr2a_gram_f64_workspace_bytes(n, d))
+    ws = torch.empty((ws_bytes // 8 + 2,), dtype=torch.float64, device=eng.device)
+    ld = int(unit_rows.stride(0)) if n > 1 else d
+    with torch.cuda.device(eng.device):
+        native.check(eng.lib.emr2a_gram_f64(unit_rows.data_ptr(), ld, n, d, None, None, gram.data_ptr(), s.data_ptr(),
+                                            ws.data_ptr(), ws.numel() * 8, eng._stream()))
+    eng.launches += 2 if n else 0
     return s, gram
 
 

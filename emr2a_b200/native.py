@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(PKG, "libemr2a.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_WORKSPACE = 0, 1, 2, 3, 4
 F32, BF16 = 0, 1
-NF_SEGNORM, NF_ROWNORM, NF_ZERO_GUARD = 1, 2, 4
+NF_SEGNORM, NF_ROWNORM, NF_ZERO_GUARD, NF_STANDARDIZE = 1, 2, 4, 8
 PREC_FP32, PREC_BF16X3, PREC_BF16X1, PREC_BF16_RESCORE = 0, 1, 2, 3
 SCORE_NONE, SCORE_ZSCORE, SCORE_MINMAX = 0, 1, 2
 ABI_VERSION = 8
@@ -31,7 +31,7 @@ _SIGNATURES = {
     "emr2a_last_error": (C.c_char_p, []),
     "emr2a_device_check": (_int, [C.POINTER(_int), C.POINTER(_int), C.POINTER(_int)]),
     "emr2a_normalize_fuse": (_int, [_p, _p, _i64, _int, _int, _i64, _i64, _f, _f, _int, _int,
-                                    _p, _i64, _p, _p, _i64, _p, _p, _p]),
+                                    _p, _i64, _p, _p, _i64, _p, _p, _p, _p]),
     "emr2a_scores": (_int, [_p, _p, _i64, _i64, _int, _i64, _i64, _p, _i64, _p]),
     "emr2a_euclid_workspace_bytes": (_sz, [_i64]),
     "emr2a_euclid_scores": (_int, [_p, _p, _i64, _int, _i64, _p, _p, _sz, _p]),
@@ -47,6 +47,9 @@ _SIGNATURES = {
     "emr2a_column_moments_workspace_bytes": (_sz, [_i64, _int]),
     "emr2a_column_moments": (_int, [_p, _i64, _i64, _int, _p, _p, _p, _p, _sz, _p]),
     "emr2a_standardize": (_int, [_p, _i64, _i64, _int, _p, _p, _p, _i64, _p]),
+    "emr2a_gram_f64_workspace_bytes": (_sz, [_i64, _int]),
+    "emr2a_gram_f64": (_int, [_p, _i64, _i64, _int, _p, _p, _p, _p, _p, _sz, _p]),
+    "emr2a_project": (_int, [_p, _i64, _i64, _int, _p, _p, _p, _i64, _int, _p, _p, _i64, _p]),
     "emr2a_scale_segments": (_int, [_p, _i64, _int, _int, _i64, _p, _p, _p]),
     "emr2a_keys_add_offset": (_int, [_p, _i64, _int, _p, _p]),
     "emr2a_segment_mean": (_int, [_p, _i64, _p, _i64, _int, _p, _i64, _p]),

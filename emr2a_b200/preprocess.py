@@ -5,9 +5,12 @@ sides (``CVRetrievalEvaluator.process_embeddings`` utils/cv_evaluator.py:73-93; 
 What runs where
     column mean / variance ........ ``emr2a_column_moments`` (hand-written, HBM-bound, float64 accumulators)
     (x - mean) / scale ............ ``emr2a_standardize``    (hand-written, HBM-bound, sklearn's fp32 arithmetic)
-    Z^T Z, eigh ................... library calls (cuBLAS DGEMM, cuSOLVER syevd through torch): a plain GEMM and a
-                                    D x D symmetric eigenproblem, fit only
-    Z W^T ......................... ``emr2a_scores`` (hand-written fp32 FMA GEMM, fixed summation order)
+    Z^T Z, column sums of Z ....... ``emr2a_gram_f64`` (hand-written float64 FMA contraction, standardisation fused
+                                    into its operand load: the raw train rows are read, Z is never written)
+    eigh .......................... library call (cuSOLVER syevd through torch): a D x D symmetric eigenproblem, fit only
+    Z W^T - bias .................. ``emr2a_project`` (hand-written fp32 FMA GEMM, fixed summation order, standardisation
+                                    fused into its operand load, bias into its epilogue)
+    scaler-only transform ......... K1 with ``NF_STANDARDIZE`` (standardise + row-normalise in one pass)
     row normalisation ............. K1 (``emr2a_normalize_fuse``)
 
 Contract.  The scaler reproduces sklearn's ``StandardScaler`` (float64 statistics, fp32 transform).  The PCA is the
@@ -125,17 +128,17 @@ def fit(x_train, pca_dim: Optional[int], engine: Optional[Engine] = None) -> Fol
     n_comp = min(int(pca_dim), n - 1, d) if pca_dim is not None else 0
     if n_comp <= 0:
         return tf
-    # covariance of the standardised rows, float64: C = (Z^T Z - n m m^T) / (n - 1)
-    gram = torch.zeros((d, d), dtype=torch.float64, device=eng.device)
-    zsum = torch.zeros((d,), dtype=torch.float64, device=eng.device)
-    buf = torch.empty((min(n, _CHUNK_ROWS), d), dtype=torch.float32, device=eng.device)
-    for lo in range(0, n, _CHUNK_ROWS):
-        hi = min(lo + _CHUNK_ROWS, n)
-        z = standardize(eng, x[lo:hi], tf.mean_f32, tf.scale_f32, out=buf[:hi - lo])
-        s, _ = column_moments(eng, z)
-        zsum += s
-        z64 = z.double()
-        gram.addmm_(z64.t(), z64)
+    # covariance of the standardised rows, float64: C = (Z^T Z - n m m^T) / (n - 1).  Z^T Z and the column sums come
+    # from ONE pass over the raw rows (emr2a_gram_f64: standardisation fused into the operand load, float64 FMA
+    # contraction, upper triangle only); the standardised matrix is never written.
+    gram = torch.empty((d, d), dtype=torch.float64, device=eng.device)
+    zsum = torch.empty((d,), dtype=torch.float64, device=eng.device)
+    ws_bytes = int(eng.lib.emr2a_gram_f64_workspace_bytes(n, d))
+    ws = torch.empty((ws_bytes // 8 + 2,), dtype=torch.float64, device=eng.device)
+    with torch.cuda.device(eng.device):
+        native.check(eng.lib.emr2a_gram_f64(x.data_ptr(), _ld(x), n, d, tf.mean_f32.data_ptr(), tf.scale_f32.data_ptr(),
+                                            gram.data_ptr(), zsum.data_ptr(), ws.data_ptr(), ws.numel() * 8, eng._stream()))
+    eng.launches += 2
     m = zsum / n
     cov = (gram - n * torch.outer(m, m)) / (n - 1)
     cov = 0.5 * (cov + cov.t())
@@ -147,8 +150,7 @@ def fit(x_train, pca_dim: Optional[int], engine: Optional[Engine] = None) -> Fol
     comps = comps * signs[:, None]
     tf.components = comps.float().contiguous()
     tf.pca_mean = m.float().contiguous()
-    with _NoTF32():
-        tf.bias = (tf.pca_mean[None, :] @ tf.components.t())[0].contiguous()
+    tf.bias = eng.scores(tf.pca_mean[None, :].contiguous(), tf.components)[0].contiguous()      # mean_ @ components_.T
     tf.explained_variance = evals
     return tf
 
@@ -164,20 +166,26 @@ def transform(tf: FoldTransform, x, engine: Optional[Engine] = None, normalize: 
     if d != tf.dim:
         raise ValueError(f"X has {d} features, but the transform was fitted with {tf.dim} features")
     if tf.components is None:
+        if normalize:
+            # scaler-only transform: standardise + row-normalise in ONE pass over the raw rows (K1, NF_STANDARDIZE)
+            col_std = torch.stack([tf.mean_f32, tf.scale_f32, 1.0 / tf.scale_f32]).contiguous()
+            try:
+                return eng.normalize_fuse(x, flags=native.NF_ROWNORM | native.NF_STANDARDIZE, col_std=col_std).f32
+            except native.Emr2aError as exc:      # shapes the fused variant does not take (odd / very wide rows)
+                if exc.code != native.ERR_UNSUPPORTED:
+                    raise
         y = standardize(eng, x, tf.mean_f32, tf.scale_f32)
     else:
+        # projection with the standardisation fused into the operand load and the bias into the epilogue
+        # (emr2a_project: one kernel, the raw rows are read once, nothing but the [n, P] result is written)
         p = tf.n_components
         y = torch.empty((n, p), dtype=torch.float32, device=eng.device)
-        buf = torch.empty((min(n, _CHUNK_ROWS), d), dtype=torch.float32, device=eng.device)
-        w = tf.components                                   # [P, D]: y[r, j] = <z_r, w_j>, the shape of emr2a_scores
-        for lo in range(0, n, _CHUNK_ROWS):
-            hi = min(lo + _CHUNK_ROWS, n)
-            z = standardize(eng, x[lo:hi], tf.mean_f32, tf.scale_f32, out=buf[:hi - lo])
-            with torch.cuda.device(eng.device):          # projection on our own fp32 FMA kernel (fixed summation order)
-                native.check(eng.lib.emr2a_scores(z.data_ptr(), w.data_ptr(), hi - lo, p, d, _ld(z), _ld(w),
-                                                  y[lo:hi].data_ptr(), p, eng._stream()))
+        w = tf.components                                   # [P, D]: y[r, j] = <z_r, w_j> - bias_j
+        if n:
+            with torch.cuda.device(eng.device):
+                native.check(eng.lib.emr2a_project(x.data_ptr(), _ld(x), n, d, tf.mean_f32.data_ptr(), tf.scale_f32.data_ptr(),
+                                                   w.data_ptr(), _ld(w), p, tf.bias.data_ptr(), y.data_ptr(), p, eng._stream()))
             eng.launches += 1
-        y -= tf.bias
     if not normalize:
         return y
     return eng.normalize_fuse(y, flags=native.NF_ROWNORM).f32

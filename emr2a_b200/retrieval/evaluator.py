@@ -51,7 +51,7 @@ class RetrievalEvaluator:
             train += members[cut:]
         return train, test
 
-    preprocess: str = os.environ.get("EMR2A_PREPROCESS", "host")
+    preprocess: str = os.environ.get("EMR2A_PREPROCESS", "auto")
 
     def _preprocess_on_gpu(self, n_train: int, n_features: int) -> bool:
         mode = self.preprocess
@@ -61,7 +61,7 @@ class RetrievalEvaluator:
             return mode == "gpu"
         from ..preprocess import sklearn_solver
         n_comp = min(self.pca_dim, n_train - 1, n_features) if self.use_pca else 0
-        return n_comp <= 0 or sklearn_solver(n_train, n_features, n_comp) != "randomized"
+        return n_comp <= 0 or sklearn_solver(n_train, n_features, n_comp) != "full"      # see CVRetrievalEvaluator.preprocess
 
     def process_embeddings(self, train_embeddings: np.ndarray, test_embeddings: np.ndarray
                            ) -> Tuple[np.ndarray, np.ndarray]:

@@ -51,7 +51,10 @@ enum emr2a_dtype { EMR2A_F32 = 0, EMR2A_BF16 = 1 };
 enum emr2a_nf_flags {
   EMR2A_NF_SEGNORM = 1,     /* first scale each segment to unit length: x / (||x|| + 1e-8) */
   EMR2A_NF_ROWNORM = 2,     /* after weighting + concatenation divide the row by (||row|| + 1e-8) */
-  EMR2A_NF_ZERO_GUARD = 4   /* ROWNORM without epsilon, zero rows stay zero (utils/common.py:4-8) */
+  EMR2A_NF_ZERO_GUARD = 4,  /* ROWNORM without epsilon, zero rows stay zero (utils/common.py:4-8) */
+  EMR2A_NF_STANDARDIZE = 8  /* first apply the fitted StandardScaler per column, (x - mean) / scale in IEEE fp32
+                               (utils/cv_evaluator.py:78-80, retrieval/evaluator.py:55-57), from col_std: the per-fold
+                               scaler and the row normalisation are ONE pass over the raw rows */
 };
 
 /* arithmetic of emr2a_topk_search */
@@ -95,6 +98,8 @@ int emr2a_device_check(int* sm_count, int* cc_major, int* cc_minor);
  *   out_hi / out_lo [n, ld_bf16]  bf16 planes for the tensor-core search:
  *            hi = bf16(out), lo = bf16(out - hi); columns [d0+d1, ld_bf16) are zero-filled
  *   inv_norm_out [n]       1 / (||row|| + 1e-8) of the final division (1.0 without ROWNORM)
+ *   col_std [3][d0+d1]     with EMR2A_NF_STANDARDIZE: per-column mean | scale | RN(1/scale) of the fitted scaler
+ *                          (fp32, 16-byte aligned; fp32 rows in and out, up to 2048 columns); NULL otherwise
  *   stats_out [2]          running maxima over the rows (atomic max; zero it before the first call):
  *                          [0] = max ||out row||, [1] = max ||out row - bf16(out row)||; needs out_hi.
  *                          Input of the EMR2A_PREC_BF16_RESCORE error bound.
@@ -103,7 +108,7 @@ int emr2a_normalize_fuse(const void* seg0, const void* seg1, int64_t n, int d0, 
                          int64_t ld0, int64_t ld1, float w0, float w1, int flags, int in_dtype,
                          float* out_f32, int64_t ld_f32,
                          uint16_t* out_hi, uint16_t* out_lo, int64_t ld_bf16,
-                         float* inv_norm_out, float* stats_out, void* stream);
+                         float* inv_norm_out, float* stats_out, const float* col_std, void* stream);
 
 /*
  * Full score matrix out[q, j] = <q_q, db_j> in fp32 (CUDA cores), for the API
@@ -237,8 +242,9 @@ int emr2a_segment_mean(const float* x, int64_t ld, const int64_t* offsets, int64
 
 /*
  * Per-fold preprocessing (StandardScaler -> PCA fitted on the train fold: utils/cv_evaluator.py:73-93,
- * retrieval/evaluator.py:44-73) -- the two HBM-bound passes; the D x D covariance / projection GEMMs and the
- * symmetric eigen-decomposition are library calls made by the host layer (emr2a_b200/preprocess.py).
+ * retrieval/evaluator.py:44-73): the HBM-bound passes, the float64 covariance contraction and the projection are
+ * kernels of this library; only the D x D symmetric eigen-decomposition is a library call made by the host layer
+ * (emr2a_b200/preprocess.py).
  *
  * emr2a_column_moments: sum[c] = SUM_r (x[r,c] - shift[c]), sumsq[c] = SUM_r (x[r,c] - shift[c])^2 over the n rows,
  *   accumulated in float64 (StandardScaler reduces float32 input in float64: sklearn _incremental_mean_and_var).
@@ -247,7 +253,21 @@ int emr2a_segment_mean(const float* x, int64_t ld, const int64_t* offsets, int64
  * emr2a_standardize: out[r,c] = (x[r,c] - mean[c]) / scale[c] in IEEE fp32, mean/scale already cast to float32 --
  *   the arithmetic of StandardScaler.transform on a float32 array (`X -= astype(mean_, X.dtype); X /= astype(scale_,
  *   X.dtype)`).  out may alias x.
+ * emr2a_gram_f64: gram[a,b] = SUM_r z[r,a] z[r,b] and zsum[a] = SUM_r z[r,a] in float64, where z = the standardised
+ *   row computed on the fly, z[r,c] = fp32((x[r,c] - mean[c]) / scale[c]) (mean/scale nullable: z = x) -- the
+ *   covariance input of the PCA fit (PCA.fit on the scaler's output, utils/cv_evaluator.py:89-90) without writing
+ *   the standardised matrix.  Hand-written float64 FMA contraction, deterministic (fixed row partition, ordered
+ *   second stage).  gram is the full symmetric D x D matrix, row-major.  workspace:
+ *   emr2a_gram_f64_workspace_bytes(n, D), 8-byte aligned.
+ * emr2a_project: out[r,j] = SUM_c z[r,c] * w[j,c] - bias[j]  (PCA.transform: `X @ components_.T - mean_ @
+ *   components_.T`, utils/cv_evaluator.py:90-91) with z standardised on the fly as above, fp32 FMA in ascending c
+ *   (bit-identical to emr2a_standardize followed by emr2a_scores and the subtraction).  bias nullable.
  */
+size_t emr2a_gram_f64_workspace_bytes(int64_t n, int D);
+int emr2a_gram_f64(const float* x, int64_t ld, int64_t n, int D, const float* mean, const float* scale,
+                   double* gram, double* zsum, void* workspace, size_t ws_bytes, void* stream);
+int emr2a_project(const float* x, int64_t ld, int64_t n, int D, const float* mean, const float* scale,
+                  const float* w, int64_t ldw, int P, const float* bias, float* out, int64_t ld_out, void* stream);
 size_t emr2a_column_moments_workspace_bytes(int64_t n, int D);
 int emr2a_column_moments(const float* x, int64_t ld, int64_t n, int D, const float* shift,
                          double* sum, double* sumsq, void* workspace, size_t ws_bytes, void* stream);

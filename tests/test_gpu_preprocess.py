@@ -192,3 +192,89 @@ def test_run_cv_arrays_equals_run_cv_with_gpu_preprocessing(golden, fusion, w):
         ev.run_cv_arrays(labels, g["image"], None, fusion="concat")
     with pytest.raises(ValueError):
         ev.run_cv_arrays(labels, g["image"], g["text"], fusion="bogus")
+
+
+@pytest.mark.parametrize("n,d,pad", [(1, 5, 0), (130, 64, 0), (1000, 130, 3), (4097, 512, 0), (50000, 96, 0), (300, 1030, 2)])
+def test_gram_f64_with_fused_standardisation(n, d, pad):
+    """emr2a_gram_f64: Z^T Z and column sums of Z in float64, Z standardised on the fly in sklearn's fp32 arithmetic --
+    against float64 numpy on the materialised fp32 Z (emr2a_standardize), with and without the scaler; symmetric,
+    deterministic."""
+    import torch
+    from emr2a_b200 import native, preprocess as pp
+    from emr2a_b200.engine import get_engine
+    eng = get_engine()
+    rng = np.random.default_rng(3 * n + d)
+    full = (rng.standard_normal((n, d + pad)) * rng.uniform(0.1, 9, d + pad) + rng.uniform(-20, 20, d + pad)).astype(np.float32)
+    x = torch.from_numpy(full).to(eng.device)[:, :d]
+    mean = torch.from_numpy(full[:, :d].mean(axis=0).astype(np.float32)).to(eng.device)
+    scale = torch.from_numpy((full[:, :d].std(axis=0) + 0.1).astype(np.float32)).to(eng.device)
+
+    def gram(m, s):
+        g = torch.empty((d, d), dtype=torch.float64, device=eng.device)
+        zs = torch.empty((d,), dtype=torch.float64, device=eng.device)
+        ws = torch.empty((int(eng.lib.emr2a_gram_f64_workspace_bytes(n, d)) // 8 + 2,), dtype=torch.float64, device=eng.device)
+        native.check(eng.lib.emr2a_gram_f64(x.data_ptr(), int(x.stride(0)) if n > 1 else d, n, d, native.ptr(m), native.ptr(s),
+                                            g.data_ptr(), zs.data_ptr(), ws.data_ptr(), ws.numel() * 8, None))
+        return g, zs
+    for m, s in ((None, None), (mean, scale)):
+        z = full[:, :d] if m is None else pp.standardize(eng, x, m, s).cpu().numpy()
+        z64 = z.astype(np.float64)
+        g, zs = gram(m, s)
+        want = z64.T @ z64
+        np.testing.assert_allclose(g.cpu().numpy(), want, rtol=1e-12, atol=1e-9 * np.abs(want).max())
+        np.testing.assert_allclose(zs.cpu().numpy(), z64.sum(axis=0), rtol=1e-12, atol=1e-9 * max(1.0, np.abs(z64).sum(axis=0).max()))
+        assert torch.equal(g, g.t())
+        g2, zs2 = gram(m, s)
+        assert torch.equal(g, g2) and torch.equal(zs, zs2)
+
+
+@pytest.mark.parametrize("n,d,p", [(1, 8, 3), (777, 48, 16), (5000, 512, 128), (300, 1030, 200), (70000, 64, 24)])
+def test_project_equals_standardize_scores_bias(n, d, p):
+    """emr2a_project (standardisation fused into the operand load, bias into the epilogue) is bit-identical to the
+    three separate steps emr2a_standardize -> emr2a_scores -> subtract."""
+    import torch
+    from emr2a_b200 import native, preprocess as pp
+    from emr2a_b200.engine import get_engine
+    eng = get_engine()
+    g = torch.Generator(device=eng.device).manual_seed(n + d + p)
+    x = torch.randn((n, d), generator=g, device=eng.device) * 3 + 1
+    mean = torch.randn((d,), generator=g, device=eng.device)
+    scale = torch.rand((d,), generator=g, device=eng.device) + 0.5
+    w = torch.randn((p, d), generator=g, device=eng.device) / d ** 0.5
+    bias = torch.randn((p,), generator=g, device=eng.device)
+    want = eng.scores(pp.standardize(eng, x, mean, scale), w) - bias
+    got = torch.empty((n, p), dtype=torch.float32, device=eng.device)
+    native.check(eng.lib.emr2a_project(x.data_ptr(), d, n, d, mean.data_ptr(), scale.data_ptr(), w.data_ptr(), d, p,
+                                       bias.data_ptr(), got.data_ptr(), p, None))
+    assert torch.equal(got, want)
+    native.check(eng.lib.emr2a_project(x.data_ptr(), d, n, d, None, None, w.data_ptr(), d, p, None, got.data_ptr(), p, None))
+    assert torch.equal(got, eng.scores(x, w))
+
+
+@pytest.mark.parametrize("n,d", [(5, 8), (777, 48), (5000, 512), (3000, 1024), (200, 2048)])
+def test_k1_fused_standardisation_equals_two_passes(n, d):
+    """K1 with NF_STANDARDIZE (scaler + row normalisation in one pass over the raw rows) equals emr2a_standardize
+    followed by K1: the per-column division is the correctly rounded quotient in both."""
+    import torch
+    from emr2a_b200 import native, preprocess as pp
+    from emr2a_b200.engine import get_engine
+    eng = get_engine()
+    g = torch.Generator(device=eng.device).manual_seed(n * 7 + d)
+    x = torch.randn((n, d), generator=g, device=eng.device) * 4 - 2
+    mean = torch.randn((d,), generator=g, device=eng.device)
+    scale = torch.rand((d,), generator=g, device=eng.device) * 3 + 0.05
+    z = pp.standardize(eng, x, mean, scale)
+    want = eng.normalize_fuse(z, flags=native.NF_ROWNORM).f32
+    col_std = torch.stack([mean, scale, 1.0 / scale]).contiguous()
+    got = eng.normalize_fuse(x, flags=native.NF_ROWNORM | native.NF_STANDARDIZE, col_std=col_std).f32
+    assert torch.equal(got, want)
+    # without the row normalisation the kernel is StandardScaler.transform itself
+    assert torch.equal(eng.normalize_fuse(x, flags=native.NF_STANDARDIZE, col_std=col_std).f32, z)
+    # shapes the fused variant does not take are refused loudly (the host layer then runs the two passes)
+    with pytest.raises(native.Emr2aError):
+        eng.normalize_fuse(x[:, :d - 1].contiguous(), flags=native.NF_ROWNORM | native.NF_STANDARDIZE,
+                           col_std=col_std[:, :d - 1].contiguous())
+    tf = pp.fit(x, None, eng)
+    a = pp.transform(tf, x, eng)                                   # scaler-only transform takes the fused pass
+    b = eng.normalize_fuse(pp.standardize(eng, x, tf.mean_f32, tf.scale_f32), flags=native.NF_ROWNORM).f32
+    assert torch.equal(a, b)

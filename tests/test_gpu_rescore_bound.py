@@ -63,7 +63,9 @@ def test_tensor_core_accumulation_error_is_far_inside_the_bound(eng):
     print(f"tensor-core fp32 accumulation, D={D}: max |err| {err.max():.3e}, max err/(n_q n_d) {rel:.3e}, "
           f"bound coefficient {(1.02 * D + 8) * 2.0 ** -23:.3e}")
     assert np.all(err <= bound)
-    assert rel < 1e-5            # (and the old constant 1e-5 n_q n_d happened to hold on this sample, too)
+    # measured on B200: 1.4e-5 * n_q n_d for the all-positive pairs (the accumulator truncates: ~115 units of 2^-23
+    # over 320 accumulation steps) -- ABOVE the constant 1e-5 n_q n_d the round-1 bound used, 45x below the new term
+    assert rel < 0.1 * (1.02 * D + 8) * 2.0 ** -23
 
 
 def test_bf16_exact_rows_with_planted_near_ties(eng, oracle):

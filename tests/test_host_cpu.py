@@ -214,10 +214,11 @@ def test_auto_mode_follows_sklearn_solver_choice():
     from emr2a_b200.utils.cv_evaluator import CVRetrievalEvaluator
     from emr2a_b200.retrieval.evaluator import RetrievalEvaluator
     ev = CVRetrievalEvaluator(pca_dim=128)
+    assert ev.preprocess == os.environ.get("EMR2A_PREPROCESS", "auto")          # the default
     ev.preprocess = "auto"
-    assert ev._preprocess_on_gpu(240, 48)            # "full"
-    assert ev._preprocess_on_gpu(8000, 512)          # "covariance_eigh"
-    assert not ev._preprocess_on_gpu(1600, 512)      # "randomized": reproduce the seeded reference on the host
+    assert not ev._preprocess_on_gpu(240, 48)        # sklearn "full": deterministic there, 2e-4 from the exact basis -> host
+    assert ev._preprocess_on_gpu(8000, 512)          # sklearn "covariance_eigh": 2e-6 from the exact basis -> device
+    assert ev._preprocess_on_gpu(1600, 512)          # sklearn "randomized", unseeded in the reference -> device (C1's shape)
     ev.preprocess = "host"
     assert not ev._preprocess_on_gpu(240, 48)
     ev.preprocess = "bogus"
@@ -225,7 +226,10 @@ def test_auto_mode_follows_sklearn_solver_choice():
         ev._preprocess_on_gpu(240, 48)
     ho = RetrievalEvaluator(use_pca=False)
     ho.preprocess = "auto"
-    assert ho._preprocess_on_gpu(1600, 512)          # scaler only: always deterministic
+    assert ho._preprocess_on_gpu(1600, 512)          # scaler only: bit-identical to sklearn
+    ho = RetrievalEvaluator(use_pca=True, pca_dim=16)
+    ho.preprocess = "auto"
+    assert not ho._preprocess_on_gpu(200, 32) and ho._preprocess_on_gpu(5000, 64)
 
 
 def test_public_signatures_match_the_reference():
