@@ -51,6 +51,17 @@ int rescore_pipeline(const uint64_t* approx, int KP, const uint32_t* tau, const 
                      const float* db_stats, const uint8_t* q_fold, const uint8_t* db_fold, uint64_t* out_keys,
                      int* status, uint8_t* qflags, void* workspace, size_t ws_bytes, cudaStream_t st);
 
+int rescore_kth_scores(const uint64_t* approx, int KP, int K, int64_t Q, float* kth, cudaStream_t st);
+int rescore_select_only(const uint64_t* approx, int KP, const uint32_t* tau, const float* kth_floor, const float* q,
+                        int64_t ldq, const float* db, int64_t lddb, int64_t Q, int64_t N, int D, int64_t idx_base, int K,
+                        const float* q_stats, const float* db_stats, uint64_t* out_keys, float* bound_out, cudaStream_t st);
+int rescore_verify_merged(const uint64_t* keys, int K, int64_t Q, const float* bounds, int parts, int64_t bounds_stride,
+                          uint8_t* flags, int* count, cudaStream_t st);
+size_t exact_rescan_workspace_bytes(int n_flagged, int K);
+int rescore_exact_rescan(const float* q, int64_t ldq, const float* db, int64_t lddb, int64_t N, int D, int64_t idx_base, int K,
+                         const uint8_t* q_fold, const uint8_t* db_fold, const int* flag_list, int n_flagged,
+                         uint64_t* out_compact, void* workspace, size_t ws_bytes, cudaStream_t st);
+
 constexpr int RESCORE_KP = 32;    // candidates kept per (query, database split) by the filter; 16 leaves too little slack (measured)
 constexpr int RESCORE_KPM = 64;   // candidates per query re-scored after merging the splits
 static inline size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
@@ -91,6 +102,39 @@ extern "C" size_t emr2a_topk_search_workspace_bytes(int64_t Q, int64_t N, int D,
   return tc_topk_workspace_bytes(Q, N, K, D);
 }
 
+// Filter stage of the RESCORE arm: 1-pass tensor-core search keeping kp candidates per (query, database split), merged
+// to the RESCORE_KPM best per query.  *cand -> [Q][*kpm] approximate keys (in `approx` or in the workspace), *tau -> [Q]
+// bound on the filter score of the rows no split kept (may be null: a single split whose list is all there is).
+static int rescore_filter_stage(const uint16_t* q_hi, int64_t ldq_bf16, const uint16_t* db_hi, int64_t lddb_bf16, int64_t Q,
+                                int64_t N, int D, const uint8_t* q_fold, const uint8_t* db_fold, int fold_sorted,
+                                int64_t idx_base, int K, uint64_t* approx, void* tc_ws, size_t tc_ws_bytes,
+                                float* debug_scores, cudaStream_t st, const uint64_t** cand, int* kpm,
+                                const uint32_t** tau) {
+  TcPartials parts{};
+  // At least two splits so that the merged candidates of several lists back the verification; with >= 8
+  // splits (or K <= 5) each split only keeps 16 (rows it drops are bounded by tau), which halves the
+  // epilogue's insertion work.
+  // A single-tile batch on single CTAs gets one split per SM (148): 8 rows per split are 1184 candidates, more than
+  // the 64 that are re-scored, and keep the merge within its 2048-key register variant.
+  const int planned = tc_planned_splits(Q, N, 2);
+  const int kp = planned > 128 ? 8 : ((planned >= 8 || K <= 5) ? 16 : RESCORE_KP);
+  int rc = tc_topk_search(q_hi, nullptr, db_hi, nullptr, Q, N, D, ldq_bf16, lddb_bf16, q_fold, db_fold, idx_base,
+                          kp, 1, nullptr, tc_ws, tc_ws_bytes, debug_scores, st, &parts, fold_sorted, 2);
+  if (rc != EMR2A_OK) return rc;
+  // several splits: re-score the 64 best approximate candidates of the query (rows outside the per-split
+  // lists are bounded by tau); one split: its candidates are all there is
+  *kpm = kp;
+  *cand = parts.parts;
+  *tau = parts.tau;
+  if (parts.splits > 1) {
+    *kpm = RESCORE_KPM;
+    rc = emr2a_topk_merge(parts.parts, parts.splits, Q, kp, Q * kp, kp, RESCORE_KPM, approx, st);
+    if (rc != EMR2A_OK) return rc;
+    *cand = approx;
+  }
+  return EMR2A_OK;
+}
+
 static int topk_search_impl(const float* q_f32, int64_t ldq_f32, const uint16_t* q_hi, const uint16_t* q_lo,
                             int64_t ldq_bf16, const float* db_f32, int64_t lddb_f32, const uint16_t* db_hi,
                             const uint16_t* db_lo, int64_t lddb_bf16, int64_t Q, int64_t N, int D,
@@ -128,29 +172,13 @@ static int topk_search_impl(const float* q_f32, int64_t ldq_f32, const uint16_t*
       const size_t r_bytes = align256(rescore_workspace_bytes(Q, K));
       if (ws_bytes < a_bytes + t_bytes + r_bytes) return fail(EMR2A_ERR_WORKSPACE, "topk_search(rescore): workspace %zu < %zu", ws_bytes, a_bytes + t_bytes + r_bytes);
       uint8_t* ws = static_cast<uint8_t*>(workspace);
-      uint64_t* approx = reinterpret_cast<uint64_t*>(ws);
-      TcPartials parts{};
-      // At least two splits so that the merged candidates of several lists back the verification; with >= 8
-      // splits (or K <= 5) each split only keeps 16 (rows it drops are bounded by tau), which halves the
-      // epilogue's insertion work.
-      // A single-tile batch on single CTAs gets one split per SM (148): 8 rows per split are 1184 candidates, more than
-      // the 64 that are re-scored, and keep the merge within its 2048-key register variant.
-      const int planned = tc_planned_splits(Q, N, 2);
-      const int kp = planned > 128 ? 8 : ((planned >= 8 || K <= 5) ? 16 : RESCORE_KP);
-      int rc = tc_topk_search(q_hi, nullptr, db_hi, nullptr, Q, N, D, ldq_bf16, lddb_bf16, q_fold, db_fold, idx_base,
-                              kp, 1, nullptr, ws + a_bytes, t_bytes, debug_scores, st, &parts, fold_sorted, 2);
+      const uint64_t* cand = nullptr;
+      const uint32_t* tau = nullptr;
+      int kpm = 0;
+      int rc = rescore_filter_stage(q_hi, ldq_bf16, db_hi, lddb_bf16, Q, N, D, q_fold, db_fold, fold_sorted, idx_base, K,
+                                    reinterpret_cast<uint64_t*>(ws), ws + a_bytes, t_bytes, debug_scores, st, &cand, &kpm, &tau);
       if (rc != EMR2A_OK) return rc;
-      // several splits: re-score the 64 best approximate candidates of the query (rows outside the per-split
-      // lists are bounded by tau); one split: its 32 candidates are all there is
-      int kpm = kp;
-      const uint64_t* cand = parts.parts;
-      if (parts.splits > 1) {
-        kpm = RESCORE_KPM;
-        rc = emr2a_topk_merge(parts.parts, parts.splits, Q, kp, Q * kp, kp, kpm, approx, st);
-        if (rc != EMR2A_OK) return rc;
-        cand = approx;
-      }
-      return rescore_pipeline(cand, kpm, parts.tau, q_f32, ldq_f32, db_f32, lddb_f32, Q, N, D, idx_base, K, q_stats,
+      return rescore_pipeline(cand, kpm, tau, q_f32, ldq_f32, db_f32, lddb_f32, Q, N, D, idx_base, K, q_stats,
                               db_stats, q_fold, db_fold, out_keys, status, qflags, ws + a_bytes + t_bytes, r_bytes, st);
     }
     default:
@@ -189,4 +217,84 @@ extern "C" int emr2a_debug_topk_search_dump(const uint16_t* q_hi, const uint16_t
 extern "C" int emr2a_debug_unit_clocks(uint64_t* host_out, int64_t cap_units, int64_t* plan_out) {
   if (!host_out || !plan_out) return fail(EMR2A_ERR_INVALID, "debug_unit_clocks: null output");
   return tc_debug_unit_clocks(reinterpret_cast<unsigned long long*>(host_out), cap_units, plan_out);
+}
+
+// ---- cooperative shards: the RESCORE arm in stages, so that row shards verify ONE merged selection -------------------
+extern "C" size_t emr2a_topk_filter_workspace_bytes(int64_t Q, int64_t N, int D, int K) {
+  if (Q <= 0 || N <= 0 || K <= 0) return 256;
+  return align256(tc_topk_workspace_bytes(Q, N, RESCORE_KP, D));
+}
+
+extern "C" int emr2a_topk_filter(const uint16_t* q_hi, int64_t ldq_bf16, const uint16_t* db_hi, int64_t lddb_bf16, int64_t Q,
+                                 int64_t N, int D, const uint8_t* q_fold, const uint8_t* db_fold, int fold_sorted,
+                                 int64_t idx_base, int K, uint64_t* cand_out, uint32_t* tau_out, float* kth_out,
+                                 void* workspace, size_t ws_bytes, void* stream) {
+  if (Q < 0 || N < 0 || D <= 0 || K <= 0 || !cand_out || !tau_out) return fail(EMR2A_ERR_INVALID, "topk_filter: bad arguments");
+  if (K > 10) return fail(EMR2A_ERR_UNSUPPORTED, "topk_filter: K=%d > 10 (use EMR2A_PREC_BF16X3)", K);
+  if ((q_fold == nullptr) != (db_fold == nullptr)) return fail(EMR2A_ERR_INVALID, "topk_filter: q_fold and db_fold must be given together");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (Q == 0) return EMR2A_OK;
+  EMR2A_CUDA_TRY(cudaMemsetAsync(tau_out, 0, sizeof(uint32_t) * static_cast<size_t>(Q), st));
+  if (N == 0) {
+    const int64_t n = Q * RESCORE_KPM;
+    zero_keys_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(cand_out, n);
+    EMR2A_LAUNCH_CHECK("zero_keys_kernel");
+  } else {
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255)) return fail(EMR2A_ERR_INVALID, "topk_filter: workspace must be 256-byte aligned");
+    const uint64_t* cand = nullptr;
+    const uint32_t* tau = nullptr;
+    int kpm = 0;
+    int rc = rescore_filter_stage(q_hi, ldq_bf16, db_hi, lddb_bf16, Q, N, D, q_fold, db_fold, fold_sorted, idx_base, K,
+                                  cand_out, workspace, ws_bytes, nullptr, st, &cand, &kpm, &tau);
+    if (rc != EMR2A_OK) return rc;
+    if (cand != cand_out) {      // a single split: pad its list to the fixed candidate width
+      rc = emr2a_topk_merge(cand, 1, Q, kpm, Q * kpm, kpm, RESCORE_KPM, cand_out, st);
+      if (rc != EMR2A_OK) return rc;
+    }
+    if (tau) EMR2A_CUDA_TRY(cudaMemcpyAsync(tau_out, tau, sizeof(uint32_t) * static_cast<size_t>(Q), cudaMemcpyDeviceToDevice, st));
+  }
+  if (kth_out) return rescore_kth_scores(cand_out, RESCORE_KPM, K, Q, kth_out, st);
+  return EMR2A_OK;
+}
+
+extern "C" int emr2a_rescore_candidates(const uint64_t* cand, const uint32_t* tau, const float* kth_floor, const float* q_f32,
+                                        int64_t ldq_f32, const float* db_f32, int64_t lddb_f32, int64_t Q, int64_t N, int D,
+                                        int64_t idx_base, int K, const float* q_stats, const float* db_stats,
+                                        uint64_t* out_keys, float* bound_out, void* stream) {
+  if (!cand || !tau || !q_f32 || !db_f32 || !q_stats || !db_stats || !out_keys || !bound_out || Q < 0 || N < 0 || D <= 0 ||
+      K <= 0 || K > 10 || ldq_f32 < D || lddb_f32 < D)
+    return fail(EMR2A_ERR_INVALID, "rescore_candidates: bad arguments");
+  if (Q == 0) return EMR2A_OK;
+  return rescore_select_only(cand, RESCORE_KPM, tau, kth_floor, q_f32, ldq_f32, db_f32, lddb_f32, Q, N, D, idx_base, K,
+                             q_stats, db_stats, out_keys, bound_out, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int emr2a_verify_merged(const uint64_t* keys, int K, int64_t Q, const float* bounds, int parts,
+                                   int64_t bounds_stride, uint8_t* flags_out, int32_t* status_out, void* stream) {
+  if (!keys || !bounds || !flags_out || !status_out || K <= 0 || Q < 0 || parts <= 0 || bounds_stride < Q)
+    return fail(EMR2A_ERR_INVALID, "verify_merged: bad arguments");
+  if (Q == 0) return EMR2A_OK;
+  return rescore_verify_merged(keys, K, Q, bounds, parts, bounds_stride, flags_out, status_out, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t emr2a_exact_rescan_workspace_bytes(int n_flagged, int K) { return exact_rescan_workspace_bytes(n_flagged, K) + 256; }
+
+extern "C" int emr2a_exact_rescan(const float* q_f32, int64_t ldq_f32, const float* db_f32, int64_t lddb_f32, int64_t N, int D,
+                                  int64_t idx_base, int K, const uint8_t* q_fold, const uint8_t* db_fold,
+                                  const int32_t* flag_list, int n_flagged, uint64_t* out_keys, void* workspace,
+                                  size_t ws_bytes, void* stream) {
+  if (!q_f32 || !db_f32 || !out_keys || N < 0 || D <= 0 || K <= 0 || n_flagged < 0 || ldq_f32 < D || lddb_f32 < D ||
+      (n_flagged > 0 && !flag_list))
+    return fail(EMR2A_ERR_INVALID, "exact_rescan: bad arguments");
+  if ((q_fold == nullptr) != (db_fold == nullptr)) return fail(EMR2A_ERR_INVALID, "exact_rescan: q_fold and db_fold must be given together");
+  if (n_flagged == 0) return EMR2A_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (N == 0) {
+    const int64_t n = static_cast<int64_t>(n_flagged) * K;
+    zero_keys_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(out_keys, n);
+    EMR2A_LAUNCH_CHECK("zero_keys_kernel");
+    return EMR2A_OK;
+  }
+  return rescore_exact_rescan(q_f32, ldq_f32, db_f32, lddb_f32, N, D, idx_base, K, q_fold, db_fold, flag_list, n_flagged,
+                              out_keys, workspace, ws_bytes, st);
 }

@@ -47,11 +47,22 @@ struct RescoreParams {
   int* flag_list;
   int cap;
   uint8_t* qflags;          // optional [Q]: 1 = selection not verified by the bound (valid even when the list overflows)
+  // cooperative shards (emr2a_rescore_select): the verification is made by the caller on the merged lists
+  const float* kth_floor;   // optional [Q]: lower bound of the GLOBAL K-th best filter score (max over the shards' local K-th)
+  float* bound_out;         // optional [Q]: upper bound of the exact score of every row of THIS shard that was not re-scored
+                            //               because it is not a candidate (tau + E); -inf if there is no such row
   // exact re-scan
   const uint8_t* q_fold;
   const uint8_t* db_fold;
   uint64_t* fb_parts;       // [blocks][cap][K]
+  int n_fixed;              // >= 0: the flag list holds exactly this many queries (emr2a_exact_rescan); < 0: status[0]
+  int compact;              // != 0: the re-scan writes list i of the flag list to out[i][K] instead of out[flag_list[i]][K]
 };
+
+__device__ __forceinline__ int flagged_count(const RescoreParams& p) {
+  int n = p.n_fixed >= 0 ? p.n_fixed : p.status[0];
+  return n > p.cap ? p.cap : n;
+}
 
 template <bool VEC>
 __device__ __forceinline__ float lane_dot(const float* __restrict__ a, const float* __restrict__ b, int D, int lane) {
@@ -124,7 +135,9 @@ __global__ void __launch_bounds__(256) rescore_select_kernel(const RescoreParams
   query_norms(qrow, p.D, lane, p.q_stats, nq, rq);
   const float E = error_bound(nq, rq, p.db_stats, p.D);
   const uint64_t kth_approx = __shfl_sync(0xffffffffu, akey[0], p.K - 1);
-  const float cut = kth_approx != 0ull ? key_score(kth_approx) - 2.0f * E : -INFINITY;
+  float kth_lb = kth_approx != 0ull ? key_score(kth_approx) : -INFINITY;
+  if (p.kth_floor != nullptr) kth_lb = fmaxf(kth_lb, __ldg(p.kth_floor + q));      // another shard already holds K better rows
+  const float cut = kth_lb - 2.0f * E;
   bool done = false;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -202,6 +215,10 @@ __global__ void __launch_bounds__(256) rescore_select_kernel(const RescoreParams
     const uint32_t t = __ldcg(p.tau + q);
     if (t != 0u) { tau = fmaxf(tau, unorder_f32(t)); bounded = true; }
   }
+  if (p.bound_out != nullptr) {               // cooperative shards: publish the bound, the caller verifies globally
+    if (lane == 0) p.bound_out[q] = bounded ? tau + E : -INFINITY;
+    return;
+  }
   bool ok = true;
   if (bounded) {
     const uint64_t kth = __shfl_sync(0xffffffffu, mine, p.K - 1);
@@ -223,8 +240,7 @@ constexpr int FB_GMAX = 8;
 template <bool VEC>
 __global__ void __launch_bounds__(FB_WARPS * 32) exact_rescan_kernel(const RescoreParams p, int G) {
   extern __shared__ __align__(16) unsigned char fb_smem[];
-  int n = p.status[0];
-  if (n > p.cap) n = p.cap;
+  const int n = flagged_count(p);
   if (n <= 0) return;
   float* qbuf = reinterpret_cast<float*>(fb_smem);                                   // [G][Dp]
   const int Dp = (p.D + 3) & ~3;
@@ -288,13 +304,12 @@ __global__ void __launch_bounds__(FB_WARPS * 32) exact_rescan_kernel(const Resco
 }
 
 __global__ void __launch_bounds__(256) rescan_merge_kernel(const RescoreParams p, int blocks) {
-  int n = p.status[0];
-  if (n > p.cap) n = p.cap;
+  const int n = flagged_count(p);
   const int lane = threadIdx.x & 31;
   const int i = static_cast<int>((static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
   if (i >= n) return;
   const int K = p.K;
-  const int64_t qd = p.flag_list[i];
+  const int64_t qd = p.compact ? i : p.flag_list[i];
   uint64_t bound = ~0ull;
   for (int rnk = 0; rnk < K; ++rnk) {
     uint64_t best = 0ull;
@@ -309,6 +324,65 @@ __global__ void __launch_bounds__(256) rescan_merge_kernel(const RescoreParams p
     bound = best;
     if (lane == 0) p.out[qd * K + rnk] = best;
   }
+}
+
+// [Q] local K-th best filter score (-inf if the list is shorter) -- what the shards exchange (max) before re-scoring
+__global__ void __launch_bounds__(256) kth_score_kernel(const uint64_t* __restrict__ approx, int KP, int K, int64_t Q,
+                                                        float* __restrict__ kth) {
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  const uint64_t k = K <= KP ? approx[q * KP + K - 1] : 0ull;
+  kth[q] = k != 0ull ? key_score(k) : -INFINITY;
+}
+
+// merged lists of all shards + every shard's bound: flag the queries whose exact K-th best does not clear every bound
+__global__ void __launch_bounds__(256) verify_merged_kernel(const uint64_t* __restrict__ keys, int K, int64_t Q,
+                                                            const float* __restrict__ bounds, int parts,
+                                                            int64_t bounds_stride, uint8_t* __restrict__ flags,
+                                                            int* __restrict__ count) {
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  float b = -INFINITY;
+  for (int p = 0; p < parts; ++p) b = fmaxf(b, bounds[static_cast<int64_t>(p) * bounds_stride + q]);
+  const uint64_t kth = keys[q * K + K - 1];
+  const bool ok = (b == -INFINITY) || (kth != 0ull && key_score(kth) > b);
+  flags[q] = ok ? 0 : 1;
+  if (!ok) { atomicAdd(count, 1); count[1] = 1; }      // [1]: the merged selection needs the exact re-scan
+}
+
+int rescore_kth_scores(const uint64_t* approx, int KP, int K, int64_t Q, float* kth, cudaStream_t st) {
+  kth_score_kernel<<<static_cast<unsigned>((Q + 255) / 256), 256, 0, st>>>(approx, KP, K, Q, kth);
+  EMR2A_LAUNCH_CHECK("kth_score_kernel");
+  return EMR2A_OK;
+}
+
+// re-score only (no local verification, no re-scan): exact keys of the candidates that clear the (global) cut + bound_out
+int rescore_select_only(const uint64_t* approx, int KP, const uint32_t* tau, const float* kth_floor, const float* q,
+                        int64_t ldq, const float* db, int64_t lddb, int64_t Q, int64_t N, int D, int64_t idx_base, int K,
+                        const float* q_stats, const float* db_stats, uint64_t* out_keys, float* bound_out, cudaStream_t st) {
+  RescoreParams p{};
+  p.approx = approx; p.KP = KP; p.tau = tau; p.q = q; p.ldq = ldq; p.db = db; p.lddb = lddb; p.Q = Q; p.N = N; p.D = D;
+  p.idx_base = idx_base; p.K = K; p.q_stats = q_stats; p.db_stats = db_stats; p.out = out_keys;
+  p.kth_floor = kth_floor; p.bound_out = bound_out;
+  auto al16 = [](const void* x) { return (reinterpret_cast<uintptr_t>(x) & 15) == 0; };
+  const bool vec = (D % 4 == 0) && (ldq % 4 == 0) && (lddb % 4 == 0) && al16(q) && al16(db);
+  if (Q <= 4 * static_cast<int64_t>(sm_count())) {
+    if (vec) rescore_select_kernel<true, 8><<<static_cast<unsigned>(Q), 256, 0, st>>>(p);
+    else rescore_select_kernel<false, 8><<<static_cast<unsigned>(Q), 256, 0, st>>>(p);
+  } else {
+    const unsigned blocks = static_cast<unsigned>((Q * 32 + 255) / 256);
+    if (vec) rescore_select_kernel<true, 1><<<blocks, 256, 0, st>>>(p);
+    else rescore_select_kernel<false, 1><<<blocks, 256, 0, st>>>(p);
+  }
+  EMR2A_LAUNCH_CHECK("rescore_select_kernel");
+  return EMR2A_OK;
+}
+
+int rescore_verify_merged(const uint64_t* keys, int K, int64_t Q, const float* bounds, int parts, int64_t bounds_stride,
+                          uint8_t* flags, int* count, cudaStream_t st) {
+  verify_merged_kernel<<<static_cast<unsigned>((Q + 255) / 256), 256, 0, st>>>(keys, K, Q, bounds, parts, bounds_stride, flags, count);
+  EMR2A_LAUNCH_CHECK("verify_merged_kernel");
+  return EMR2A_OK;
 }
 
 int rescore_fallback_blocks() { return 2 * sm_count(); }
@@ -328,6 +402,27 @@ size_t rescore_workspace_bytes(int64_t Q, int K) {
          sizeof(uint64_t) * static_cast<size_t>(rescore_fallback_blocks()) * cap * K + 256;
 }
 
+static int launch_rescan(const RescoreParams& p, bool vec, cudaStream_t st) {
+  const int D = p.D, K = p.K;
+  const int Dp = (D + 3) & ~3;
+  int G = static_cast<int>((96 * 1024) / (sizeof(float) * Dp));
+  if (G > FB_GMAX) G = FB_GMAX;
+  if (G < 1) return fail(EMR2A_ERR_UNSUPPORTED, "topk_search(rescore): D=%d too large for the exact re-scan", D);
+  const size_t smem = sizeof(float) * G * Dp + sizeof(uint64_t) * FB_WARPS * G * K;
+  const int fb_blocks = rescore_fallback_blocks();
+  if (vec) {
+    EMR2A_CUDA_TRY(cudaFuncSetAttribute(exact_rescan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    exact_rescan_kernel<true><<<fb_blocks, FB_WARPS * 32, smem, st>>>(p, G);
+  } else {
+    EMR2A_CUDA_TRY(cudaFuncSetAttribute(exact_rescan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    exact_rescan_kernel<false><<<fb_blocks, FB_WARPS * 32, smem, st>>>(p, G);
+  }
+  EMR2A_LAUNCH_CHECK("exact_rescan_kernel");
+  rescan_merge_kernel<<<static_cast<unsigned>((static_cast<int64_t>(p.cap) * 32 + 255) / 256), 256, 0, st>>>(p, fb_blocks);
+  EMR2A_LAUNCH_CHECK("rescan_merge_kernel");
+  return EMR2A_OK;
+}
+
 // approx: merged approximate keys [Q][KP]; writes exact keys [Q][K]; status[0..1] must be zeroed by the caller.
 int rescore_pipeline(const uint64_t* approx, int KP, const uint32_t* tau, const float* q, int64_t ldq, const float* db,
                      int64_t lddb, int64_t Q, int64_t N, int D, int64_t idx_base, int K, const float* q_stats,
@@ -340,6 +435,7 @@ int rescore_pipeline(const uint64_t* approx, int KP, const uint32_t* tau, const 
   p.approx = approx; p.KP = KP; p.tau = tau; p.q = q; p.ldq = ldq; p.db = db; p.lddb = lddb; p.Q = Q; p.N = N; p.D = D;
   p.idx_base = idx_base; p.K = K; p.q_stats = q_stats; p.db_stats = db_stats; p.out = out_keys; p.status = status;
   p.cap = rescore_cap(Q);
+  p.n_fixed = -1;
   p.qflags = qflags;
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   p.flag_list = reinterpret_cast<int*>(ws);
@@ -358,23 +454,28 @@ int rescore_pipeline(const uint64_t* approx, int KP, const uint32_t* tau, const 
   }
   EMR2A_LAUNCH_CHECK("rescore_select_kernel");
   // exact re-scan of unverified queries; both kernels return at once when status[0] == 0
-  const int Dp = (D + 3) & ~3;
-  int G = static_cast<int>((96 * 1024) / (sizeof(float) * Dp));
-  if (G > FB_GMAX) G = FB_GMAX;
-  if (G < 1) return fail(EMR2A_ERR_UNSUPPORTED, "topk_search(rescore): D=%d too large for the exact re-scan", D);
-  const size_t smem = sizeof(float) * G * Dp + sizeof(uint64_t) * FB_WARPS * G * K;
-  const int fb_blocks = rescore_fallback_blocks();
-  if (vec) {
-    EMR2A_CUDA_TRY(cudaFuncSetAttribute(exact_rescan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    exact_rescan_kernel<true><<<fb_blocks, FB_WARPS * 32, smem, st>>>(p, G);
-  } else {
-    EMR2A_CUDA_TRY(cudaFuncSetAttribute(exact_rescan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    exact_rescan_kernel<false><<<fb_blocks, FB_WARPS * 32, smem, st>>>(p, G);
-  }
-  EMR2A_LAUNCH_CHECK("exact_rescan_kernel");
-  rescan_merge_kernel<<<static_cast<unsigned>((static_cast<int64_t>(p.cap) * 32 + 255) / 256), 256, 0, st>>>(p, fb_blocks);
-  EMR2A_LAUNCH_CHECK("rescan_merge_kernel");
-  return EMR2A_OK;
+  return launch_rescan(p, vec, st);
+}
+
+// The exact re-scan alone, for a flag list the caller holds (cooperative shards: the queries the MERGED lists could not
+// verify are re-searched exactly on every shard, the compact lists [n_flagged][K] are merged by the caller).
+size_t exact_rescan_workspace_bytes(int n_flagged, int K) {
+  return sizeof(uint64_t) * static_cast<size_t>(rescore_fallback_blocks()) * static_cast<size_t>(n_flagged > 0 ? n_flagged : 1) * K + 256;
+}
+
+int rescore_exact_rescan(const float* q, int64_t ldq, const float* db, int64_t lddb, int64_t N, int D, int64_t idx_base, int K,
+                         const uint8_t* q_fold, const uint8_t* db_fold, const int* flag_list, int n_flagged,
+                         uint64_t* out_compact, void* workspace, size_t ws_bytes, cudaStream_t st) {
+  if (n_flagged <= 0) return EMR2A_OK;
+  if (!workspace || exact_rescan_workspace_bytes(n_flagged, K) > ws_bytes) return fail(EMR2A_ERR_WORKSPACE, "exact_rescan: workspace too small");
+  RescoreParams p{};
+  p.q = q; p.ldq = ldq; p.db = db; p.lddb = lddb; p.N = N; p.D = D; p.idx_base = idx_base; p.K = K; p.out = out_compact;
+  p.flag_list = const_cast<int*>(flag_list); p.cap = n_flagged; p.n_fixed = n_flagged; p.compact = 1;
+  p.q_fold = q_fold; p.db_fold = db_fold;
+  p.fb_parts = reinterpret_cast<uint64_t*>(workspace);
+  auto al16 = [](const void* x) { return (reinterpret_cast<uintptr_t>(x) & 15) == 0; };
+  const bool vec = (D % 4 == 0) && (ldq % 4 == 0) && (lddb % 4 == 0) && al16(q) && al16(db);
+  return launch_rescan(p, vec, st);
 }
 
 }  // namespace emr2a

@@ -5,6 +5,7 @@ inside the keys, and ties break on the global index, so results are bit-identica
 GPU count."""
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -43,9 +44,15 @@ def sharded_search_and_vote(eng, db_segs_local: Sequence, q_segs: Sequence, db_l
                             q_weights=(1.0, 1.0), k_list=(1, 3, 5), precision: str = "auto",
                             q_fold=None, db_fold_local=None, q_group=None, n_groups: int = 1,
                             want_lists: bool = True, timers: Optional[dict] = None,
-                            defer_status: bool = False) -> Dict[str, torch.Tensor]:
+                            defer_status: bool = False, cooperative: bool = True) -> Dict[str, torch.Tensor]:
     """Each rank: K1 on its database shard and on the (replicated) queries, local K2 with
-    ``idx_base = row_offset``; all-gather keys; K3 merge; K4 vote on the merged lists."""
+    ``idx_base = row_offset``; all-gather keys; K3 merge; K4 vote on the merged lists.
+
+    With the ``rescore`` arithmetic the shards work COOPERATIVELY (``_cooperative_search_and_vote``): they exchange
+    their K-th best filter score before re-scoring, so a shard only re-scores the candidates that can still reach the
+    global Top-K, and the verification is made once on the merged lists -- the per-rank cost of the exact stage shrinks
+    with the shard instead of staying at 64 candidates per query.  ``cooperative=False`` (or ``EMR2A_COOP_SHARDS=0``)
+    keeps every shard's search self-contained; both give bit-identical results."""
     n_q = int(q_segs[0].shape[0])
     n_db = int(db_segs_local[0].shape[0])
     dim = sum(int(s.shape[1]) for s in db_segs_local if s is not None)
@@ -53,6 +60,9 @@ def sharded_search_and_vote(eng, db_segs_local: Sequence, q_segs: Sequence, db_l
     prec = eng.pick_precision(n_q, max(n_db, 1) * world, dim, k, precision)
     db = eng.prepare(db_segs_local[0], db_segs_local[1] if len(db_segs_local) > 1 else None, 1.0, 1.0, db_flags, prec)
     qs = eng.prepare(q_segs[0], q_segs[1] if len(q_segs) > 1 else None, q_weights[0], q_weights[1], q_flags, prec)
+    if prec == "rescore" and world > 1 and cooperative and os.environ.get("EMR2A_COOP_SHARDS", "1") != "0":
+        return _cooperative_search_and_vote(eng, qs, db, db_labels_global, q_labels, n_classes, k, row_offset, k_list,
+                                            q_fold, db_fold_local, q_group, n_groups, want_lists, timers, defer_status)
     if timers is not None:
         timers["k2_start"].record()
     keys = eng.topk_search(qs, db, k, prec, q_fold=q_fold, db_fold=db_fold_local, idx_base=row_offset)
@@ -84,6 +94,48 @@ def sharded_search_and_vote(eng, db_segs_local: Sequence, q_segs: Sequence, db_l
                                            row_offset, db_flags, q_flags, q_weights, k_list, "bf16x3", q_fold,
                                            db_fold_local, q_group, n_groups, want_lists, timers)
         res["unverified"] = int(st[0])
+    return res
+
+
+def _cooperative_search_and_vote(eng, qs, db, db_labels_global, q_labels, n_classes, k, row_offset, k_list, q_fold,
+                                 db_fold_local, q_group, n_groups, want_lists, timers, defer_status):
+    """The staged K2 of include/emr2a.h ("cooperative row shards") around two collectives:
+        filter (tensor cores)  ->  all-reduce MAX of the local K-th best filter score (4*Q bytes)
+        ->  exact re-scoring of the candidates above the global cut  ->  all-gather of exact keys + bounds
+        ->  K3 merge  ->  verification of the MERGED selection  ->  K4 vote.
+    Queries the merged lists cannot verify (rare: the global K-th best clears a shard's bound far more easily than a
+    shard's own K-th best does) are re-searched exactly on every shard after the vote and patched in."""
+    n_q = qs.n
+    if timers is not None:
+        timers["k2_start"].record()
+    cand, tau, kth = eng.topk_filter(qs, db, k, q_fold=q_fold, db_fold=db_fold_local, idx_base=row_offset)
+    if timers is not None:
+        timers["k2_end"].record()                  # the dominant kernel: tensor-core filter + merge of its partial lists
+    dist.all_reduce(kth, op=dist.ReduceOp.MAX)
+    payload = eng.rescore_candidates(cand, tau, kth, qs, db, k, idx_base=row_offset)
+    allp = gather_keys(payload.unsqueeze(0)).squeeze(1)                  # [world, Q*K + ceil(Q/2)]
+    keys = eng.merge_payload(allp, n_q, k)
+    flags, status = eng.verify_merged(keys, allp, k)
+
+    def vote(kk):
+        return eng.vote_metrics(kk, db_labels_global, q_labels, n_classes, k_list=k_list, q_group=q_group,
+                                n_groups=n_groups, want_lists=want_lists)
+
+    res = vote(keys)
+    res["precision"] = "rescore"
+    res["keys"] = keys
+    if defer_status:
+        res["status"] = status          # [1] != 0: some query needs the repair below -- the caller must not use the step
+        return res
+    n_flagged = int(status.cpu()[0])    # the step's only host synchronisation; identical on every rank
+    if n_flagged:
+        idx = torch.nonzero(flags).squeeze(1).to(torch.int32)
+        comp = eng.exact_rescan(qs, db, idx, k, idx_base=row_offset, q_fold=q_fold, db_fold=db_fold_local)
+        keys.index_copy_(0, idx.long(), eng.topk_merge(gather_keys(comp), k))
+        res = vote(keys)
+        res["precision"] = "rescore"
+        res["keys"] = keys
+    res["unverified"] = n_flagged
     return res
 
 

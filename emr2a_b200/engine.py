@@ -296,6 +296,117 @@ class Engine:
             self.launches += 1
         return keys
 
+    # ------------------------------------------------ K2 in stages (cooperative row shards, include/emr2a.h)
+    CAND_WIDTH = 64
+
+    def topk_filter(self, q: Operand, db: Operand, k: int, q_fold=None, db_fold=None, fold_sorted: bool = False,
+                    idx_base: int = 0) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Stage 1: tensor-core filter of this shard.  Returns (cand int64 [Q, 64], tau int32 [Q], kth float32 [Q])."""
+        if q.hi is None or db.hi is None:
+            raise ValueError("topk_filter needs bf16 operand planes")
+        if k > _RESCORE_MAX_K:
+            raise ValueError(f"topk_filter: K={k} > {_RESCORE_MAX_K}")
+        Q, N, D = q.n, db.n, q.dim
+        cand = torch.empty((Q, self.CAND_WIDTH), dtype=torch.int64, device=self.device)
+        tau = torch.empty((Q,), dtype=torch.int32, device=self.device)
+        kth = torch.empty((Q,), dtype=torch.float32, device=self.device)
+        if Q == 0:
+            return cand, tau, kth
+        ws_bytes = int(self.lib.emr2a_topk_filter_workspace_bytes(Q, N, D, k))
+        ws = torch.empty((ws_bytes + 256,), dtype=torch.uint8, device=self.device)
+        if q_fold is not None:
+            q_fold = self.to_device(q_fold, torch.uint8)
+            db_fold = self.to_device(db_fold, torch.uint8)
+        with torch.cuda.device(self.device):
+            native.check(self.lib.emr2a_topk_filter(
+                q.hi.data_ptr(), _ld(q.hi), db.hi.data_ptr() if N else None, _ld(db.hi) if N else 0, Q, N, D,
+                native.ptr(q_fold), native.ptr(db_fold), int(fold_sorted), int(idx_base), int(k),
+                cand.data_ptr(), tau.data_ptr(), kth.data_ptr(), _round_up(ws.data_ptr(), 256), ws_bytes, self._stream()))
+        self.launches += 3
+        return cand, tau, kth
+
+    def rescore_candidates(self, cand: torch.Tensor, tau: torch.Tensor, kth_floor: Optional[torch.Tensor], q: Operand,
+                           db: Operand, k: int, idx_base: int = 0) -> torch.Tensor:
+        """Stage 3: exact fp32 scores of the candidates that can reach the global Top-K.  Returns ONE int64 buffer
+        [Q*k + ceil(Q/2)] -- the shard's exact keys [Q, k] followed by its float32 bounds [Q] -- so that keys and
+        bounds travel in a single all-gather (``split_payload`` takes it apart)."""
+        if q.f32 is None or db.f32 is None or q.stats is None or db.stats is None:
+            raise ValueError("rescore_candidates needs fp32 operands prepared with stats")
+        Q, N, D = q.n, db.n, q.dim
+        payload = torch.zeros((Q * k + (Q + 1) // 2,), dtype=torch.int64, device=self.device)
+        if Q == 0:
+            return payload
+        keys, bounds = self.split_payload(payload, Q, k)
+        if N == 0:
+            bounds.fill_(float("-inf"))
+            return payload
+        with torch.cuda.device(self.device):
+            native.check(self.lib.emr2a_rescore_candidates(
+                cand.data_ptr(), tau.data_ptr(), native.ptr(kth_floor), q.f32.data_ptr(), _ld(q.f32), db.f32.data_ptr(),
+                _ld(db.f32), Q, N, D, int(idx_base), int(k), q.stats.data_ptr(), db.stats.data_ptr(), keys.data_ptr(),
+                bounds.data_ptr(), self._stream()))
+        self.launches += 1
+        return payload
+
+    @staticmethod
+    def split_payload(payload: torch.Tensor, Q: int, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """payload [..., Q*k + ceil(Q/2)] int64 -> (keys [..., Q, k] int64, bounds [..., Q] float32), both views."""
+        lead = payload.shape[:-1]
+        keys = payload[..., :Q * k].unflatten(-1, (Q, k)) if lead else payload[:Q * k].view(Q, k)
+        bounds = payload[..., Q * k:].view(torch.float32)[..., :Q]
+        return keys, bounds
+
+    def verify_merged(self, keys: torch.Tensor, all_payload: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Stage 5.  ``keys`` [Q, k]: the merged exact lists; ``all_payload`` [P, Q*k + ceil(Q/2)]: the gathered stage-3
+        buffers.  Returns (flags uint8 [Q], status int32 [4]); status[0] = number of flagged queries."""
+        Q = int(keys.shape[0])
+        P, width = all_payload.shape
+        flags = torch.zeros((Q,), dtype=torch.uint8, device=self.device)
+        status = torch.zeros((4,), dtype=torch.int32, device=self.device)
+        if Q:
+            bounds_ptr = all_payload.data_ptr() + 8 * Q * k
+            with torch.cuda.device(self.device):
+                native.check(self.lib.emr2a_verify_merged(keys.data_ptr(), int(k), Q, bounds_ptr, int(P),
+                                                          int(all_payload.stride(0)) * 2, flags.data_ptr(),
+                                                          status.data_ptr(), self._stream()))
+            self.launches += 1
+        return flags, status
+
+    def merge_payload(self, all_payload: torch.Tensor, Q: int, k: int) -> torch.Tensor:
+        """Stage 4: K3 merge of the key part of the gathered stage-3 buffers [P, Q*k + ceil(Q/2)] -> [Q, k]."""
+        P = int(all_payload.shape[0])
+        out = torch.empty((Q, k), dtype=torch.int64, device=self.device)
+        if Q:
+            with torch.cuda.device(self.device):
+                native.check(self.lib.emr2a_topk_merge(all_payload.data_ptr(), P, Q, k, int(all_payload.stride(0)), k, k,
+                                                       out.data_ptr(), self._stream()))
+            self.launches += 1
+        return out
+
+    def exact_rescan(self, q: Operand, db: Operand, flag_list: torch.Tensor, k: int, idx_base: int = 0, q_fold=None,
+                     db_fold=None) -> torch.Tensor:
+        """Stage 6: exact fp32 search of this shard for the queries in ``flag_list`` (int32, the same on every shard).
+        Returns compact keys [n_flagged, k]."""
+        flag_list = self.to_device(flag_list, torch.int32)
+        n = int(flag_list.shape[0])
+        out = torch.zeros((n, k), dtype=torch.int64, device=self.device)
+        if n == 0:
+            return out
+        if q.f32 is None or (db.n and db.f32 is None):
+            raise ValueError("exact_rescan needs fp32 operands")
+        ws_bytes = int(self.lib.emr2a_exact_rescan_workspace_bytes(n, k))
+        ws = torch.empty((ws_bytes + 256,), dtype=torch.uint8, device=self.device)
+        if q_fold is not None:
+            q_fold = self.to_device(q_fold, torch.uint8)
+            db_fold = self.to_device(db_fold, torch.uint8)
+        with torch.cuda.device(self.device):
+            native.check(self.lib.emr2a_exact_rescan(
+                q.f32.data_ptr(), _ld(q.f32), db.f32.data_ptr() if db.n else q.f32.data_ptr(), _ld(db.f32) if db.n else q.dim,
+                db.n, q.dim, int(idx_base), int(k), native.ptr(q_fold), native.ptr(db_fold), flag_list.data_ptr(), n,
+                out.data_ptr(), _round_up(ws.data_ptr(), 256), ws_bytes, self._stream()))
+        self.launches += 2
+        return out
+
     def pop_status_tensor(self) -> Optional[torch.Tensor]:
         """Device-side status (int32[4], element-wise max over the pending rescore searches) without a
         host synchronisation; the caller decides when to look at it."""

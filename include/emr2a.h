@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define EMR2A_ABI_VERSION 8
+#define EMR2A_ABI_VERSION 9
 
 enum emr2a_status {
   EMR2A_OK = 0,
@@ -175,6 +175,56 @@ int emr2a_topk_search(const float* q_f32, int64_t ldq_f32,
                       const float* q_stats, const float* db_stats,
                       uint64_t* out_keys, int32_t* status_out, uint8_t* unverified_out,
                       void* workspace, size_t ws_bytes, void* stream);
+
+/*
+ * K2 in stages for COOPERATIVE ROW SHARDS (EMR2A_PREC_BF16_RESCORE arithmetic).  When the database is row-sharded
+ * over GPUs, emr2a_topk_search on every shard re-scores 64 candidates per query and verifies its LOCAL selection --
+ * work that does not shrink with the shard.  The staged calls let the shards verify ONE merged selection instead
+ * (the reference scores every query against the whole database, utils/cv_evaluator.py:112,123 -- a shard only has
+ * to contribute the rows that can reach the GLOBAL Top-K):
+ *   1. emr2a_topk_filter        tensor-core filter of the shard: cand_out [Q, 64] approximate keys (best first, 0 =
+ *                               empty), tau_out [Q] (order-preserving image of the largest filter score a row outside
+ *                               the candidate lists can have; 0 = none), kth_out [Q] (nullable) = the shard's K-th
+ *                               best FILTER score (-inf if it holds fewer than K admissible rows);
+ *   2. the caller reduces kth_out with MAX over the shards (NCCL all-reduce, 4*Q bytes): a lower bound of the global
+ *      K-th best filter score, because the shard that attains the maximum alone holds K rows at or above it;
+ *   3. emr2a_rescore_candidates exact fp32 scores of the candidates whose filter score is >= kth_floor - 2E (E = the
+ *                               per-query error bound of csrc/rescore.cu); a candidate below that cannot be among the
+ *                               exact global K best.  out_keys [Q, K]: the shard's exact best; bound_out [Q]: an
+ *                               upper bound (tau + E) of the exact score of every shard row that is NOT a candidate,
+ *                               -inf if every admissible row is one.  kth_floor may be NULL (single shard);
+ *   4. the caller all-gathers out_keys and bound_out and merges the keys (emr2a_topk_merge);
+ *   5. emr2a_verify_merged      flags_out [Q] = 1 where the merged exact K-th best does not exceed EVERY shard's
+ *                               bound (bounds[p * bounds_stride + q]), status_out[0] += the number of such queries
+ *                               (zero it first).  Unflagged queries are exact: the rows not re-scored either are
+ *                               candidates cut in step 3 or are bounded by bound_out;
+ *   6. emr2a_exact_rescan       for the (rare) flagged queries: flag_list [n_flagged] query numbers (identical, in
+ *                               the same order, on every shard); exact fp32 search of the whole shard, compact
+ *                               lists out_keys [n_flagged, K]; the caller merges them across shards and writes
+ *                               them over the flagged rows.
+ * Results are bit-identical to emr2a_topk_search on the unsharded database (same fp32 re-scoring arithmetic, same
+ * tie rule).  Operand requirements are those of EMR2A_PREC_BF16_RESCORE (K <= 10).
+ */
+size_t emr2a_topk_filter_workspace_bytes(int64_t Q, int64_t N, int D, int K);
+int emr2a_topk_filter(const uint16_t* q_hi, int64_t ldq_bf16, const uint16_t* db_hi, int64_t lddb_bf16,
+                      int64_t Q, int64_t N, int D,
+                      const uint8_t* q_fold, const uint8_t* db_fold, int fold_sorted,
+                      int64_t idx_base, int K,
+                      uint64_t* cand_out, uint32_t* tau_out, float* kth_out,
+                      void* workspace, size_t ws_bytes, void* stream);
+int emr2a_rescore_candidates(const uint64_t* cand, const uint32_t* tau, const float* kth_floor,
+                             const float* q_f32, int64_t ldq_f32, const float* db_f32, int64_t lddb_f32,
+                             int64_t Q, int64_t N, int D, int64_t idx_base, int K,
+                             const float* q_stats, const float* db_stats,
+                             uint64_t* out_keys, float* bound_out, void* stream);
+int emr2a_verify_merged(const uint64_t* keys, int K, int64_t Q, const float* bounds, int parts,
+                        int64_t bounds_stride, uint8_t* flags_out, int32_t* status_out, void* stream);
+size_t emr2a_exact_rescan_workspace_bytes(int n_flagged, int K);
+int emr2a_exact_rescan(const float* q_f32, int64_t ldq_f32, const float* db_f32, int64_t lddb_f32,
+                       int64_t N, int D, int64_t idx_base, int K,
+                       const uint8_t* q_fold, const uint8_t* db_fold,
+                       const int32_t* flag_list, int n_flagged,
+                       uint64_t* out_keys, void* workspace, size_t ws_bytes, void* stream);
 
 /*
  * K3 -- merge `parts` partial Top-K lists per query into one.  Every input list must be sorted

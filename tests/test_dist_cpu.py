@@ -204,3 +204,154 @@ def test_sharded_cv_world2_equals_single_process():
         for layout in ("contiguous", "balanced"):                                 # any sharding, same result
             for key, want in single.items():
                 assert np.array_equal(outs[rank][layout][key], want), (rank, layout, key)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# dist.sharded_search_and_vote, cooperative row shards ("K2 in stages", include/emr2a.h) under gloo: the two
+# collectives (all-reduce MAX of the K-th best filter score, all-gather of exact keys + bounds in ONE buffer), the
+# verification of the merged lists and the repair of flagged queries -- with a numpy stand-in for the staged kernels
+# whose "filter" is the exact score plus a bounded perturbation (|s~ - s| <= E), as the bf16 filter is.
+class _CoopStub(_StubEngine):
+    E = np.float32(0.02)
+    WIDTH = 12                                   # candidates per query and shard (64 on the GPU)
+
+    def pick_precision(self, q, n, d, k, requested="auto"):
+        return "rescore"
+
+    def _scores(self, qs, db, q_fold, db_fold):
+        sc = (qs.f32.numpy().astype(np.float64) @ db.f32.numpy().astype(np.float64).T).astype(np.float32)
+        if q_fold is not None:
+            sc = np.where(q_fold.numpy()[:, None] == db_fold.numpy()[None, :], -np.inf, sc)
+        return sc
+
+    def topk_filter(self, qs, db, k, q_fold=None, db_fold=None, fold_sorted=False, idx_base=0):
+        sc = self._scores(qs, db, q_fold, db_fold)
+        gidx = np.arange(sc.shape[1]) + idx_base
+        noise = (((np.arange(sc.shape[0])[:, None] * 7919 + gidx[None, :] * 104729) % 2001) / 1000.0 - 1.0).astype(np.float32)
+        approx = sc + self.E * noise                                              # deterministic, |error| <= E
+        w = self.WIDTH
+        order = np.argsort(-approx, axis=1, kind="stable")
+        top = np.take_along_axis(approx, order, axis=1)
+        cand = np.zeros((sc.shape[0], w), dtype=np.int64)
+        kk = min(w, sc.shape[1])
+        cand[:, :kk] = np.where(np.isfinite(top[:, :kk]), _pack(top[:, :kk], order[:, :kk] + idx_base), 0)
+        tau = np.full(sc.shape[0], -np.inf, dtype=np.float32)                     # best filter score outside the list
+        if sc.shape[1] > w:
+            tau = top[:, w].astype(np.float32)
+        kth = top[:, k - 1].astype(np.float32) if sc.shape[1] >= k else np.full(sc.shape[0], -np.inf, dtype=np.float32)
+        kth = np.where(np.isfinite(kth), kth, -np.inf).astype(np.float32)
+        self.launches += 3
+        return torch.from_numpy(cand), torch.from_numpy(tau), torch.from_numpy(kth)
+
+    def rescore_candidates(self, cand, tau, kth_floor, qs, db, k, idx_base=0):
+        from emr2a_b200.engine import Engine
+        Q = qs.n
+        u = cand.numpy().view(np.uint64)
+        bits = (u >> np.uint64(32)).astype(np.uint32)
+        fb = np.where(bits & np.uint32(0x80000000), bits ^ np.uint32(0x80000000), ~bits).astype(np.uint32)
+        approx = np.where(u == 0, -np.inf, fb.view(np.float32))
+        idx = (np.uint64(0xFFFFFFFF) - (u & np.uint64(0xFFFFFFFF))).astype(np.int64) - idx_base
+        local_kth = approx[:, k - 1] if approx.shape[1] >= k else np.full(Q, -np.inf)
+        cut = np.maximum(local_kth, kth_floor.numpy()) - 2 * self.E
+        exact = np.full(approx.shape, -np.inf, dtype=np.float32)
+        qf, df = qs.f32.numpy().astype(np.float64), db.f32.numpy().astype(np.float64)
+        self.rescored = 0
+        for i in range(Q):
+            for j in range(approx.shape[1]):
+                if u[i, j] != 0 and approx[i, j] >= cut[i]:
+                    exact[i, j] = np.float32(qf[i] @ df[idx[i, j]])
+                    self.rescored += 1
+        order = np.argsort(-exact, axis=1, kind="stable")[:, :k]
+        top = np.take_along_axis(exact, order, axis=1)
+        keys = np.where(np.isfinite(top), _pack(top, np.take_along_axis(idx, order, axis=1) + idx_base), 0)
+        if keys.shape[1] < k:
+            keys = np.concatenate([keys, np.zeros((Q, k - keys.shape[1]), dtype=np.int64)], axis=1)
+        # ties on the exact score must order by index like the keys do: sort the packed keys themselves
+        keys = np.sort(keys.view(np.uint64), axis=1)[:, ::-1].copy().view(np.int64)
+        payload = torch.zeros((Q * k + (Q + 1) // 2,), dtype=torch.int64)
+        kv, bv = Engine.split_payload(payload, Q, k)
+        kv.copy_(torch.from_numpy(np.ascontiguousarray(keys)))
+        bv.copy_(torch.from_numpy(np.where(np.isfinite(tau.numpy()), tau.numpy() + self.E, -np.inf).astype(np.float32)))
+        self.launches += 1
+        return payload
+
+    def merge_payload(self, allp, Q, k):
+        from emr2a_b200.engine import Engine
+        return self.topk_merge(Engine.split_payload(allp, Q, k)[0].contiguous(), k)
+
+    def verify_merged(self, keys, allp, k):
+        from emr2a_b200.engine import Engine
+        Q = keys.shape[0]
+        bounds = Engine.split_payload(allp, Q, k)[1].numpy().max(axis=0)
+        u = keys.numpy().view(np.uint64)[:, k - 1]
+        bits = (u >> np.uint64(32)).astype(np.uint32)
+        kth = np.where(bits & np.uint32(0x80000000), bits ^ np.uint32(0x80000000), ~bits).astype(np.uint32).view(np.float32)
+        ok = np.isneginf(bounds) | ((u != 0) & (kth > bounds))
+        n_bad = int((~ok).sum())
+        return torch.from_numpy((~ok).astype(np.uint8)), torch.tensor([n_bad, int(n_bad > 0), 0, 0], dtype=torch.int32)
+
+    def exact_rescan(self, qs, db, flag_list, k, idx_base=0, q_fold=None, db_fold=None):
+        from emr2a_b200.engine import Operand
+        sel = flag_list.long()
+        sub = Operand(n=int(sel.numel()), dim=qs.dim, f32=qs.f32[sel])
+        return _StubEngine.topk_search(self, sub, db, k, "fp32", q_fold=None if q_fold is None else q_fold[sel],
+                                       db_fold=db_fold, idx_base=idx_base)
+
+
+def _coop_case():
+    rng = np.random.default_rng(21)
+    n, d, n_q, k = 1500, 16, 64, 5
+    labels = rng.integers(0, 3, n).astype(np.int32)
+    db = (rng.standard_normal((n, d)) + labels[:, None]).astype(np.float32)
+    ql = rng.integers(0, 3, n_q).astype(np.int32)
+    qs = (rng.standard_normal((n_q, d)) + ql[:, None]).astype(np.float32)
+    return db, labels, qs, ql, k
+
+
+def _coop_run(world, rank, width, defer=False):
+    from emr2a_b200.dist import shard_range, sharded_search_and_vote
+    db, labels, qs, ql, k = _coop_case()
+    lo, hi = shard_range(len(labels), rank, world)
+    eng = _CoopStub()
+    eng.WIDTH = width
+    r = sharded_search_and_vote(eng, (db[lo:hi],), (qs,), torch.from_numpy(labels), torch.from_numpy(ql), 3, k, lo, 0, 0,
+                                k_list=(1, 3), precision="auto", defer_status=defer)
+    out = {"keys": r["keys"].numpy().copy(), "hit_counts": r["hit_counts"].numpy().copy(),
+           "unverified": int(r.get("unverified", -1)), "rescored": getattr(eng, "rescored", None)}
+    if defer:
+        out["status"] = r["status"].numpy().copy()
+    return out
+
+
+def _coop_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    out = {"wide": _coop_run(world, rank, 40), "narrow": _coop_run(world, rank, 7), "deferred": _coop_run(world, rank, 7, defer=True)}
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_cooperative_shards_world2_equal_exact_search():
+    db, labels, qs, ql, k = _coop_case()
+    stub = _StubEngine()
+    want = stub.topk_search(stub.prepare(qs, None, 1, 1, 0, "fp32"), stub.prepare(db, None, 1, 1, 0, "fp32"), k, "fp32").numpy()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_coop_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = dict(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    for rank in (0, 1):
+        wide, narrow, deferred = outs[rank]["wide"], outs[rank]["narrow"], outs[rank]["deferred"]
+        assert np.array_equal(wide["keys"], want) and np.array_equal(narrow["keys"], want)
+        assert wide["unverified"] == 0                      # 40 candidates per shard: every merged selection verifies
+        assert narrow["unverified"] > 0                     # 7 candidates for K = 5 and E = 0.02: the repair path ran
+        assert np.array_equal(wide["hit_counts"], narrow["hit_counts"])
+        # deferred status: no repair inside the call, [1] tells the caller the step must not be used as it is
+        assert deferred["status"][0] == narrow["unverified"] and deferred["status"][1] == 1
+        # the exchange of the K-th best filter score cuts the re-scoring: fewer candidates than shards x lists hold
+        assert wide["rescored"] < 64 * 40
+    assert outs[0]["narrow"]["unverified"] == outs[1]["narrow"]["unverified"]

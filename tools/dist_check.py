@@ -18,16 +18,18 @@ labels = synth.device_labels(0, n, c, 11, dev)
 qi, ql = synth.device_block(50_003_968, q, d, c, 11, dev, label_seed=11)
 qt, _ = synth.device_block(50_003_968, q, d, c, 12, dev, label_seed=11)
 ok = True
-for prec in ("bf16x3", "fp32"):
+for prec in ("rescore", "rescore-selfcontained", "bf16x3", "fp32"):
+    coop = prec == "rescore"                      # cooperative shards (staged K2, two collectives) vs self-contained ones
+    name, prec = prec, prec.split("-")[0]
     lo, hi = shard_range(n, rank, world)
     di, _ = synth.device_block(lo, hi - lo, d, c, 11, dev, label_seed=11)
     dt, _ = synth.device_block(lo, hi - lo, d, c, 12, dev, label_seed=11)
-    r = sharded_search_and_vote(eng, (di, dt), (qi, qt), labels, ql, c, k, lo, flags, flags, precision=prec)
+    r = sharded_search_and_vote(eng, (di, dt), (qi, qt), labels, ql, c, k, lo, flags, flags, precision=prec, cooperative=coop)
     fi, _ = synth.device_block(0, n, d, c, 11, dev, label_seed=11)
     ft, _ = synth.device_block(0, n, d, c, 12, dev, label_seed=11)
     full = eng.search_and_vote((fi, ft), (qi, qt), labels, ql, c, k, db_flags=flags, q_flags=flags, precision=prec)
     same = torch.equal(r["keys"], full["keys"]) and torch.equal(r["pred_vote"], full["pred_vote"]) and torch.equal(r["confusion"], full["confusion"])
-    print(f"rank {rank}/{world} {prec}: sharded == single-GPU: {same}", flush=True)
+    print(f"rank {rank}/{world} {name}: sharded == single-GPU: {same} (unverified {r.get('unverified')})", flush=True)
     ok = ok and same
 # all-queries CV over the sharded cohort == the single-GPU one-pass CV
 n_cv, n_folds = 200_000, 5
