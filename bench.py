@@ -658,27 +658,37 @@ def main():
     if rank == 0:
         sampler.start()
     windows = []
-    for _ in range(max(args.warmup, 3)):
-        res = step()
-    barrier()
+    for attempt in range(2):
+        for _ in range(max(args.warmup, 3)):
+            res = step()
+        barrier()
+        deferred.clear()
 
-    # ---- timed region: device-resident ----
-    launches0 = eng.launches
-    w0 = time.time()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    k2_events = []
-    for _ in range(args.steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        timers["k2_start"], timers["k2_end"] = e0, e1
-        res = step(record_k2=True)
-        k2_events.append((e0, e1))
-    ev1.record()
-    barrier()
-    windows.append((w0, time.time()))
-    unverified_total, overflow = eng.check_deferred(deferred)
-    assert not overflow, "rescore re-scan list overflowed: results of the timed steps are not valid"
+        # ---- timed region: device-resident ----
+        launches0 = eng.launches
+        w0 = time.time()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        k2_events = []
+        for _ in range(args.steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            timers["k2_start"], timers["k2_end"] = e0, e1
+            res = step(record_k2=True)
+            k2_events.append((e0, e1))
+        ev1.record()
+        barrier()
+        w1 = time.time()
+        unverified_total, overflow = eng.check_deferred(deferred)
+        if not overflow:
+            windows.append((w0, w1))
+            break
+        # Cooperative shards defer the repair of queries the merged lists cannot verify (status[1]); a timed step that
+        # needed it is not a valid step.  Every rank sees the same status, so all of them repeat the measurement with
+        # self-contained shards (exact re-scan inside the step).
+        assert attempt == 0 and world > 1 and os.environ.get("EMR2A_COOP_SHARDS", "1") != "0", \
+            "rescore re-scan list overflowed: results of the timed steps are not valid"
+        os.environ["EMR2A_COOP_SHARDS"] = "0"
     ms = ev0.elapsed_time(ev1)
     launches = eng.launches - launches0
     k2_ms = [a.elapsed_time(b) for a, b in k2_events]
@@ -751,6 +761,7 @@ def main():
     clocks = sampler.summary(windows) if rank == 0 else None
 
     # ---- roofline of the dominant kernel (K2, tensor pipe) ----
+    coop_shards = world > 1 and res["precision"] == "rescore" and os.environ.get("EMR2A_COOP_SHARDS", "1") != "0"
     pk = peaks()
     flops = 2.0 * dim * n_q * (hi - lo)
     passes = {"bf16x3": 3, "bf16x1": 1, "fp32": 1, "rescore": 1}[res["precision"]]
@@ -762,8 +773,11 @@ def main():
                 "traffic_source": traffic_src,
                 "peak_source": pk["src"] + " " + t_src,
                 "frac_of_burst": achieved / pk["tflops_burst"], "frac_of_sustained": achieved / pk["tflops"],
-                "kernel": "emr2a_topk_search = tc2_topk_kernel (tcgen05 cta_group::2, TMA, fused Top-K) + K3 merge of partial lists"
-                          + (" + exact fp32 rescore of <=64 candidates/query + (empty) re-scan" if res["precision"] == "rescore" else ""),
+                "kernel": ("emr2a_topk_filter = tc2_topk_kernel (tcgen05 cta_group::2, TMA, fused Top-K) + K3 merge of partial "
+                           "lists (the exact re-scoring follows the shards' exchange of their K-th best filter score)"
+                           if coop_shards else
+                           "emr2a_topk_search = tc2_topk_kernel (tcgen05 cta_group::2, TMA, fused Top-K) + K3 merge of partial lists"
+                           + (" + exact fp32 rescore of <=64 candidates/query + (empty) re-scan" if res["precision"] == "rescore" else "")),
                 "kernel_ms": k2_avg_ms,
                 "issued_tflops": achieved * passes, "issued_frac": achieved * passes / t_peak,
                 "share_of_step": k2_avg_ms / ms_per_step}
@@ -789,7 +803,10 @@ def main():
                 "dtype": {"bf16x3": "bf16x3", "bf16x1": "bf16", "fp32": "f32", "rescore": "bf16+f32"}[res["precision"]],
                 "data": "synthetic",
                 "config": {"workload": workload_string(args.workload),
-                           "parallelism": f"database row-sharded x{world}, NCCL all-gather of local Top-K" if world > 1 else "single GPU",
+                           "parallelism": (f"database row-sharded x{world}, cooperative shards: NCCL all-reduce (MAX) of the K-th best filter "
+                                           "score, exact re-scoring of the surviving candidates, NCCL all-gather of exact Top-K + bounds, "
+                                           "verification of the merged lists" if coop_shards else
+                                           f"database row-sharded x{world}, NCCL all-gather of local Top-K") if world > 1 else "single GPU",
                            "arithmetic": {"bf16x3": "tcgen05 bf16 2-way split (hi*lo + lo*hi + hi*hi), fp32 accumulate",
                                           "bf16x1": "tcgen05 bf16 operands, fp32 accumulate", "fp32": "CUDA-core fp32 FMA",
                                           "rescore": "tcgen05 bf16 filter (fp32 accumulate) + exact f32 re-scoring of the "

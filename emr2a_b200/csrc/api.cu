@@ -47,20 +47,21 @@ int tc_planned_splits(int64_t Q, int64_t N, int min_splits);
 
 size_t rescore_workspace_bytes(int64_t Q, int K);
 int rescore_pipeline(const uint64_t* approx, int KP, const uint32_t* tau, const float* q, int64_t ldq, const float* db,
-                     int64_t lddb, int64_t Q, int64_t N, int D, int64_t idx_base, int K, const float* q_stats,
-                     const float* db_stats, const uint8_t* q_fold, const uint8_t* db_fold, uint64_t* out_keys,
-                     int* status, uint8_t* qflags, void* workspace, size_t ws_bytes, cudaStream_t st);
+                     int64_t lddb, const emr2a_lazy_rows* db_lazy, int64_t Q, int64_t N, int D, int64_t idx_base, int K,
+                     const float* q_stats, const float* db_stats, const uint8_t* q_fold, const uint8_t* db_fold,
+                     uint64_t* out_keys, int* status, uint8_t* qflags, void* workspace, size_t ws_bytes, cudaStream_t st);
 
 int rescore_kth_scores(const uint64_t* approx, int KP, int K, int64_t Q, float* kth, cudaStream_t st);
 int rescore_select_only(const uint64_t* approx, int KP, const uint32_t* tau, const float* kth_floor, const float* q,
-                        int64_t ldq, const float* db, int64_t lddb, int64_t Q, int64_t N, int D, int64_t idx_base, int K,
-                        const float* q_stats, const float* db_stats, uint64_t* out_keys, float* bound_out, cudaStream_t st);
+                        int64_t ldq, const float* db, int64_t lddb, const emr2a_lazy_rows* db_lazy, int64_t Q, int64_t N, int D,
+                        int64_t idx_base, int K, const float* q_stats, const float* db_stats, uint64_t* out_keys,
+                        float* bound_out, cudaStream_t st);
 int rescore_verify_merged(const uint64_t* keys, int K, int64_t Q, const float* bounds, int parts, int64_t bounds_stride,
                           uint8_t* flags, int* count, cudaStream_t st);
 size_t exact_rescan_workspace_bytes(int n_flagged, int K);
-int rescore_exact_rescan(const float* q, int64_t ldq, const float* db, int64_t lddb, int64_t N, int D, int64_t idx_base, int K,
-                         const uint8_t* q_fold, const uint8_t* db_fold, const int* flag_list, int n_flagged,
-                         uint64_t* out_compact, void* workspace, size_t ws_bytes, cudaStream_t st);
+int rescore_exact_rescan(const float* q, int64_t ldq, const float* db, int64_t lddb, const emr2a_lazy_rows* db_lazy, int64_t N,
+                         int D, int64_t idx_base, int K, const uint8_t* q_fold, const uint8_t* db_fold, const int* flag_list,
+                         int n_flagged, uint64_t* out_compact, void* workspace, size_t ws_bytes, cudaStream_t st);
 
 constexpr int RESCORE_KP = 32;    // candidates kept per (query, database split) by the filter; 16 leaves too little slack (measured)
 constexpr int RESCORE_KPM = 64;   // candidates per query re-scored after merging the splits
@@ -141,7 +142,7 @@ static int topk_search_impl(const float* q_f32, int64_t ldq_f32, const uint16_t*
                             const uint8_t* q_fold, const uint8_t* db_fold, int fold_sorted, int64_t idx_base, int K,
                             int precision, const float* q_stats, const float* db_stats, uint64_t* out_keys,
                             int32_t* status, uint8_t* qflags, void* workspace, size_t ws_bytes, float* debug_scores,
-                            void* stream) {
+                            const emr2a_lazy_rows* db_lazy, void* stream) {
   if (Q < 0 || N < 0 || D <= 0 || K <= 0 || !out_keys) return fail(EMR2A_ERR_INVALID, "topk_search: bad arguments (Q=%lld N=%lld D=%d K=%d)", (long long)Q, (long long)N, D, K);
   if ((q_fold == nullptr) != (db_fold == nullptr)) return fail(EMR2A_ERR_INVALID, "topk_search: q_fold and db_fold must be given together");
   if (idx_base < 0) return fail(EMR2A_ERR_INVALID, "topk_search: negative idx_base");
@@ -164,8 +165,8 @@ static int topk_search_impl(const float* q_f32, int64_t ldq_f32, const uint16_t*
       return tc_topk_search(q_hi, nullptr, db_hi, nullptr, Q, N, D, ldq_bf16, lddb_bf16, q_fold, db_fold, idx_base, K, 1, out_keys, workspace, ws_bytes, debug_scores, st, nullptr, fold_sorted, 1);
     case EMR2A_PREC_BF16_RESCORE: {
       if (K > 10) return fail(EMR2A_ERR_UNSUPPORTED, "topk_search(rescore): K=%d > 10 (use EMR2A_PREC_BF16X3)", K);
-      if (!q_f32 || !db_f32) return fail(EMR2A_ERR_INVALID, "topk_search(rescore): q_f32/db_f32 required");
-      if (ldq_f32 < D || lddb_f32 < D) return fail(EMR2A_ERR_INVALID, "topk_search(rescore): leading dimension smaller than D");
+      if (!q_f32 || (!db_f32 && !db_lazy)) return fail(EMR2A_ERR_INVALID, "topk_search(rescore): q_f32 and db_f32 (or db_lazy) required");
+      if (ldq_f32 < D || (!db_lazy && lddb_f32 < D)) return fail(EMR2A_ERR_INVALID, "topk_search(rescore): leading dimension smaller than D");
       if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255)) return fail(EMR2A_ERR_INVALID, "topk_search(rescore): workspace must be 256-byte aligned");
       const size_t a_bytes = align256(sizeof(uint64_t) * static_cast<size_t>(Q) * RESCORE_KPM);
       const size_t t_bytes = align256(tc_topk_workspace_bytes(Q, N, RESCORE_KP, D));
@@ -178,7 +179,7 @@ static int topk_search_impl(const float* q_f32, int64_t ldq_f32, const uint16_t*
       int rc = rescore_filter_stage(q_hi, ldq_bf16, db_hi, lddb_bf16, Q, N, D, q_fold, db_fold, fold_sorted, idx_base, K,
                                     reinterpret_cast<uint64_t*>(ws), ws + a_bytes, t_bytes, debug_scores, st, &cand, &kpm, &tau);
       if (rc != EMR2A_OK) return rc;
-      return rescore_pipeline(cand, kpm, tau, q_f32, ldq_f32, db_f32, lddb_f32, Q, N, D, idx_base, K, q_stats,
+      return rescore_pipeline(cand, kpm, tau, q_f32, ldq_f32, db_f32, lddb_f32, db_lazy, Q, N, D, idx_base, K, q_stats,
                               db_stats, q_fold, db_fold, out_keys, status, qflags, ws + a_bytes + t_bytes, r_bytes, st);
     }
     default:
@@ -192,10 +193,11 @@ extern "C" int emr2a_topk_search(const float* q_f32, int64_t ldq_f32, const uint
                                  const uint8_t* q_fold, const uint8_t* db_fold, int fold_sorted, int64_t idx_base,
                                  int K, int precision, const float* q_stats, const float* db_stats,
                                  uint64_t* out_keys, int32_t* status_out, uint8_t* unverified_out, void* workspace,
-                                 size_t ws_bytes, void* stream) {
+                                 size_t ws_bytes, const emr2a_lazy_rows* db_lazy, void* stream) {
+  if (db_lazy && precision != EMR2A_PREC_BF16_RESCORE) return fail(EMR2A_ERR_INVALID, "topk_search: db_lazy is for EMR2A_PREC_BF16_RESCORE only");
   return topk_search_impl(q_f32, ldq_f32, q_hi, q_lo, ldq_bf16, db_f32, lddb_f32, db_hi, db_lo, lddb_bf16, Q, N, D,
                           q_fold, db_fold, fold_sorted, idx_base, K, precision, q_stats, db_stats, out_keys,
-                          status_out, unverified_out, workspace, ws_bytes, nullptr, stream);
+                          status_out, unverified_out, workspace, ws_bytes, nullptr, db_lazy, stream);
 }
 
 // Diagnostics: same as emr2a_topk_search on the tensor-core arms, additionally dumping every
@@ -209,7 +211,7 @@ extern "C" int emr2a_debug_topk_search_dump(const uint16_t* q_hi, const uint16_t
     return fail(EMR2A_ERR_INVALID, "debug dump is for the tensor-core arms only");
   return topk_search_impl(nullptr, 0, q_hi, q_lo, ldq, nullptr, 0, db_hi, db_lo, lddb, Q, N, D, q_fold, db_fold, 0,
                           idx_base, K, precision, nullptr, nullptr, out_keys, nullptr, nullptr, workspace, ws_bytes,
-                          debug_scores, stream);
+                          debug_scores, nullptr, stream);
 }
 
 // Diagnostics: globaltimer stamps (start, end) of every work unit of the last CTA-pair launch made with
@@ -260,13 +262,14 @@ extern "C" int emr2a_topk_filter(const uint16_t* q_hi, int64_t ldq_bf16, const u
 extern "C" int emr2a_rescore_candidates(const uint64_t* cand, const uint32_t* tau, const float* kth_floor, const float* q_f32,
                                         int64_t ldq_f32, const float* db_f32, int64_t lddb_f32, int64_t Q, int64_t N, int D,
                                         int64_t idx_base, int K, const float* q_stats, const float* db_stats,
-                                        uint64_t* out_keys, float* bound_out, void* stream) {
-  if (!cand || !tau || !q_f32 || !db_f32 || !q_stats || !db_stats || !out_keys || !bound_out || Q < 0 || N < 0 || D <= 0 ||
-      K <= 0 || K > 10 || ldq_f32 < D || lddb_f32 < D)
+                                        uint64_t* out_keys, float* bound_out, const emr2a_lazy_rows* db_lazy,
+                                        void* stream) {
+  if (!cand || !tau || !q_f32 || (!db_f32 && !db_lazy) || !q_stats || !db_stats || !out_keys || !bound_out || Q < 0 || N < 0 ||
+      D <= 0 || K <= 0 || K > 10 || ldq_f32 < D || (!db_lazy && lddb_f32 < D))
     return fail(EMR2A_ERR_INVALID, "rescore_candidates: bad arguments");
   if (Q == 0) return EMR2A_OK;
-  return rescore_select_only(cand, RESCORE_KPM, tau, kth_floor, q_f32, ldq_f32, db_f32, lddb_f32, Q, N, D, idx_base, K,
-                             q_stats, db_stats, out_keys, bound_out, static_cast<cudaStream_t>(stream));
+  return rescore_select_only(cand, RESCORE_KPM, tau, kth_floor, q_f32, ldq_f32, db_f32, lddb_f32, db_lazy, Q, N, D, idx_base,
+                             K, q_stats, db_stats, out_keys, bound_out, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int emr2a_verify_merged(const uint64_t* keys, int K, int64_t Q, const float* bounds, int parts,
@@ -282,9 +285,9 @@ extern "C" size_t emr2a_exact_rescan_workspace_bytes(int n_flagged, int K) { ret
 extern "C" int emr2a_exact_rescan(const float* q_f32, int64_t ldq_f32, const float* db_f32, int64_t lddb_f32, int64_t N, int D,
                                   int64_t idx_base, int K, const uint8_t* q_fold, const uint8_t* db_fold,
                                   const int32_t* flag_list, int n_flagged, uint64_t* out_keys, void* workspace,
-                                  size_t ws_bytes, void* stream) {
-  if (!q_f32 || !db_f32 || !out_keys || N < 0 || D <= 0 || K <= 0 || n_flagged < 0 || ldq_f32 < D || lddb_f32 < D ||
-      (n_flagged > 0 && !flag_list))
+                                  size_t ws_bytes, const emr2a_lazy_rows* db_lazy, void* stream) {
+  if (!q_f32 || (!db_f32 && !db_lazy && N > 0) || !out_keys || N < 0 || D <= 0 || K <= 0 || n_flagged < 0 || ldq_f32 < D ||
+      (!db_lazy && N > 0 && lddb_f32 < D) || (n_flagged > 0 && !flag_list))
     return fail(EMR2A_ERR_INVALID, "exact_rescan: bad arguments");
   if ((q_fold == nullptr) != (db_fold == nullptr)) return fail(EMR2A_ERR_INVALID, "exact_rescan: q_fold and db_fold must be given together");
   if (n_flagged == 0) return EMR2A_OK;
@@ -295,6 +298,6 @@ extern "C" int emr2a_exact_rescan(const float* q_f32, int64_t ldq_f32, const flo
     EMR2A_LAUNCH_CHECK("zero_keys_kernel");
     return EMR2A_OK;
   }
-  return rescore_exact_rescan(q_f32, ldq_f32, db_f32, lddb_f32, N, D, idx_base, K, q_fold, db_fold, flag_list, n_flagged,
-                              out_keys, workspace, ws_bytes, st);
+  return rescore_exact_rescan(q_f32, ldq_f32, db_f32, lddb_f32, db_lazy, N, D, idx_base, K, q_fold, db_fold, flag_list,
+                              n_flagged, out_keys, workspace, ws_bytes, st);
 }

@@ -9,7 +9,7 @@
 // divisions by (sqrt(sum x^2) + 1e-8f) in fp32 -- so the fp32 output differs from
 // numpy only through the summation order of the norm (<= ~1e-7 relative).
 #include <type_traits>
-#include "common.cuh"
+#include "row_math.cuh"
 
 namespace emr2a {
 
@@ -29,6 +29,7 @@ struct NfParams {
   float* inv_norm;
   float* stats;     // [0] = max row norm, [1] = max ||row - bf16(row)||  (atomic max on the float bits)
   const float* col_std;   // EMR2A_NF_STANDARDIZE: [3][d0 + d1] = per-column mean | scale | RN(1 / scale)
+  float* row_div;         // optional [n][4]: the divisors this pass used for the row (row_math.cuh: LazyRows)
 };
 
 __device__ __forceinline__ void stats_flush(float* stats, float max_norm2, float max_res2) {
@@ -37,72 +38,6 @@ __device__ __forceinline__ void stats_flush(float* stats, float max_norm2, float
   atomicMax(u, __float_as_uint(__fsqrt_ru(max_norm2)));
   atomicMax(u + 1, __float_as_uint(__fsqrt_ru(max_res2)));
 }
-
-template <typename InT> struct Loader;
-template <> struct Loader<float> {
-  typedef float4 Raw;
-  static __device__ __forceinline__ Raw load_raw(const void* base, int64_t elem) {
-    return ldg_stream_f4(reinterpret_cast<const float4*>(static_cast<const float*>(base) + elem));
-  }
-  static __device__ __forceinline__ float4 widen(const Raw& r) { return r; }
-  static __device__ __forceinline__ float4 load4(const void* base, int64_t elem) {
-    return ldg_stream_f4(reinterpret_cast<const float4*>(static_cast<const float*>(base) + elem));
-  }
-  static __device__ __forceinline__ float load1(const void* base, int64_t elem) {
-    return __ldg(static_cast<const float*>(base) + elem);
-  }
-};
-template <> struct Loader<__nv_bfloat16> {
-  typedef uint2 Raw;
-  static __device__ __forceinline__ Raw load_raw(const void* base, int64_t elem) {
-    return ldg_stream_u2(reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(base) + elem));
-  }
-  static __device__ __forceinline__ float4 widen(const Raw& r) {
-    float4 f;
-    f.x = __uint_as_float(r.x << 16);
-    f.y = __uint_as_float(r.x & 0xFFFF0000u);
-    f.z = __uint_as_float(r.y << 16);
-    f.w = __uint_as_float(r.y & 0xFFFF0000u);
-    return f;
-  }
-  static __device__ __forceinline__ float4 load4(const void* base, int64_t elem) {
-    uint2 r = ldg_stream_u2(reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(base) + elem));
-    float4 f;
-    f.x = __uint_as_float(r.x << 16);
-    f.y = __uint_as_float(r.x & 0xFFFF0000u);
-    f.z = __uint_as_float(r.y << 16);
-    f.w = __uint_as_float(r.y & 0xFFFF0000u);
-    return f;
-  }
-  static __device__ __forceinline__ float load1(const void* base, int64_t elem) {
-    uint16_t r = __ldg(static_cast<const uint16_t*>(base) + elem);
-    return __uint_as_float(static_cast<uint32_t>(r) << 16);
-  }
-};
-
-__device__ __forceinline__ float sq4(const float4& a) { return a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w; }
-// Division of a whole row by one divisor: r = RN(1/d) once per row, then per element
-// q0 = x*r, rem = x - q0*d (exact in an FMA), q = q0 + rem*r -- the correctly rounded quotient
-// x/d (Markstein) without the per-element special-case branches of __fdiv_rn, which made K1
-// ALU-bound (3160 instructions per row).  Inputs are finite and d >= 1e-8.
-struct RowDiv {
-  float d, r;
-  __device__ __forceinline__ float operator()(float x) const {
-    const float q0 = x * r;
-    const float rem = fmaf(-q0, d, x);
-    return fmaf(rem, r, q0);
-  }
-};
-__device__ __forceinline__ RowDiv row_div(float d) {
-  RowDiv v;
-  v.d = d;
-  v.r = __frcp_rn(d);
-  return v;
-}
-__device__ __forceinline__ void div4(float4& a, const RowDiv& dv) {
-  a.x = dv(a.x); a.y = dv(a.y); a.z = dv(a.z); a.w = dv(a.w);
-}
-__device__ __forceinline__ void mul4(float4& a, float w) { a.x *= w; a.y *= w; a.z *= w; a.w *= w; }
 
 // Register-cached path: every lane keeps MAXC chunks of 4 elements.
 template <typename InT, int MAXC>
@@ -163,6 +98,7 @@ __global__ void __launch_bounds__(256, (MAXC <= 8 ? 2 : 1)) normalize_fuse_vec_k
       }
     }
     float ss0 = 0.f, ss1 = 0.f;
+    float4 divs = make_float4(1.f, 1.f, 1.f, 0.f);      // what row_div_out records (row_math.cuh: LazyRows)
     if (p.flags & EMR2A_NF_SEGNORM) {
 #pragma unroll
       for (int j = 0; j < MAXC; ++j) {
@@ -173,6 +109,7 @@ __global__ void __launch_bounds__(256, (MAXC <= 8 ? 2 : 1)) normalize_fuse_vec_k
     if (p.flags & EMR2A_NF_SEGNORM) {
       const RowDiv n0 = row_div(__fsqrt_rn(warp_sum(ss0)) + EMR2A_EPS);
       const RowDiv n1 = row_div(__fsqrt_rn(warp_sum(ss1)) + EMR2A_EPS);
+      divs.x = n0.d; divs.y = n1.d;
 #pragma unroll
       for (int j = 0; j < MAXC; ++j) {
         const int c = lane + 32 * j;
@@ -199,9 +136,11 @@ __global__ void __launch_bounds__(256, (MAXC <= 8 ? 2 : 1)) normalize_fuse_vec_k
 #pragma unroll
         for (int j = 0; j < MAXC; ++j) div4(v[j], dv);
         inv = dv.r;
+        divs.z = nrm; divs.w = 1.f;
       }
     }
     if (p.inv_norm && lane == 0) p.inv_norm[row] = inv;
+    if (p.row_div && lane == 0) reinterpret_cast<float4*>(p.row_div)[row] = divs;
     if (p.out_f32) {
 #pragma unroll
       for (int j = 0; j < MAXC; ++j) {
@@ -303,6 +242,7 @@ __global__ void __launch_bounds__(256, 2) normalize_fuse_block_kernel(const NfPa
       const int64_t r2 = row + static_cast<int64_t>(PF) * gridDim.x;
       if (r2 < p.n) load_row_block<InT, CPT>(p, r2, c0, ctot, ring[s]);
     }
+    float4 divs = make_float4(1.f, 1.f, 1.f, 0.f);
     if (p.flags & EMR2A_NF_SEGNORM) {
       float ss0 = 0.f, ss1 = 0.f;
 #pragma unroll
@@ -313,6 +253,7 @@ __global__ void __launch_bounds__(256, 2) normalize_fuse_block_kernel(const NfPa
       const float2 t = block_sum2(ss0, ss1, red);
       const RowDiv n0 = row_div(__fsqrt_rn(t.x) + EMR2A_EPS);
       const RowDiv n1 = row_div(__fsqrt_rn(t.y) + EMR2A_EPS);
+      divs.x = n0.d; divs.y = n1.d;
 #pragma unroll
       for (int j = 0; j < CPT; ++j) {
         const int c = threadIdx.x + 256 * j;
@@ -339,9 +280,11 @@ __global__ void __launch_bounds__(256, 2) normalize_fuse_block_kernel(const NfPa
 #pragma unroll
         for (int j = 0; j < CPT; ++j) div4(v[j], dv);
         inv = dv.r;
+        divs.z = nrm; divs.w = 1.f;
       }
     }
     if (p.inv_norm && threadIdx.x == 0) p.inv_norm[row] = inv;
+    if (p.row_div && threadIdx.x == 0) reinterpret_cast<float4*>(p.row_div)[row] = divs;
     if (p.out_f32) {
 #pragma unroll
       for (int j = 0; j < CPT; ++j) {
@@ -430,6 +373,7 @@ __global__ void __launch_bounds__(256) normalize_fuse_scalar_kernel(const NfPara
       if (divide) inv = __fdiv_rn(1.0f, nrm);
     }
     if (p.inv_norm && lane == 0) p.inv_norm[row] = inv;
+    if (p.row_div && lane == 0) reinterpret_cast<float4*>(p.row_div)[row] = make_float4(n0, n1, divide ? nrm : 1.f, divide ? 1.f : 0.f);
     const int epad = p.out_hi ? static_cast<int>(p.ld_bf16) : dtot;
     float n2 = 0.f, r2 = 0.f;
     for (int e = lane; e < epad; e += 32) {
@@ -511,7 +455,7 @@ extern "C" int emr2a_normalize_fuse(const void* seg0, const void* seg1, int64_t 
                                     int64_t ld0, int64_t ld1, float w0, float w1, int flags, int in_dtype,
                                     float* out_f32, int64_t ld_f32, uint16_t* out_hi, uint16_t* out_lo,
                                     int64_t ld_bf16, float* inv_norm_out, float* stats_out, const float* col_std,
-                                    void* stream) {
+                                    float* row_div_out, void* stream) {
   if (n < 0 || d0 <= 0 || d1 < 0) return fail(EMR2A_ERR_INVALID, "normalize_fuse: bad shape n=%lld d0=%d d1=%d", (long long)n, d0, d1);
   if (!seg0 || (d1 > 0 && !seg1)) return fail(EMR2A_ERR_INVALID, "normalize_fuse: null segment pointer");
   if (ld0 < d0 || (d1 > 0 && ld1 < d1)) return fail(EMR2A_ERR_INVALID, "normalize_fuse: leading dimension smaller than row");
@@ -522,7 +466,9 @@ extern "C" int emr2a_normalize_fuse(const void* seg0, const void* seg1, int64_t 
   if (out_hi && ld_bf16 < d0 + d1) return fail(EMR2A_ERR_INVALID, "normalize_fuse: ld_bf16 too small");
   if (n == 0) return EMR2A_OK;
   NfParams p{seg0, seg1, n, d0, d1, ld0, d1 > 0 ? ld1 : 0, w0, w1, flags,
-             out_f32, ld_f32, out_hi, out_lo, ld_bf16, inv_norm_out, stats_out, col_std};
+             out_f32, ld_f32, out_hi, out_lo, ld_bf16, inv_norm_out, stats_out, col_std, row_div_out};
+  if (row_div_out && ((flags & EMR2A_NF_STANDARDIZE) || (reinterpret_cast<uintptr_t>(row_div_out) & 15)))
+    return fail(EMR2A_ERR_UNSUPPORTED, "normalize_fuse: row_div_out needs 16-byte alignment and no fused standardisation");
   const size_t in_align = in_dtype == EMR2A_F32 ? 16 : 8;
   auto aligned = [](const void* q, size_t a) { return (reinterpret_cast<uintptr_t>(q) % a) == 0; };
   bool vec_ok = (d0 % 4 == 0) && (d1 % 4 == 0) && (ld0 % 4 == 0) && (d1 == 0 || ld1 % 4 == 0) &&

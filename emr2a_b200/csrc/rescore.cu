@@ -26,7 +26,7 @@
 //           appended to a flag list and re-searched exactly against the whole database
 //           (exact_rescan_kernel, cost proportional to the number of flagged queries).
 // Roofline: HBM-bound gather: Q * KP * D * 4 bytes (C2: 1.3 GB, ~0.3 ms).
-#include "common.cuh"
+#include "row_math.cuh"
 
 namespace emr2a {
 
@@ -55,6 +55,7 @@ struct RescoreParams {
   const uint8_t* q_fold;
   const uint8_t* db_fold;
   uint64_t* fb_parts;       // [blocks][cap][K]
+  LazyRows lazy;            // SRC != 0: the database rows are re-created from the raw rows (row_math.cuh), db is unused
   int n_fixed;              // >= 0: the flag list holds exactly this many queries (emr2a_exact_rescan); < 0: status[0]
   int compact;              // != 0: the re-scan writes list i of the flag list to out[i][K] instead of out[flag_list[i]][K]
 };
@@ -64,20 +65,10 @@ __device__ __forceinline__ int flagged_count(const RescoreParams& p) {
   return n > p.cap ? p.cap : n;
 }
 
-template <bool VEC>
-__device__ __forceinline__ float lane_dot(const float* __restrict__ a, const float* __restrict__ b, int D, int lane) {
-  float acc = 0.f;
-  if (VEC) {
-    for (int c = lane * 4; c < D; c += 128) {
-      const float4 x = *reinterpret_cast<const float4*>(a + c);
-      const float4 y = __ldg(reinterpret_cast<const float4*>(b + c));
-      acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
-    }
-  } else {
-    for (int c = lane; c < D; c += 32) acc = fmaf(a[c], __ldg(b + c), acc);
-  }
-  return acc;
-}
+// SRC: where the fp32 database rows come from.  0 = the fp32 matrix K1 wrote; 1 / 2 = re-created from the raw fp32 /
+// bf16 rows with the divisors K1 recorded (deferred fp32 rows: same values bit for bit, no fp32 copy of the database).
+template <int SRC> struct RawOf { typedef float T; };
+template <> struct RawOf<2> { typedef __nv_bfloat16 T; };
 
 __device__ __forceinline__ float error_bound(float nq, float rq, const float* ds, int D) {
   // the four norms are fp32 sums of D squares (relative error of a norm <= D * 2^-25): widen them accordingly
@@ -92,14 +83,30 @@ __device__ __forceinline__ float error_bound(float nq, float rq, const float* ds
 // the filter used is bf16_rn of exactly these values), clamped by the batch maxima K1 wrote.  Batches whose query
 // norms differ (late fusion with per-query z-score / min-max scaling, emr2a_b200/late.py) get a bound as tight as a
 // homogeneous batch would.
+template <bool VEC>
 __device__ __forceinline__ void query_norms(const float* __restrict__ qrow, int D, int lane, const float* qs,
                                             float& nq, float& rq) {
   float n2 = 0.f, r2 = 0.f;
-  for (int e = lane; e < D; e += 32) {
-    const float x = __ldg(qrow + e);
-    const float r = x - __bfloat162float(__float2bfloat16_rn(x));
-    n2 = fmaf(x, x, n2);
-    r2 = fmaf(r, r, r2);
+  if (VEC) {                                 // 128-bit loads, four of them in flight: the pass is pure load latency
+#pragma unroll 4
+    for (int e = lane * 4; e < D; e += 128) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(qrow + e));
+      const float v[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float r = v[c] - __bfloat162float(__float2bfloat16_rn(v[c]));
+        n2 = fmaf(v[c], v[c], n2);
+        r2 = fmaf(r, r, r2);
+      }
+    }
+  } else {
+#pragma unroll 4
+    for (int e = lane; e < D; e += 32) {
+      const float x = __ldg(qrow + e);
+      const float r = x - __bfloat162float(__float2bfloat16_rn(x));
+      n2 = fmaf(x, x, n2);
+      r2 = fmaf(r, r, r2);
+    }
   }
   n2 = warp_sum(n2);
   r2 = warp_sum(r2);
@@ -111,8 +118,9 @@ __device__ __forceinline__ void query_norms(const float* __restrict__ qrow, int 
 // and its 8 warps re-score 8 of the 64 candidates each -- for small batches (serving), where a single warp walking
 // 16 groups of dependent row gathers is pure latency (~90 us at D = 1024); selection and verification are then done
 // by warp 0 from the exact keys the warps exchanged through shared memory.
-template <bool VEC, int WPQ>
-__global__ void __launch_bounds__(256) rescore_select_kernel(const RescoreParams p) {
+template <bool VEC, int WPQ, int SRC = 0>
+__global__ void __launch_bounds__(256, WPQ == 1 ? (SRC == 0 ? 4 : 3) : 1) rescore_select_kernel(const RescoreParams p) {
+  static_assert(SRC == 0 || VEC, "deferred fp32 rows need the 128-bit path");
   __shared__ uint64_t xkeys[WPQ == 1 ? 1 : 64];
   const int lane = threadIdx.x & 31;
   const int wq = WPQ == 1 ? 0 : (threadIdx.x >> 5);                      // this warp's share of the candidate groups
@@ -132,13 +140,13 @@ __global__ void __launch_bounds__(256) rescore_select_kernel(const RescoreParams
   // A candidate c with s~(c) + E < s~(K-th candidate) - E cannot be among the exact K best (the K best
   // filter scores all have exact scores >= s~_K - E), so it is not re-scored: typically ~20 of 64 are.
   float nq, rq;
-  query_norms(qrow, p.D, lane, p.q_stats, nq, rq);
+  query_norms<VEC>(qrow, p.D, lane, p.q_stats, nq, rq);
   const float E = error_bound(nq, rq, p.db_stats, p.D);
   const uint64_t kth_approx = __shfl_sync(0xffffffffu, akey[0], p.K - 1);
   float kth_lb = kth_approx != 0ull ? key_score(kth_approx) : -INFINITY;
   if (p.kth_floor != nullptr) kth_lb = fmaxf(kth_lb, __ldg(p.kth_floor + q));      // another shard already holds K better rows
-  const float cut = kth_lb - 2.0f * E;
-  bool done = false;
+  float cut = kth_lb - 2.0f * E;
+  bool done = false, tightened = false;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     for (int g = 0; g < 32 && !done && h * 32 + g < p.KP; g += 4) {
@@ -153,13 +161,21 @@ __global__ void __launch_bounds__(256) rescore_select_kernel(const RescoreParams
       if (kk[0] == 0ull) { done = true; break; }      // lists are packed: nothing valid beyond the first empty slot
       if (WPQ > 1 && (((h * 32 + g) >> 2) % WPQ) != wq) continue;      // another warp of the block takes this group
       if (VEC) {
+        LazyRowCtx ctx[SRC == 0 ? 1 : 4];
+        if (SRC != 0) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (kk[c] != 0ull) ctx[SRC == 0 ? 0 : c] = lazy_row_ctx(p.lazy, static_cast<int64_t>(key_index(kk[c])) - p.idx_base);
+        }
+#pragma unroll 2
         for (int e = lane * 4; e < p.D; e += 128) {
           const float4 x = __ldg(reinterpret_cast<const float4*>(qrow + e));
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             if (kk[c] != 0ull) {
               const int64_t row = static_cast<int64_t>(key_index(kk[c])) - p.idx_base;
-              const float4 y = __ldg(reinterpret_cast<const float4*>(p.db + row * p.lddb + e));
+              const float4 y = SRC == 0 ? __ldg(reinterpret_cast<const float4*>(p.db + row * p.lddb + e))
+                                        : lazy_load4<typename RawOf<SRC>::T>(p.lazy, ctx[SRC == 0 ? 0 : c], row, e);
               acc[c] = fmaf(x.x, y.x, acc[c]); acc[c] = fmaf(x.y, y.y, acc[c]);
               acc[c] = fmaf(x.z, y.z, acc[c]); acc[c] = fmaf(x.w, y.w, acc[c]);
             }
@@ -181,6 +197,25 @@ __global__ void __launch_bounds__(256) rescore_select_kernel(const RescoreParams
       for (int c = 0; c < 4; ++c) {
         const float s = warp_sum(acc[c]);
         if (lane == g + c && kk[c] != 0ull) ekey[h] = pack_key(s, key_index(kk[c]));
+      }
+      // Once the K + 2 .. K + 5 best filter candidates have their exact scores, the K-th best of THOSE (<= the final
+      // exact K-th best) tightens the cut: a candidate with s~ + E below it has s <= s~ + E < that K-th best and cannot
+      // enter the Top-K.  This replaces the a-priori margin 2E by E for the rest of the list -- about a third fewer
+      // row gathers (the scores within 2E of the K-th best are as many again as the Top-K itself).
+      if (WPQ == 1 && h == 0 && !tightened && g + 4 >= p.K + 2) {
+        float v = ekey[0] != 0ull ? key_score(ekey[0]) : -INFINITY;
+#pragma unroll
+        for (int k2 = 2; k2 <= 32; k2 <<= 1) {                 // bitonic sort across the warp, descending
+#pragma unroll
+          for (int j = k2 >> 1; j > 0; j >>= 1) {
+            const float o = __shfl_xor_sync(0xffffffffu, v, j);
+            const bool take_max = ((lane & j) == 0) == ((lane & k2) == 0);
+            v = take_max ? fmaxf(v, o) : fminf(v, o);
+          }
+        }
+        const float kth_exact = __shfl_sync(0xffffffffu, v, p.K - 1);
+        cut = fmaxf(cut, kth_exact - E);
+        tightened = true;
       }
     }
   }
@@ -237,8 +272,9 @@ __global__ void __launch_bounds__(256) rescore_select_kernel(const RescoreParams
 constexpr int FB_WARPS = 8;
 constexpr int FB_GMAX = 8;
 
-template <bool VEC>
+template <bool VEC, int SRC = 0>
 __global__ void __launch_bounds__(FB_WARPS * 32) exact_rescan_kernel(const RescoreParams p, int G) {
+  static_assert(SRC == 0 || VEC, "deferred fp32 rows need the 128-bit path");
   extern __shared__ __align__(16) unsigned char fb_smem[];
   const int n = flagged_count(p);
   if (n <= 0) return;
@@ -263,10 +299,40 @@ __global__ void __launch_bounds__(FB_WARPS * 32) exact_rescan_kernel(const Resco
     uint64_t kth = 0ull;                             // lane g: K-th best of (this warp, query g)
     const int my_fold = (p.q_fold && lane < gc) ? p.q_fold[p.flag_list[g0 + lane]] : -1;
     for (int64_t r = r0 + warp; r < r1; r += FB_WARPS) {
-      const float* drow = p.db + r * p.lddb;
       const int dfold = p.db_fold ? p.db_fold[r] : -2;
-      for (int g = 0; g < gc; ++g) {
-        const float s = warp_sum(lane_dot<VEC>(qbuf + g * Dp, drow, p.D, lane));
+      // every row element is fetched (or re-created) ONCE and used for all queries of the group; per query the fused
+      // multiply-adds run in the order the re-scoring stage uses, so the scores of the two stages are equal bit for bit
+      float acc[FB_GMAX];
+#pragma unroll
+      for (int g = 0; g < FB_GMAX; ++g) acc[g] = 0.f;
+      if (VEC) {
+        LazyRowCtx ctx;
+        if (SRC != 0) ctx = lazy_row_ctx(p.lazy, r);
+        for (int c = lane * 4; c < p.D; c += 128) {
+          const float4 y = SRC == 0 ? __ldg(reinterpret_cast<const float4*>(p.db + r * p.lddb + c))
+                                    : lazy_load4<typename RawOf<SRC>::T>(p.lazy, ctx, r, c);
+#pragma unroll
+          for (int g = 0; g < FB_GMAX; ++g) {
+            if (g < gc) {
+              const float4 x = *reinterpret_cast<const float4*>(qbuf + g * Dp + c);
+              acc[g] = fmaf(x.x, y.x, acc[g]); acc[g] = fmaf(x.y, y.y, acc[g]);
+              acc[g] = fmaf(x.z, y.z, acc[g]); acc[g] = fmaf(x.w, y.w, acc[g]);
+            }
+          }
+        }
+      } else {
+        const float* drow = p.db + r * p.lddb;
+        for (int c = lane; c < p.D; c += 32) {
+          const float y = __ldg(drow + c);
+#pragma unroll
+          for (int g = 0; g < FB_GMAX; ++g)
+            if (g < gc) acc[g] = fmaf(qbuf[g * Dp + c], y, acc[g]);
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < FB_GMAX; ++g) {
+        if (g >= gc) break;
+        const float s = warp_sum(acc[g]);
         if (lane == g && dfold != my_fold) {
           const uint64_t key = pack_key(s, static_cast<uint32_t>(r + p.idx_base));
           if (key > kth) {
@@ -356,26 +422,64 @@ int rescore_kth_scores(const uint64_t* approx, int KP, int K, int64_t Q, float* 
   return EMR2A_OK;
 }
 
+// src of the fp32 database rows: 0 = matrix, 1 / 2 = deferred (raw fp32 / bf16 rows + K1's divisors)
+static int rows_src(const emr2a_lazy_rows* lz) { return lz == nullptr ? 0 : (lz->dtype == EMR2A_BF16 ? 2 : 1); }
+
+static int lazy_fill(RescoreParams& p, const emr2a_lazy_rows* lz, int D) {
+  if (lz == nullptr) return EMR2A_OK;
+  const size_t al = lz->dtype == EMR2A_BF16 ? 8 : 16;
+  auto ok = [&](const void* x) { return x != nullptr && (reinterpret_cast<uintptr_t>(x) % al) == 0; };
+  if ((lz->dtype != EMR2A_F32 && lz->dtype != EMR2A_BF16) || lz->d0 <= 0 || lz->d1 < 0 || lz->d0 + lz->d1 != D ||
+      (lz->d0 % 4) || (lz->d1 % 4) || (lz->ld0 % 4) || (lz->d1 > 0 && (lz->ld1 % 4)) || !ok(lz->seg0) ||
+      (lz->d1 > 0 && !ok(lz->seg1)) || lz->row_div == nullptr || (reinterpret_cast<uintptr_t>(lz->row_div) & 15) ||
+      (lz->flags & EMR2A_NF_STANDARDIZE))
+    return fail(EMR2A_ERR_UNSUPPORTED, "deferred fp32 rows need 4-element-aligned segments, aligned pointers, row_div and no fused standardisation");
+  p.lazy.seg0 = lz->seg0; p.lazy.seg1 = lz->seg1; p.lazy.d0 = lz->d0; p.lazy.d1 = lz->d1; p.lazy.ld0 = lz->ld0;
+  p.lazy.ld1 = lz->d1 > 0 ? lz->ld1 : 0; p.lazy.w0 = lz->w0; p.lazy.w1 = lz->w1; p.lazy.flags = lz->flags;
+  p.lazy.row_div = lz->row_div;
+  return EMR2A_OK;
+}
+
+template <int SRC>
+static void launch_select_src(const RescoreParams& p, bool vec, cudaStream_t st) {
+  if (p.Q <= 4 * static_cast<int64_t>(sm_count())) {        // small batch: a block per query (latency layout)
+    if (vec) rescore_select_kernel<true, 8, SRC><<<static_cast<unsigned>(p.Q), 256, 0, st>>>(p);
+    else if constexpr (SRC == 0) rescore_select_kernel<false, 8, 0><<<static_cast<unsigned>(p.Q), 256, 0, st>>>(p);
+  } else {
+    const unsigned blocks = static_cast<unsigned>((p.Q * 32 + 255) / 256);
+    if (vec) rescore_select_kernel<true, 1, SRC><<<blocks, 256, 0, st>>>(p);
+    else if constexpr (SRC == 0) rescore_select_kernel<false, 1, 0><<<blocks, 256, 0, st>>>(p);
+  }
+}
+
+static bool rows_vec(const RescoreParams& p, int src) {
+  auto al16 = [](const void* x) { return (reinterpret_cast<uintptr_t>(x) & 15) == 0; };
+  const bool qv = (p.D % 4 == 0) && (p.ldq % 4 == 0) && al16(p.q);
+  return src != 0 ? qv : (qv && (p.lddb % 4 == 0) && al16(p.db));
+}
+
+static int launch_select(const RescoreParams& p, int src, cudaStream_t st) {
+  const bool vec = rows_vec(p, src);
+  if (src != 0 && !vec) return fail(EMR2A_ERR_UNSUPPORTED, "deferred fp32 rows need 16-byte aligned fp32 query rows with D %% 4 == 0");
+  if (src == 0) launch_select_src<0>(p, vec, st);
+  else if (src == 1) launch_select_src<1>(p, vec, st);
+  else launch_select_src<2>(p, vec, st);
+  EMR2A_LAUNCH_CHECK("rescore_select_kernel");
+  return EMR2A_OK;
+}
+
 // re-score only (no local verification, no re-scan): exact keys of the candidates that clear the (global) cut + bound_out
 int rescore_select_only(const uint64_t* approx, int KP, const uint32_t* tau, const float* kth_floor, const float* q,
-                        int64_t ldq, const float* db, int64_t lddb, int64_t Q, int64_t N, int D, int64_t idx_base, int K,
-                        const float* q_stats, const float* db_stats, uint64_t* out_keys, float* bound_out, cudaStream_t st) {
+                        int64_t ldq, const float* db, int64_t lddb, const emr2a_lazy_rows* db_lazy, int64_t Q, int64_t N, int D,
+                        int64_t idx_base, int K, const float* q_stats, const float* db_stats, uint64_t* out_keys,
+                        float* bound_out, cudaStream_t st) {
   RescoreParams p{};
   p.approx = approx; p.KP = KP; p.tau = tau; p.q = q; p.ldq = ldq; p.db = db; p.lddb = lddb; p.Q = Q; p.N = N; p.D = D;
   p.idx_base = idx_base; p.K = K; p.q_stats = q_stats; p.db_stats = db_stats; p.out = out_keys;
   p.kth_floor = kth_floor; p.bound_out = bound_out;
-  auto al16 = [](const void* x) { return (reinterpret_cast<uintptr_t>(x) & 15) == 0; };
-  const bool vec = (D % 4 == 0) && (ldq % 4 == 0) && (lddb % 4 == 0) && al16(q) && al16(db);
-  if (Q <= 4 * static_cast<int64_t>(sm_count())) {
-    if (vec) rescore_select_kernel<true, 8><<<static_cast<unsigned>(Q), 256, 0, st>>>(p);
-    else rescore_select_kernel<false, 8><<<static_cast<unsigned>(Q), 256, 0, st>>>(p);
-  } else {
-    const unsigned blocks = static_cast<unsigned>((Q * 32 + 255) / 256);
-    if (vec) rescore_select_kernel<true, 1><<<blocks, 256, 0, st>>>(p);
-    else rescore_select_kernel<false, 1><<<blocks, 256, 0, st>>>(p);
-  }
-  EMR2A_LAUNCH_CHECK("rescore_select_kernel");
-  return EMR2A_OK;
+  const int rc = lazy_fill(p, db_lazy, D);
+  if (rc != EMR2A_OK) return rc;
+  return launch_select(p, rows_src(db_lazy), st);
 }
 
 int rescore_verify_merged(const uint64_t* keys, int K, int64_t Q, const float* bounds, int parts, int64_t bounds_stride,
@@ -402,7 +506,20 @@ size_t rescore_workspace_bytes(int64_t Q, int K) {
          sizeof(uint64_t) * static_cast<size_t>(rescore_fallback_blocks()) * cap * K + 256;
 }
 
-static int launch_rescan(const RescoreParams& p, bool vec, cudaStream_t st) {
+template <int SRC>
+static int launch_rescan_src(const RescoreParams& p, bool vec, int G, size_t smem, int fb_blocks, cudaStream_t st) {
+  if (vec) {
+    EMR2A_CUDA_TRY(cudaFuncSetAttribute(exact_rescan_kernel<true, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    exact_rescan_kernel<true, SRC><<<fb_blocks, FB_WARPS * 32, smem, st>>>(p, G);
+  } else if constexpr (SRC == 0) {
+    EMR2A_CUDA_TRY(cudaFuncSetAttribute(exact_rescan_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    exact_rescan_kernel<false, 0><<<fb_blocks, FB_WARPS * 32, smem, st>>>(p, G);
+  }
+  EMR2A_LAUNCH_CHECK("exact_rescan_kernel");
+  return EMR2A_OK;
+}
+
+static int launch_rescan(const RescoreParams& p, int src, cudaStream_t st) {
   const int D = p.D, K = p.K;
   const int Dp = (D + 3) & ~3;
   int G = static_cast<int>((96 * 1024) / (sizeof(float) * Dp));
@@ -410,14 +527,12 @@ static int launch_rescan(const RescoreParams& p, bool vec, cudaStream_t st) {
   if (G < 1) return fail(EMR2A_ERR_UNSUPPORTED, "topk_search(rescore): D=%d too large for the exact re-scan", D);
   const size_t smem = sizeof(float) * G * Dp + sizeof(uint64_t) * FB_WARPS * G * K;
   const int fb_blocks = rescore_fallback_blocks();
-  if (vec) {
-    EMR2A_CUDA_TRY(cudaFuncSetAttribute(exact_rescan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    exact_rescan_kernel<true><<<fb_blocks, FB_WARPS * 32, smem, st>>>(p, G);
-  } else {
-    EMR2A_CUDA_TRY(cudaFuncSetAttribute(exact_rescan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    exact_rescan_kernel<false><<<fb_blocks, FB_WARPS * 32, smem, st>>>(p, G);
-  }
-  EMR2A_LAUNCH_CHECK("exact_rescan_kernel");
+  const bool vec = rows_vec(p, src);
+  if (src != 0 && !vec) return fail(EMR2A_ERR_UNSUPPORTED, "deferred fp32 rows need 16-byte aligned fp32 query rows with D %% 4 == 0");
+  const int rc = src == 0 ? launch_rescan_src<0>(p, vec, G, smem, fb_blocks, st)
+               : src == 1 ? launch_rescan_src<1>(p, vec, G, smem, fb_blocks, st)
+                          : launch_rescan_src<2>(p, vec, G, smem, fb_blocks, st);
+  if (rc != EMR2A_OK) return rc;
   rescan_merge_kernel<<<static_cast<unsigned>((static_cast<int64_t>(p.cap) * 32 + 255) / 256), 256, 0, st>>>(p, fb_blocks);
   EMR2A_LAUNCH_CHECK("rescan_merge_kernel");
   return EMR2A_OK;
@@ -425,9 +540,9 @@ static int launch_rescan(const RescoreParams& p, bool vec, cudaStream_t st) {
 
 // approx: merged approximate keys [Q][KP]; writes exact keys [Q][K]; status[0..1] must be zeroed by the caller.
 int rescore_pipeline(const uint64_t* approx, int KP, const uint32_t* tau, const float* q, int64_t ldq, const float* db,
-                     int64_t lddb, int64_t Q, int64_t N, int D, int64_t idx_base, int K, const float* q_stats,
-                     const float* db_stats, const uint8_t* q_fold, const uint8_t* db_fold, uint64_t* out_keys,
-                     int* status, uint8_t* qflags, void* workspace, size_t ws_bytes, cudaStream_t st) {
+                     int64_t lddb, const emr2a_lazy_rows* db_lazy, int64_t Q, int64_t N, int D, int64_t idx_base, int K,
+                     const float* q_stats, const float* db_stats, const uint8_t* q_fold, const uint8_t* db_fold,
+                     uint64_t* out_keys, int* status, uint8_t* qflags, void* workspace, size_t ws_bytes, cudaStream_t st) {
   if (!q_stats || !db_stats) return fail(EMR2A_ERR_INVALID, "topk_search(rescore): q_stats/db_stats (K1 stats) required");
   if (!status) return fail(EMR2A_ERR_INVALID, "topk_search(rescore): status_out required");
   if (rescore_workspace_bytes(Q, K) > ws_bytes) return fail(EMR2A_ERR_WORKSPACE, "topk_search(rescore): workspace too small");
@@ -442,19 +557,12 @@ int rescore_pipeline(const uint64_t* approx, int KP, const uint32_t* tau, const 
   const size_t off = (sizeof(int) * static_cast<size_t>(p.cap) + 255) & ~static_cast<size_t>(255);
   p.fb_parts = reinterpret_cast<uint64_t*>(ws + off);
   p.q_fold = q_fold; p.db_fold = db_fold;
-  auto al16 = [](const void* x) { return (reinterpret_cast<uintptr_t>(x) & 15) == 0; };
-  const bool vec = (D % 4 == 0) && (ldq % 4 == 0) && (lddb % 4 == 0) && al16(q) && al16(db);
-  if (Q <= 4 * static_cast<int64_t>(sm_count())) {        // small batch: a block per query (latency layout)
-    if (vec) rescore_select_kernel<true, 8><<<static_cast<unsigned>(Q), 256, 0, st>>>(p);
-    else rescore_select_kernel<false, 8><<<static_cast<unsigned>(Q), 256, 0, st>>>(p);
-  } else {
-    const unsigned blocks = static_cast<unsigned>((Q * 32 + 255) / 256);
-    if (vec) rescore_select_kernel<true, 1><<<blocks, 256, 0, st>>>(p);
-    else rescore_select_kernel<false, 1><<<blocks, 256, 0, st>>>(p);
-  }
-  EMR2A_LAUNCH_CHECK("rescore_select_kernel");
+  int rc = lazy_fill(p, db_lazy, D);
+  if (rc != EMR2A_OK) return rc;
+  const int src = rows_src(db_lazy);
+  if ((rc = launch_select(p, src, st)) != EMR2A_OK) return rc;
   // exact re-scan of unverified queries; both kernels return at once when status[0] == 0
-  return launch_rescan(p, vec, st);
+  return launch_rescan(p, src, st);
 }
 
 // The exact re-scan alone, for a flag list the caller holds (cooperative shards: the queries the MERGED lists could not
@@ -463,9 +571,9 @@ size_t exact_rescan_workspace_bytes(int n_flagged, int K) {
   return sizeof(uint64_t) * static_cast<size_t>(rescore_fallback_blocks()) * static_cast<size_t>(n_flagged > 0 ? n_flagged : 1) * K + 256;
 }
 
-int rescore_exact_rescan(const float* q, int64_t ldq, const float* db, int64_t lddb, int64_t N, int D, int64_t idx_base, int K,
-                         const uint8_t* q_fold, const uint8_t* db_fold, const int* flag_list, int n_flagged,
-                         uint64_t* out_compact, void* workspace, size_t ws_bytes, cudaStream_t st) {
+int rescore_exact_rescan(const float* q, int64_t ldq, const float* db, int64_t lddb, const emr2a_lazy_rows* db_lazy, int64_t N,
+                         int D, int64_t idx_base, int K, const uint8_t* q_fold, const uint8_t* db_fold, const int* flag_list,
+                         int n_flagged, uint64_t* out_compact, void* workspace, size_t ws_bytes, cudaStream_t st) {
   if (n_flagged <= 0) return EMR2A_OK;
   if (!workspace || exact_rescan_workspace_bytes(n_flagged, K) > ws_bytes) return fail(EMR2A_ERR_WORKSPACE, "exact_rescan: workspace too small");
   RescoreParams p{};
@@ -473,9 +581,9 @@ int rescore_exact_rescan(const float* q, int64_t ldq, const float* db, int64_t l
   p.flag_list = const_cast<int*>(flag_list); p.cap = n_flagged; p.n_fixed = n_flagged; p.compact = 1;
   p.q_fold = q_fold; p.db_fold = db_fold;
   p.fb_parts = reinterpret_cast<uint64_t*>(workspace);
-  auto al16 = [](const void* x) { return (reinterpret_cast<uintptr_t>(x) & 15) == 0; };
-  const bool vec = (D % 4 == 0) && (ldq % 4 == 0) && (lddb % 4 == 0) && al16(q) && al16(db);
-  return launch_rescan(p, vec, st);
+  const int rc = lazy_fill(p, db_lazy, D);
+  if (rc != EMR2A_OK) return rc;
+  return launch_rescan(p, rows_src(db_lazy), st);
 }
 
 }  // namespace emr2a

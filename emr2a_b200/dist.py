@@ -58,7 +58,8 @@ def sharded_search_and_vote(eng, db_segs_local: Sequence, q_segs: Sequence, db_l
     dim = sum(int(s.shape[1]) for s in db_segs_local if s is not None)
     world = dist.get_world_size() if dist.is_initialized() else 1
     prec = eng.pick_precision(n_q, max(n_db, 1) * world, dim, k, precision)
-    db = eng.prepare(db_segs_local[0], db_segs_local[1] if len(db_segs_local) > 1 else None, 1.0, 1.0, db_flags, prec)
+    db = eng.prepare(db_segs_local[0], db_segs_local[1] if len(db_segs_local) > 1 else None, 1.0, 1.0, db_flags, prec,
+                     defer_f32=True)
     qs = eng.prepare(q_segs[0], q_segs[1] if len(q_segs) > 1 else None, q_weights[0], q_weights[1], q_flags, prec)
     if prec == "rescore" and world > 1 and cooperative and os.environ.get("EMR2A_COOP_SHARDS", "1") != "0":
         return _cooperative_search_and_vote(eng, qs, db, db_labels_global, q_labels, n_classes, k, row_offset, k_list,

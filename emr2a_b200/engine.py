@@ -46,10 +46,46 @@ class Operand:
     lo: Optional[torch.Tensor] = None
     inv_norm: Optional[torch.Tensor] = None
     stats: Optional[torch.Tensor] = None    # [max row norm, max ||row - bf16(row)||]  (rescore error bound)
+    lazy: Optional["DeferredRows"] = None   # rescore arm: fp32 rows re-created from the raw rows instead of ``f32``
 
     @property
     def ld_planes(self) -> int:
         return 0 if self.hi is None else self.hi.shape[1]
+
+
+@dataclass
+class DeferredRows:
+    """Deferred fp32 rows (include/emr2a.h: emr2a_lazy_rows): the raw rows K1 read and the divisors it recorded.  The
+    tensors are referenced here so they stay alive as long as the operand does."""
+    seg0: torch.Tensor
+    seg1: Optional[torch.Tensor]
+    code: int
+    w0: float
+    w1: float
+    flags: int
+    row_div: torch.Tensor                   # float32 [n, 4]
+
+    def struct(self, lo: int = 0, hi: Optional[int] = None) -> "native.LazyRows":
+        a = self.seg0[lo:hi]
+        b = self.seg1[lo:hi] if self.seg1 is not None else None
+        return native.LazyRows(a.data_ptr(), b.data_ptr() if b is not None else None, int(a.shape[1]),
+                               int(b.shape[1]) if b is not None else 0, _ld(a), _ld(b) if b is not None else 0, self.code,
+                               float(self.w0), float(self.w1), int(self.flags), self.row_div[lo:hi].data_ptr())
+
+    def slice(self, lo: int, hi: int) -> "DeferredRows":
+        return DeferredRows(self.seg0[lo:hi], self.seg1[lo:hi] if self.seg1 is not None else None, self.code, self.w0,
+                            self.w1, self.flags, self.row_div[lo:hi])
+
+
+def _lazy_arg(op: "Operand"):
+    """(ctypes argument, keep-alive) for the db_lazy parameter of the rescore entry points."""
+    if op.lazy is None:
+        return None, None
+    st = op.lazy.struct()
+    return C.byref(st), st
+
+
+_DEFER_F32 = os.environ.get("EMR2A_DEFER_F32", "1") != "0"
 
 
 class Engine:
@@ -103,7 +139,7 @@ class Engine:
     def normalize_fuse(self, seg0, seg1=None, w0: float = 1.0, w1: float = 1.0, flags: int = native.NF_ROWNORM,
                        want_f32: bool = True, want_planes: bool = False, want_lo: bool = True,
                        want_inv_norm: bool = False, want_stats: bool = False,
-                       col_std: Optional[torch.Tensor] = None) -> Operand:
+                       col_std: Optional[torch.Tensor] = None, defer_f32: bool = False) -> Operand:
         """K1.  ``col_std`` (float32 [3, d0 + d1]: per-column mean | scale | 1/scale of a fitted StandardScaler) with
         ``native.NF_STANDARDIZE`` in ``flags`` standardises the raw rows inside the same pass."""
         a, code = self._embedding(seg0)
@@ -119,6 +155,13 @@ class Engine:
             d1 = b.shape[1]
         dim = d0 + d1
         out = Operand(n=n, dim=dim)
+        row_div = None
+        if defer_f32:          # no fp32 copy of the rows: K1 records its divisors, the search re-creates what it needs
+            if not self.can_defer(a, b, flags):
+                raise ValueError("normalize_fuse(defer_f32): needs segment widths / strides that are multiples of 4 and no fused standardisation")
+            want_f32 = False
+            row_div = torch.empty((n, 4), dtype=torch.float32, device=self.device)
+            out.lazy = DeferredRows(a, b, code, float(w0), float(w1), int(flags), row_div)
         if want_f32:
             out.f32 = torch.empty((n, dim), dtype=torch.float32, device=self.device)
         ld_planes = 0
@@ -138,9 +181,22 @@ class Engine:
                 a.data_ptr(), native.ptr(b), n, d0, d1, _ld(a), _ld(b) if b is not None else 0,
                 float(w0), float(w1), int(flags), code,
                 native.ptr(out.f32), dim, native.ptr(out.hi), native.ptr(out.lo), ld_planes,
-                native.ptr(out.inv_norm), native.ptr(out.stats), native.ptr(col_std), self._stream()))
+                native.ptr(out.inv_norm), native.ptr(out.stats), native.ptr(col_std), native.ptr(row_div), self._stream()))
         self.launches += 1
         return out
+
+    @staticmethod
+    def can_defer(a: torch.Tensor, b: Optional[torch.Tensor], flags: int) -> bool:
+        """Shapes the deferred-fp32-rows arithmetic takes (row_math.cuh): 4-element chunks must not straddle segments."""
+        if flags & native.NF_STANDARDIZE:
+            return False
+        al = 16 if a.dtype == torch.float32 else 8
+        for t in (a, b):
+            if t is None:
+                continue
+            if int(t.shape[1]) % 4 or (int(t.shape[0]) > 1 and int(t.stride(0)) % 4) or t.data_ptr() % al or t.stride(1) != 1:
+                return False
+        return True
 
     # ----------------------------------------------------------------- scores
     def scores(self, q: torch.Tensor, db: torch.Tensor) -> torch.Tensor:
@@ -230,11 +286,20 @@ class Engine:
                 return "bf16x3"
         return "fp32"
 
-    def prepare(self, seg0, seg1=None, w0=1.0, w1=1.0, flags=native.NF_ROWNORM, precision="fp32") -> Operand:
-        """K1 with the outputs the chosen K2 arm consumes."""
+    def prepare(self, seg0, seg1=None, w0=1.0, w1=1.0, flags=native.NF_ROWNORM, precision="fp32",
+                defer_f32: bool = False) -> Operand:
+        """K1 with the outputs the chosen K2 arm consumes.  ``defer_f32`` (rescore arm, DATABASE side): do not write the
+        fp32 rows -- the search re-creates the few it needs from the raw rows (``DeferredRows``); silently falls back
+        to materialised rows for shapes that arithmetic does not take or with ``EMR2A_DEFER_F32=0``."""
         if precision == "fp32":
             return self.normalize_fuse(seg0, seg1, w0, w1, flags, want_f32=True, want_planes=False)
         if precision == "rescore":
+            if defer_f32 and _DEFER_F32:
+                a = self._embedding(seg0)[0]
+                b = self._embedding(seg1)[0] if seg1 is not None else None
+                if (b is None or a.dtype == b.dtype) and self.can_defer(a, b, flags):
+                    return self.normalize_fuse(a, b, w0, w1, flags, want_planes=True, want_lo=False, want_stats=True,
+                                               defer_f32=True)
             return self.normalize_fuse(seg0, seg1, w0, w1, flags, want_f32=True, want_planes=True, want_lo=False,
                                        want_stats=True)
         return self.normalize_fuse(seg0, seg1, w0, w1, flags, want_f32=False, want_planes=True,
@@ -258,7 +323,10 @@ class Engine:
         ws_ptr = _round_up(ws.data_ptr(), 256)
         need_f32 = prec in (native.PREC_FP32, native.PREC_BF16_RESCORE)
         need_hi = prec != native.PREC_FP32
-        if need_f32 and (q.f32 is None or db.f32 is None):
+        lazy_arg, _lazy_keep = (None, None)
+        if prec == native.PREC_BF16_RESCORE and db.f32 is None:
+            lazy_arg, _lazy_keep = _lazy_arg(db)
+        if need_f32 and (q.f32 is None or (db.f32 is None and lazy_arg is None)):
             raise ValueError(f"topk_search({precision}) needs fp32 operands")
         if need_hi and (q.hi is None or db.hi is None or (prec == native.PREC_BF16X3 and (q.lo is None or db.lo is None))):
             raise ValueError(f"topk_search({precision}) needs bf16 operand planes")
@@ -282,7 +350,7 @@ class Engine:
                 Q, N, D, native.ptr(q_fold), native.ptr(db_fold), int(fold_sorted),
                 int(idx_base), int(k), prec, native.ptr(q.stats), native.ptr(db.stats),
                 keys.data_ptr(), native.ptr(status), native.ptr(self.last_unverified if status is not None else None),
-                ws_ptr, ws_bytes, self._stream()))
+                ws_ptr, ws_bytes, lazy_arg, self._stream()))
         self.launches += 2 if status is None else 6
         if status is not None:
             self._status_log.append(status)
@@ -330,7 +398,8 @@ class Engine:
         """Stage 3: exact fp32 scores of the candidates that can reach the global Top-K.  Returns ONE int64 buffer
         [Q*k + ceil(Q/2)] -- the shard's exact keys [Q, k] followed by its float32 bounds [Q] -- so that keys and
         bounds travel in a single all-gather (``split_payload`` takes it apart)."""
-        if q.f32 is None or db.f32 is None or q.stats is None or db.stats is None:
+        lazy_arg, _lazy_keep = _lazy_arg(db) if db.f32 is None else (None, None)
+        if q.f32 is None or (db.f32 is None and lazy_arg is None and db.n) or q.stats is None or db.stats is None:
             raise ValueError("rescore_candidates needs fp32 operands prepared with stats")
         Q, N, D = q.n, db.n, q.dim
         payload = torch.zeros((Q * k + (Q + 1) // 2,), dtype=torch.int64, device=self.device)
@@ -342,9 +411,9 @@ class Engine:
             return payload
         with torch.cuda.device(self.device):
             native.check(self.lib.emr2a_rescore_candidates(
-                cand.data_ptr(), tau.data_ptr(), native.ptr(kth_floor), q.f32.data_ptr(), _ld(q.f32), db.f32.data_ptr(),
-                _ld(db.f32), Q, N, D, int(idx_base), int(k), q.stats.data_ptr(), db.stats.data_ptr(), keys.data_ptr(),
-                bounds.data_ptr(), self._stream()))
+                cand.data_ptr(), tau.data_ptr(), native.ptr(kth_floor), q.f32.data_ptr(), _ld(q.f32), native.ptr(db.f32),
+                _ld(db.f32) if db.f32 is not None else 0, Q, N, D, int(idx_base), int(k), q.stats.data_ptr(),
+                db.stats.data_ptr(), keys.data_ptr(), bounds.data_ptr(), lazy_arg, self._stream()))
         self.launches += 1
         return payload
 
@@ -392,7 +461,8 @@ class Engine:
         out = torch.zeros((n, k), dtype=torch.int64, device=self.device)
         if n == 0:
             return out
-        if q.f32 is None or (db.n and db.f32 is None):
+        lazy_arg, _lazy_keep = _lazy_arg(db) if (db.f32 is None and db.n) else (None, None)
+        if q.f32 is None or (db.n and db.f32 is None and lazy_arg is None):
             raise ValueError("exact_rescan needs fp32 operands")
         ws_bytes = int(self.lib.emr2a_exact_rescan_workspace_bytes(n, k))
         ws = torch.empty((ws_bytes + 256,), dtype=torch.uint8, device=self.device)
@@ -401,9 +471,10 @@ class Engine:
             db_fold = self.to_device(db_fold, torch.uint8)
         with torch.cuda.device(self.device):
             native.check(self.lib.emr2a_exact_rescan(
-                q.f32.data_ptr(), _ld(q.f32), db.f32.data_ptr() if db.n else q.f32.data_ptr(), _ld(db.f32) if db.n else q.dim,
+                q.f32.data_ptr(), _ld(q.f32), native.ptr(db.f32) if db.n else q.f32.data_ptr(),
+                (_ld(db.f32) if db.f32 is not None else 0) if db.n else q.dim,
                 db.n, q.dim, int(idx_base), int(k), native.ptr(q_fold), native.ptr(db_fold), flag_list.data_ptr(), n,
-                out.data_ptr(), _round_up(ws.data_ptr(), 256), ws_bytes, self._stream()))
+                out.data_ptr(), _round_up(ws.data_ptr(), 256), ws_bytes, lazy_arg, self._stream()))
         self.launches += 2
         return out
 
@@ -500,7 +571,8 @@ class Engine:
         n_q = int(q_segs[0].shape[0])
         dim = sum(int(s.shape[1]) for s in db_segs if s is not None)
         prec = self.pick_precision(n_q, n_db, dim, k, precision)
-        db = self.prepare(db_segs[0], db_segs[1] if len(db_segs) > 1 else None, db_weights[0], db_weights[1], db_flags, prec)
+        db = self.prepare(db_segs[0], db_segs[1] if len(db_segs) > 1 else None, db_weights[0], db_weights[1], db_flags, prec,
+                          defer_f32=True)      # the database's fp32 rows are re-created for the re-scored candidates only
         qs = self.prepare(q_segs[0], q_segs[1] if len(q_segs) > 1 else None, q_weights[0], q_weights[1], q_flags, prec)
         keys = self.topk_search(qs, db, k, prec, q_fold=q_fold, db_fold=db_fold)
         res = self.vote_metrics(keys, db_labels, q_labels, n_classes, k_list=k_list, wacc_f32=wacc_f32,
@@ -710,7 +782,7 @@ class Engine:
             h2d += sum((hi - lo) * int(s.shape[1]) * s.element_size() for s in db_host)
             compute.wait_event(copied[sl])
             segs = [b[:hi - lo] for b in slots[sl]]
-            db = self.prepare(segs[0], segs[1] if len(segs) > 1 else None, 1.0, 1.0, db_flags, prec)
+            db = self.prepare(segs[0], segs[1] if len(segs) > 1 else None, 1.0, 1.0, db_flags, prec, defer_f32=True)
             parts.append(self.topk_search(qs, db, k, prec, idx_base=row_offset + lo))
             freed[sl].record(compute)
             n_chunks += 1

@@ -18,7 +18,7 @@ F32, BF16 = 0, 1
 NF_SEGNORM, NF_ROWNORM, NF_ZERO_GUARD, NF_STANDARDIZE = 1, 2, 4, 8
 PREC_FP32, PREC_BF16X3, PREC_BF16X1, PREC_BF16_RESCORE = 0, 1, 2, 3
 SCORE_NONE, SCORE_ZSCORE, SCORE_MINMAX = 0, 1, 2
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 _p = C.c_void_p
 _i64 = C.c_int64
@@ -31,20 +31,20 @@ _SIGNATURES = {
     "emr2a_last_error": (C.c_char_p, []),
     "emr2a_device_check": (_int, [C.POINTER(_int), C.POINTER(_int), C.POINTER(_int)]),
     "emr2a_normalize_fuse": (_int, [_p, _p, _i64, _int, _int, _i64, _i64, _f, _f, _int, _int,
-                                    _p, _i64, _p, _p, _i64, _p, _p, _p, _p]),
+                                    _p, _i64, _p, _p, _i64, _p, _p, _p, _p, _p]),
     "emr2a_scores": (_int, [_p, _p, _i64, _i64, _int, _i64, _i64, _p, _i64, _p]),
     "emr2a_euclid_workspace_bytes": (_sz, [_i64]),
     "emr2a_euclid_scores": (_int, [_p, _p, _i64, _int, _i64, _p, _p, _sz, _p]),
     "emr2a_late_fuse_scores": (_int, [_p, _p, _i64, _i64, _i64, _f, _f, _int, _p, _i64, _p]),
     "emr2a_topk_search_workspace_bytes": (_sz, [_i64, _i64, _int, _int, _int]),
     "emr2a_topk_search": (_int, [_p, _i64, _p, _p, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _int, _p, _p, _int,
-                                 _i64, _int, _int, _p, _p, _p, _p, _p, _p, _sz, _p]),
+                                 _i64, _int, _int, _p, _p, _p, _p, _p, _p, _sz, _p, _p]),
     "emr2a_topk_filter_workspace_bytes": (_sz, [_i64, _i64, _int, _int]),
     "emr2a_topk_filter": (_int, [_p, _i64, _p, _i64, _i64, _i64, _int, _p, _p, _int, _i64, _int, _p, _p, _p, _p, _sz, _p]),
-    "emr2a_rescore_candidates": (_int, [_p, _p, _p, _p, _i64, _p, _i64, _i64, _i64, _int, _i64, _int, _p, _p, _p, _p, _p]),
+    "emr2a_rescore_candidates": (_int, [_p, _p, _p, _p, _i64, _p, _i64, _i64, _i64, _int, _i64, _int, _p, _p, _p, _p, _p, _p]),
     "emr2a_verify_merged": (_int, [_p, _int, _i64, _p, _int, _i64, _p, _p, _p]),
     "emr2a_exact_rescan_workspace_bytes": (_sz, [_int, _int]),
-    "emr2a_exact_rescan": (_int, [_p, _i64, _p, _i64, _i64, _int, _i64, _int, _p, _p, _p, _int, _p, _p, _sz, _p]),
+    "emr2a_exact_rescan": (_int, [_p, _i64, _p, _i64, _i64, _int, _i64, _int, _p, _p, _p, _int, _p, _p, _sz, _p, _p]),
     "emr2a_topk_merge": (_int, [_p, _int, _i64, _int, _i64, _i64, _int, _p, _p]),
     "emr2a_keys_map_rows": (_int, [_p, _i64, _p, _i64, _i64, _p]),
     "emr2a_vote_metrics": (_int, [_p, _i64, _int, _p, _i64, _p, _p, _int, _int, C.POINTER(C.c_int32), _int, _int,
@@ -64,6 +64,13 @@ _SIGNATURES = {
                                             _p, _p, _sz, _p, _p]),
     "emr2a_debug_unit_clocks": (_int, [_p, _i64, _p]),
 }
+
+
+class LazyRows(C.Structure):
+    """``emr2a_lazy_rows`` of include/emr2a.h: deferred fp32 rows (raw rows + the divisors K1 recorded)."""
+    _fields_ = [("seg0", C.c_void_p), ("seg1", C.c_void_p), ("d0", C.c_int32), ("d1", C.c_int32),
+                ("ld0", C.c_int64), ("ld1", C.c_int64), ("dtype", C.c_int32), ("w0", C.c_float), ("w1", C.c_float),
+                ("flags", C.c_int32), ("row_div", C.c_void_p)]
 
 
 def symbols():

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define EMR2A_ABI_VERSION 9
+#define EMR2A_ABI_VERSION 10
 
 enum emr2a_status {
   EMR2A_OK = 0,
@@ -100,6 +100,7 @@ int emr2a_device_check(int* sm_count, int* cc_major, int* cc_minor);
  *   inv_norm_out [n]       1 / (||row|| + 1e-8) of the final division (1.0 without ROWNORM)
  *   col_std [3][d0+d1]     with EMR2A_NF_STANDARDIZE: per-column mean | scale | RN(1/scale) of the fitted scaler
  *                          (fp32, 16-byte aligned; fp32 rows in and out, up to 2048 columns); NULL otherwise
+ *   row_div_out [n][4]     the divisors used per row (deferred fp32 rows, see emr2a_lazy_rows below); NULL otherwise
  *   stats_out [2]          running maxima over the rows (atomic max; zero it before the first call):
  *                          [0] = max ||out row||, [1] = max ||out row - bf16(out row)||; needs out_hi.
  *                          Input of the EMR2A_PREC_BF16_RESCORE error bound.
@@ -108,7 +109,32 @@ int emr2a_normalize_fuse(const void* seg0, const void* seg1, int64_t n, int d0, 
                          int64_t ld0, int64_t ld1, float w0, float w1, int flags, int in_dtype,
                          float* out_f32, int64_t ld_f32,
                          uint16_t* out_hi, uint16_t* out_lo, int64_t ld_bf16,
-                         float* inv_norm_out, float* stats_out, const float* col_std, void* stream);
+                         float* inv_norm_out, float* stats_out, const float* col_std,
+                         float* row_div_out, void* stream);
+
+/*
+ * Deferred fp32 rows.  The EMR2A_PREC_BF16_RESCORE arm reads the fp32 rows of the DATABASE only for the few
+ * candidates it re-scores (and for the rare exact re-scan), so K1 does not have to write them: with out_f32 = NULL
+ * and row_div_out [n][4] (16-byte aligned; not with EMR2A_NF_STANDARDIZE) K1 records the divisors it used per row --
+ *   [0] ||seg0|| + 1e-8, [1] ||seg1|| + 1e-8 (1.0 without SEGNORM), [2] the row divisor, [3] 1.0 if it was applied --
+ * and the search re-creates an element from the RAW row on the fly: x -> RN(x / n_seg) -> * w -> RN(. / n_row), the
+ * same correctly rounded IEEE operations on the same inputs, hence the same fp32 value bit for bit
+ * (utils/cv_evaluator.py:95-105 are those operations in numpy).  K1 then moves 6 instead of 10 bytes per fp32 input
+ * element and the database needs no fp32 copy in HBM.  This struct (HOST memory, device pointers inside) describes
+ * such rows to emr2a_topk_search / emr2a_rescore_candidates / emr2a_exact_rescan in place of db_f32; the raw rows
+ * must stay alive and unchanged until those calls have run.  Segment widths and leading dimensions must be multiples
+ * of 4 elements, pointers 16-byte (fp32) / 8-byte (bf16) aligned.
+ */
+typedef struct emr2a_lazy_rows {
+  const void* seg0;       /* raw rows as passed to emr2a_normalize_fuse */
+  const void* seg1;       /* NULL with d1 = 0 */
+  int32_t d0, d1;
+  int64_t ld0, ld1;
+  int32_t dtype;          /* EMR2A_F32 / EMR2A_BF16 */
+  float w0, w1;
+  int32_t flags;          /* emr2a_nf_flags of that call */
+  const float* row_div;   /* row_div_out of that call */
+} emr2a_lazy_rows;
 
 /*
  * Full score matrix out[q, j] = <q_q, db_j> in fp32 (CUDA cores), for the API
@@ -163,6 +189,7 @@ int emr2a_late_fuse_scores(const float* text_scores, const float* image_scores, 
  *       marked in unverified_out.
  * unverified_out (uint8 [Q], nullable, BF16_RESCORE only): 1 for every query the bound could not verify
  *   (complete even when the re-scan list overflowed), 0 otherwise.
+ * db_lazy (nullable, BF16_RESCORE only): deferred fp32 database rows (see emr2a_lazy_rows) instead of db_f32.
  */
 size_t emr2a_topk_search_workspace_bytes(int64_t Q, int64_t N, int D, int K, int precision);
 int emr2a_topk_search(const float* q_f32, int64_t ldq_f32,
@@ -174,7 +201,7 @@ int emr2a_topk_search(const float* q_f32, int64_t ldq_f32,
                       int64_t idx_base, int K, int precision,
                       const float* q_stats, const float* db_stats,
                       uint64_t* out_keys, int32_t* status_out, uint8_t* unverified_out,
-                      void* workspace, size_t ws_bytes, void* stream);
+                      void* workspace, size_t ws_bytes, const emr2a_lazy_rows* db_lazy, void* stream);
 
 /*
  * K2 in stages for COOPERATIVE ROW SHARDS (EMR2A_PREC_BF16_RESCORE arithmetic).  When the database is row-sharded
@@ -203,7 +230,8 @@ int emr2a_topk_search(const float* q_f32, int64_t ldq_f32,
  *                               lists out_keys [n_flagged, K]; the caller merges them across shards and writes
  *                               them over the flagged rows.
  * Results are bit-identical to emr2a_topk_search on the unsharded database (same fp32 re-scoring arithmetic, same
- * tie rule).  Operand requirements are those of EMR2A_PREC_BF16_RESCORE (K <= 10).
+ * tie rule).  Operand requirements are those of EMR2A_PREC_BF16_RESCORE (K <= 10); db_lazy (nullable) replaces db_f32
+ * as in emr2a_topk_search.
  */
 size_t emr2a_topk_filter_workspace_bytes(int64_t Q, int64_t N, int D, int K);
 int emr2a_topk_filter(const uint16_t* q_hi, int64_t ldq_bf16, const uint16_t* db_hi, int64_t lddb_bf16,
@@ -216,7 +244,7 @@ int emr2a_rescore_candidates(const uint64_t* cand, const uint32_t* tau, const fl
                              const float* q_f32, int64_t ldq_f32, const float* db_f32, int64_t lddb_f32,
                              int64_t Q, int64_t N, int D, int64_t idx_base, int K,
                              const float* q_stats, const float* db_stats,
-                             uint64_t* out_keys, float* bound_out, void* stream);
+                             uint64_t* out_keys, float* bound_out, const emr2a_lazy_rows* db_lazy, void* stream);
 int emr2a_verify_merged(const uint64_t* keys, int K, int64_t Q, const float* bounds, int parts,
                         int64_t bounds_stride, uint8_t* flags_out, int32_t* status_out, void* stream);
 size_t emr2a_exact_rescan_workspace_bytes(int n_flagged, int K);
@@ -224,7 +252,8 @@ int emr2a_exact_rescan(const float* q_f32, int64_t ldq_f32, const float* db_f32,
                        int64_t N, int D, int64_t idx_base, int K,
                        const uint8_t* q_fold, const uint8_t* db_fold,
                        const int32_t* flag_list, int n_flagged,
-                       uint64_t* out_keys, void* workspace, size_t ws_bytes, void* stream);
+                       uint64_t* out_keys, void* workspace, size_t ws_bytes,
+                       const emr2a_lazy_rows* db_lazy, void* stream);
 
 /*
  * K3 -- merge `parts` partial Top-K lists per query into one.  Every input list must be sorted

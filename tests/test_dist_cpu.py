@@ -86,7 +86,7 @@ class _StubEngine:
     def pick_precision(self, q, n, d, k, requested="auto"):
         return "fp32"
 
-    def prepare(self, s0, s1, w0, w1, flags, prec):
+    def prepare(self, s0, s1, w0, w1, flags, prec, defer_f32=False):
         mats = [np.asarray(s0, dtype=np.float32) * np.float32(w0)] + ([np.asarray(s1, dtype=np.float32) * np.float32(w1)] if s1 is not None else [])
         rows = np.concatenate(mats, axis=1)
         from emr2a_b200.engine import Operand
