@@ -74,6 +74,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-c5", action="store_true", help="N > 1: skip the C5 sub-record next to the C2 headline")
+    ap.add_argument("--shard-of", type=int, default=int(os.environ.get("EMR2A_BENCH_SHARD_OF", 1)),
+                    help="profiling aid (single GPU): search only shard 0 of this many row shards, i.e. the kernel a rank of "
+                         "an N-GPU run launches -- ncu cannot follow a multi-rank job; the line is marked and is not a bench value")
     return ap.parse_args()
 
 
@@ -614,6 +617,8 @@ def main():
     n_db, d_img, d_txt, n_q, k, n_cls, seed = WORKLOADS[args.workload]
     dim = d_img + d_txt
     lo, hi = shard_range(n_db, rank, world)
+    if world == 1 and args.shard_of > 1:
+        lo, hi = shard_range(n_db, 0, args.shard_of)
     flags = native.NF_SEGNORM | native.NF_ROWNORM          # normalise each modality, concat, normalise (a12+a13)
     q_weights = (1.0, 1.0)
     in_dtype = torch.float32
@@ -784,7 +789,7 @@ def main():
 
     # ---- CPU baseline + parity on the sample (rank 0, N = 1): the reference loop against ALL database rows ----
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.shard_of == 1:
         _, feed = _oracle()
         pick = torch.linspace(0, n_q - 1, min(args.cpu_sample, n_q), device=dev).long()
         got = {nm: res[nm][pick].cpu().numpy() for nm in ("top_idx", "top_scores", "pred_vote", "pred_weighted")}
@@ -815,6 +820,8 @@ def main():
                            "step": "K1 normalise+fuse (db shard + queries) -> K2 GEMM+Top-K -> K3 merge -> K4 vote"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                 "unverified_queries": int(unverified_total),
+                **({"profiling_aid": f"shard 0 of {args.shard_of} only ({hi - lo} rows): not a bench value"}
+                   if world == 1 and args.shard_of > 1 else {}),
                 "accuracy": {"top1": float(hits[0]) / n_q, f"top{k}": float(hits[3]) / n_q,
                              "vote_acc": float(res["vote_counts"][0, 1]) / n_q}}
 

@@ -147,6 +147,18 @@ __global__ void __launch_bounds__(256, WPQ == 1 ? (SRC == 0 ? 4 : 3) : 1) rescor
   if (p.kth_floor != nullptr) kth_lb = fmaxf(kth_lb, __ldg(p.kth_floor + q));      // another shard already holds K better rows
   float cut = kth_lb - 2.0f * E;
   bool done = false, tightened = false;
+  // deferred fp32 rows: every lane fetches the recorded divisors of ITS candidates now (all gathers in flight at once);
+  // the groups below pick them up with shuffles instead of paying a dependent 16-byte gather per group
+  float4 rdiv[SRC == 0 ? 1 : 2];
+  if (SRC != 0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      rdiv[SRC == 0 ? 0 : h] = make_float4(1.f, 1.f, 1.f, 0.f);
+      if (akey[h] != 0ull && key_score(akey[h]) >= cut)
+        rdiv[SRC == 0 ? 0 : h] = __ldg(reinterpret_cast<const float4*>(p.lazy.row_div) +
+                                       (static_cast<int64_t>(key_index(akey[h])) - p.idx_base));
+    }
+  }
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     for (int g = 0; g < 32 && !done && h * 32 + g < p.KP; g += 4) {
@@ -164,8 +176,14 @@ __global__ void __launch_bounds__(256, WPQ == 1 ? (SRC == 0 ? 4 : 3) : 1) rescor
         LazyRowCtx ctx[SRC == 0 ? 1 : 4];
         if (SRC != 0) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            if (kk[c] != 0ull) ctx[SRC == 0 ? 0 : c] = lazy_row_ctx(p.lazy, static_cast<int64_t>(key_index(kk[c])) - p.idx_base);
+          for (int c = 0; c < 4; ++c) {
+            float4 d;
+            d.x = __shfl_sync(0xffffffffu, rdiv[SRC == 0 ? 0 : h].x, g + c);
+            d.y = __shfl_sync(0xffffffffu, rdiv[SRC == 0 ? 0 : h].y, g + c);
+            d.z = __shfl_sync(0xffffffffu, rdiv[SRC == 0 ? 0 : h].z, g + c);
+            d.w = __shfl_sync(0xffffffffu, rdiv[SRC == 0 ? 0 : h].w, g + c);
+            ctx[SRC == 0 ? 0 : c] = lazy_ctx_from(p.lazy, d);
+          }
         }
 #pragma unroll 2
         for (int e = lane * 4; e < p.D; e += 128) {

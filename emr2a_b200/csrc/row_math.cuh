@@ -95,14 +95,16 @@ struct LazyRowCtx {
   bool seg, weight, row;
 };
 
-__device__ __forceinline__ LazyRowCtx lazy_row_ctx(const LazyRows& L, int64_t row) {
-  const float4 d = __ldg(reinterpret_cast<const float4*>(L.row_div) + row);
+__device__ __forceinline__ LazyRowCtx lazy_ctx_from(const LazyRows& L, const float4& d) {
   LazyRowCtx c;
   c.n0 = row_div(d.x); c.n1 = row_div(d.y); c.dv = row_div(d.z);
   c.seg = (L.flags & EMR2A_NF_SEGNORM) != 0;
   c.weight = L.w0 != 1.0f || L.w1 != 1.0f;
   c.row = d.w != 0.f;
   return c;
+}
+__device__ __forceinline__ LazyRowCtx lazy_row_ctx(const LazyRows& L, int64_t row) {
+  return lazy_ctx_from(L, __ldg(reinterpret_cast<const float4*>(L.row_div) + row));
 }
 
 // elements [e, e + 4) of output row `row` (e % 4 == 0; d0 % 4 == 0 so that a chunk never straddles the segments)

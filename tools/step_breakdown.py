@@ -15,7 +15,7 @@ prec = os.environ.get("PREC", "rescore")
 def ev(): return torch.cuda.Event(enable_timing=True)
 for it in range(6):
     e = [ev() for _ in range(6)]
-    e[0].record(); db = eng.prepare(di, dt, 1.0, 1.0, flags, prec)
+    e[0].record(); db = eng.prepare(di, dt, 1.0, 1.0, flags, prec, defer_f32=True)   # EMR2A_DEFER_F32=0: materialised fp32 rows
     e[1].record(); qs = eng.prepare(qi, qt, 1.0, 1.0, flags, prec)
     e[2].record(); keys = eng.topk_search(qs, db, k, prec)
     e[3].record(); st = eng.consume_status()
