@@ -111,6 +111,14 @@ def tensor_peak(pk, load_seconds):
     return pk["tflops_burst"], f"bf16 burst (continuous load {load_seconds:.1f} s < 1.5 s)"
 
 
+def device_index():
+    """CUDA device of this rank.  With fewer ranks than visible GPUs the ranks are spread evenly over the devices
+    (emr2a_b200.dist.spread_device: neighbouring GPUs share a host bridge and its host-memory bandwidth)."""
+    from emr2a_b200.dist import spread_device
+    lr = int(os.environ.get("LOCAL_RANK", 0))
+    return spread_device(lr, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", 1))))
+
+
 def k2_traffic(workload, precision, world):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture for this workload
     (profiles/k2_traffic.json names the capture each figure comes from); None when there is no capture of it."""
@@ -444,7 +452,7 @@ def run_c5(args):
     import torch.distributed as dist
     from emr2a_b200.engine import get_engine
     world = int(os.environ.get("WORLD_SIZE", 1)); rank = int(os.environ.get("RANK", 0))
-    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    local_rank = device_index()
     torch.cuda.set_device(local_rank); dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -602,12 +610,12 @@ def main():
     import torch
     import torch.distributed as dist
     from emr2a_b200 import native, synth
-    from emr2a_b200.dist import gather_keys, shard_range, sharded_search_and_vote
+    from emr2a_b200.dist import gather_keys, h2d_rates, shard_range, sharded_search_and_vote, weighted_ranges
     from emr2a_b200.engine import get_engine
 
     world = int(os.environ.get("WORLD_SIZE", 1))
     rank = int(os.environ.get("RANK", 0))
-    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    local_rank = device_index()           # the GPU of this rank: spread over the visible devices (dist.spread_device)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -707,7 +715,22 @@ def main():
     # ---- e2e: host (pinned) inputs through the public host-buffer API ----
     e2e = None
     if not args.no_e2e:
-        h_img = db_img.cpu().pin_memory(); h_txt = db_txt.cpu().pin_memory()
+        # Host-resident shards: the step is bound by the copy to the device, and the ranks' links to host memory are
+        # not equally fast under concurrent load (8-GPU boxes of this pool: 23 GB/s per GPU for GPUs 0-3, 35 GB/s for
+        # GPUs 4-7, tools/h2d_probe.py).  The rows are therefore dealt out in proportion to each rank's measured
+        # concurrent H2D rate, so that all ranks finish their copies together (dist.h2d_rates / weighted_ranges;
+        # EMR2A_E2E_WEIGHTED=0: equal shards).  Row indices are global, the results do not depend on the split.
+        e_lo, e_hi, h2d_gbs = lo, hi, None
+        if world > 1 and os.environ.get("EMR2A_E2E_WEIGHTED", "1") != "0":
+            h2d_gbs = h2d_rates(dev)
+            e_lo, e_hi = weighted_ranges(n_db, h2d_gbs)[rank]
+        if (e_lo, e_hi) == (lo, hi):
+            h_img = db_img.cpu().pin_memory(); h_txt = db_txt.cpu().pin_memory()
+        else:
+            del db_img, db_txt
+            h_img = synth.device_block(e_lo, e_hi - e_lo, d_img, n_cls, seed, dev, label_seed=seed, dtype=gen_dt)[0].cpu().pin_memory()
+            h_txt = synth.device_block(e_lo, e_hi - e_lo, d_txt, n_cls, seed + 1, dev, label_seed=seed, dtype=gen_dt)[0].cpu().pin_memory()
+            db_img = db_txt = None
         hq_img = q_img.cpu().pin_memory(); hq_txt = q_txt.cpu().pin_memory()
         h_lab = db_labels.cpu().pin_memory(); hq_lab = q_labels.cpu().pin_memory()
 
@@ -717,7 +740,7 @@ def main():
         def e2e_step():
             return eng.search_and_vote_host((h_img, h_txt), (hq_img, hq_txt), h_lab, hq_lab, n_cls, k,
                                             db_flags=flags, q_flags=flags, q_weights=q_weights, k_list=k_list,
-                                            precision=args.precision, row_offset=lo, reduce_fn=reduce_fn,
+                                            precision=args.precision, row_offset=e_lo, reduce_fn=reduce_fn,
                                             chunk_rows=(int(os.environ["EMR2A_E2E_CHUNK"]) if "EMR2A_E2E_CHUNK" in os.environ else None))
         for _ in range(2):
             out = e2e_step()
@@ -738,6 +761,11 @@ def main():
         e2e = {"value": n_q / (e_ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": int(out["h2d_bytes"]),
                "d2h_bytes_per_step": int(out["d2h_bytes"]), "ms_per_step": e_ms,
                "api": "emr2a_b200.engine.Engine.search_and_vote_host (pinned host inputs, chunked H2D overlapped with K1/K2)"}
+        if world > 1:
+            e2e["h2d_bytes_per_step_note"] = "rank 0's bytes; every rank copies its own shard"
+            if h2d_gbs is not None:
+                e2e["shards"] = {"rows_rank0": e_hi - e_lo, "split": "proportional to each rank's concurrent H2D rate",
+                                 "h2d_gbs_per_rank": [round(x, 1) for x in h2d_gbs]}
         # the two paths must agree bit for bit
         assert torch.equal(out["top_idx"], res["top_idx"].cpu()), "e2e and device-resident results differ"
         del h_img, h_txt

@@ -119,7 +119,7 @@ __device__ __forceinline__ void query_norms(const float* __restrict__ qrow, int 
 // 16 groups of dependent row gathers is pure latency (~90 us at D = 1024); selection and verification are then done
 // by warp 0 from the exact keys the warps exchanged through shared memory.
 template <bool VEC, int WPQ, int SRC = 0>
-__global__ void __launch_bounds__(256, WPQ == 1 ? (SRC == 0 ? 4 : 3) : 1) rescore_select_kernel(const RescoreParams p) {
+__global__ void __launch_bounds__(256, WPQ == 1 ? (SRC == 0 ? 4 : 2) : 1) rescore_select_kernel(const RescoreParams p) {
   static_assert(SRC == 0 || VEC, "deferred fp32 rows need the 128-bit path");
   __shared__ uint64_t xkeys[WPQ == 1 ? 1 : 64];
   const int lane = threadIdx.x & 31;
@@ -188,12 +188,20 @@ __global__ void __launch_bounds__(256, WPQ == 1 ? (SRC == 0 ? 4 : 3) : 1) rescor
 #pragma unroll 2
         for (int e = lane * 4; e < p.D; e += 128) {
           const float4 x = __ldg(reinterpret_cast<const float4*>(qrow + e));
+          typedef typename RawChunk<typename RawOf<SRC>::T>::T Raw;
+          Raw raw[SRC == 0 ? 1 : 4];
+          if (SRC != 0) {                      // all four gathers first, then the arithmetic
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (kk[c] != 0ull)
+                raw[SRC == 0 ? 0 : c] = lazy_raw4<typename RawOf<SRC>::T>(p.lazy, static_cast<int64_t>(key_index(kk[c])) - p.idx_base, e);
+          }
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             if (kk[c] != 0ull) {
               const int64_t row = static_cast<int64_t>(key_index(kk[c])) - p.idx_base;
               const float4 y = SRC == 0 ? __ldg(reinterpret_cast<const float4*>(p.db + row * p.lddb + e))
-                                        : lazy_load4<typename RawOf<SRC>::T>(p.lazy, ctx[SRC == 0 ? 0 : c], row, e);
+                                        : lazy_apply4<typename RawOf<SRC>::T>(p.lazy, ctx[SRC == 0 ? 0 : c], raw[SRC == 0 ? 0 : c], e);
               acc[c] = fmaf(x.x, y.x, acc[c]); acc[c] = fmaf(x.y, y.y, acc[c]);
               acc[c] = fmaf(x.z, y.z, acc[c]); acc[c] = fmaf(x.w, y.w, acc[c]);
             }
@@ -287,18 +295,22 @@ __global__ void __launch_bounds__(256, WPQ == 1 ? (SRC == 0 ? 4 : 3) : 1) rescor
 // Exact re-search of the flagged queries against every database row (fp32, CUDA cores).  A block
 // owns a contiguous row range and walks the flagged queries in groups held in shared memory; each
 // warp keeps one sorted list per query of the group.
-constexpr int FB_WARPS = 8;
+constexpr int FB_WARPS = 8;      // warps per block; wide rows (the query group would not fit beside a second block) take 16
 constexpr int FB_GMAX = 8;
+constexpr int FB_ROWS = 4;     // database rows a warp scores per pass over the query group
 
-template <bool VEC, int SRC = 0>
-__global__ void __launch_bounds__(FB_WARPS * 32) exact_rescan_kernel(const RescoreParams p, int G) {
+// NW = warps per block.  8 (two blocks per SM) while a group of 8 queries fits in 96 KB of shared memory; wider rows
+// (D = 5120: 20 KB per query) run ONE block of 16 warps per SM with up to 200 KB, so that a pass over the database still
+// serves 8 queries -- the passes, not the queries, are what the re-scan costs.
+template <bool VEC, int SRC = 0, int NW = FB_WARPS>
+__global__ void __launch_bounds__(NW * 32, NW == FB_WARPS ? 2 : 1) exact_rescan_kernel(const RescoreParams p, int G) {
   static_assert(SRC == 0 || VEC, "deferred fp32 rows need the 128-bit path");
   extern __shared__ __align__(16) unsigned char fb_smem[];
   const int n = flagged_count(p);
   if (n <= 0) return;
   float* qbuf = reinterpret_cast<float*>(fb_smem);                                   // [G][Dp]
   const int Dp = (p.D + 3) & ~3;
-  uint64_t* lists = reinterpret_cast<uint64_t*>(fb_smem + sizeof(float) * G * Dp);   // [FB_WARPS][G][K]
+  uint64_t* lists = reinterpret_cast<uint64_t*>(fb_smem + sizeof(float) * G * Dp);   // [NW][G][K]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int K = p.K;
   const int64_t per = (p.N + gridDim.x - 1) / gridDim.x;
@@ -312,64 +324,99 @@ __global__ void __launch_bounds__(FB_WARPS * 32) exact_rescan_kernel(const Resco
       const int g = e / Dp, c = e - g * Dp;
       qbuf[e] = c < p.D ? p.q[static_cast<int64_t>(p.flag_list[g0 + g]) * p.ldq + c] : 0.f;
     }
-    for (int e = threadIdx.x; e < FB_WARPS * G * K; e += blockDim.x) lists[e] = 0ull;
+    for (int e = threadIdx.x; e < NW * G * K; e += blockDim.x) lists[e] = 0ull;
     __syncthreads();
     uint64_t kth = 0ull;                             // lane g: K-th best of (this warp, query g)
     const int my_fold = (p.q_fold && lane < gc) ? p.q_fold[p.flag_list[g0 + lane]] : -1;
-    for (int64_t r = r0 + warp; r < r1; r += FB_WARPS) {
-      const int dfold = p.db_fold ? p.db_fold[r] : -2;
-      // every row element is fetched (or re-created) ONCE and used for all queries of the group; per query the fused
-      // multiply-adds run in the order the re-scoring stage uses, so the scores of the two stages are equal bit for bit
-      float acc[FB_GMAX];
+    // A warp walks FB_ROWS rows at a time.  Every row element is fetched (or re-created) ONCE and every query chunk read
+    // from shared memory serves FB_ROWS rows: with one row per warp the kernel was bound by shared-memory bandwidth
+    // (G query reads per row chunk: 0.9-1.4 TB/s of database stream), not by HBM.  Per (row, query) the fused
+    // multiply-adds run in the order the re-scoring stage uses, so the scores of the two stages are equal bit for bit.
+    for (int64_t rb = r0 + static_cast<int64_t>(warp) * FB_ROWS; rb < r1; rb += NW * FB_ROWS) {
+      const int nr = (r1 - rb < FB_ROWS) ? static_cast<int>(r1 - rb) : FB_ROWS;
+      float acc[FB_ROWS][FB_GMAX];
 #pragma unroll
-      for (int g = 0; g < FB_GMAX; ++g) acc[g] = 0.f;
+      for (int r = 0; r < FB_ROWS; ++r)
+#pragma unroll
+        for (int g = 0; g < FB_GMAX; ++g) acc[r][g] = 0.f;
       if (VEC) {
-        LazyRowCtx ctx;
-        if (SRC != 0) ctx = lazy_row_ctx(p.lazy, r);
+        typedef typename RawChunk<typename RawOf<SRC>::T>::T Raw;
+        LazyRowCtx ctx[SRC == 0 ? 1 : FB_ROWS];
+        if (SRC != 0) {
+#pragma unroll
+          for (int r = 0; r < FB_ROWS; ++r)
+            if (r < nr) ctx[SRC == 0 ? 0 : r] = lazy_row_ctx(p.lazy, rb + r);
+        }
+#pragma unroll 2
         for (int c = lane * 4; c < p.D; c += 128) {
-          const float4 y = SRC == 0 ? __ldg(reinterpret_cast<const float4*>(p.db + r * p.lddb + c))
-                                    : lazy_load4<typename RawOf<SRC>::T>(p.lazy, ctx, r, c);
+          Raw raw[FB_ROWS];
+#pragma unroll
+          for (int r = 0; r < FB_ROWS; ++r) {            // FB_ROWS independent 128-bit (fp32) / 64-bit (bf16) loads in flight
+            if (r < nr) {
+              if (SRC == 0) *reinterpret_cast<float4*>(&raw[r]) = __ldg(reinterpret_cast<const float4*>(p.db + (rb + r) * p.lddb + c));
+              else raw[r] = lazy_raw4<typename RawOf<SRC>::T>(p.lazy, rb + r, c);
+            }
+          }
+          float4 y[FB_ROWS];
+#pragma unroll
+          for (int r = 0; r < FB_ROWS; ++r) {
+            if (r < nr) y[r] = SRC == 0 ? *reinterpret_cast<const float4*>(&raw[r])
+                                        : lazy_apply4<typename RawOf<SRC>::T>(p.lazy, ctx[SRC == 0 ? 0 : r], raw[r], c);
+            else y[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
 #pragma unroll
           for (int g = 0; g < FB_GMAX; ++g) {
             if (g < gc) {
               const float4 x = *reinterpret_cast<const float4*>(qbuf + g * Dp + c);
-              acc[g] = fmaf(x.x, y.x, acc[g]); acc[g] = fmaf(x.y, y.y, acc[g]);
-              acc[g] = fmaf(x.z, y.z, acc[g]); acc[g] = fmaf(x.w, y.w, acc[g]);
+#pragma unroll
+              for (int r = 0; r < FB_ROWS; ++r) {
+                acc[r][g] = fmaf(x.x, y[r].x, acc[r][g]); acc[r][g] = fmaf(x.y, y[r].y, acc[r][g]);
+                acc[r][g] = fmaf(x.z, y[r].z, acc[r][g]); acc[r][g] = fmaf(x.w, y[r].w, acc[r][g]);
+              }
             }
           }
         }
       } else {
-        const float* drow = p.db + r * p.lddb;
         for (int c = lane; c < p.D; c += 32) {
-          const float y = __ldg(drow + c);
 #pragma unroll
-          for (int g = 0; g < FB_GMAX; ++g)
-            if (g < gc) acc[g] = fmaf(qbuf[g * Dp + c], y, acc[g]);
+          for (int r = 0; r < FB_ROWS; ++r) {
+            if (r < nr) {
+              const float y = __ldg(p.db + (rb + r) * p.lddb + c);
+#pragma unroll
+              for (int g = 0; g < FB_GMAX; ++g)
+                if (g < gc) acc[r][g] = fmaf(qbuf[g * Dp + c], y, acc[r][g]);
+            }
+          }
         }
       }
 #pragma unroll
-      for (int g = 0; g < FB_GMAX; ++g) {
-        if (g >= gc) break;
-        const float s = warp_sum(acc[g]);
-        if (lane == g && dfold != my_fold) {
-          const uint64_t key = pack_key(s, static_cast<uint32_t>(r + p.idx_base));
-          if (key > kth) {
-            uint64_t* mine = lists + (warp * G + g) * K;
-            int pos = K - 1;
-            while (pos > 0 && mine[pos - 1] < key) { mine[pos] = mine[pos - 1]; --pos; }
-            mine[pos] = key;
-            kth = mine[K - 1];
+      for (int r = 0; r < FB_ROWS; ++r) {
+        if (r >= nr) break;
+        const int dfold = p.db_fold ? p.db_fold[rb + r] : -2;
+#pragma unroll
+        for (int g = 0; g < FB_GMAX; ++g) {
+          if (g >= gc) break;
+          const float s = warp_sum(acc[r][g]);
+          if (lane == g && dfold != my_fold) {
+            const uint64_t key = pack_key(s, static_cast<uint32_t>(rb + r + p.idx_base));
+            if (key > kth) {
+              uint64_t* mine = lists + (warp * G + g) * K;
+              int pos = K - 1;
+              while (pos > 0 && mine[pos - 1] < key) { mine[pos] = mine[pos - 1]; --pos; }
+              mine[pos] = key;
+              kth = mine[K - 1];
+            }
           }
         }
       }
     }
     __syncthreads();
-    // merge the FB_WARPS lists of each query: warp w serves queries w, w+8, ...
-    for (int g = warp; g < gc; g += FB_WARPS) {
+    // merge the NW lists of each query: warp w serves queries w, w + NW, ...
+    for (int g = warp; g < gc; g += NW) {
       uint64_t bound = ~0ull;
       for (int rnk = 0; rnk < K; ++rnk) {
         uint64_t best = 0ull;
-        for (int t = lane; t < FB_WARPS * K; t += 32) {
+        for (int t = lane; t < NW * K; t += 32) {
           const int w = t / K, j = t - w * K;
           const uint64_t key = lists[(w * G + g) * K + j];
           if (key < bound && key > best) best = key;
@@ -524,14 +571,14 @@ size_t rescore_workspace_bytes(int64_t Q, int K) {
          sizeof(uint64_t) * static_cast<size_t>(rescore_fallback_blocks()) * cap * K + 256;
 }
 
-template <int SRC>
+template <int SRC, int NW>
 static int launch_rescan_src(const RescoreParams& p, bool vec, int G, size_t smem, int fb_blocks, cudaStream_t st) {
   if (vec) {
-    EMR2A_CUDA_TRY(cudaFuncSetAttribute(exact_rescan_kernel<true, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    exact_rescan_kernel<true, SRC><<<fb_blocks, FB_WARPS * 32, smem, st>>>(p, G);
+    EMR2A_CUDA_TRY(cudaFuncSetAttribute(exact_rescan_kernel<true, SRC, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+    exact_rescan_kernel<true, SRC, NW><<<fb_blocks, NW * 32, smem, st>>>(p, G);
   } else if constexpr (SRC == 0) {
-    EMR2A_CUDA_TRY(cudaFuncSetAttribute(exact_rescan_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    exact_rescan_kernel<false, 0><<<fb_blocks, FB_WARPS * 32, smem, st>>>(p, G);
+    EMR2A_CUDA_TRY(cudaFuncSetAttribute(exact_rescan_kernel<false, 0, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+    exact_rescan_kernel<false, 0, NW><<<fb_blocks, NW * 32, smem, st>>>(p, G);
   }
   EMR2A_LAUNCH_CHECK("exact_rescan_kernel");
   return EMR2A_OK;
@@ -541,15 +588,22 @@ static int launch_rescan(const RescoreParams& p, int src, cudaStream_t st) {
   const int D = p.D, K = p.K;
   const int Dp = (D + 3) & ~3;
   int G = static_cast<int>((96 * 1024) / (sizeof(float) * Dp));
+  const bool wide = G < FB_GMAX;            // the query group does not fit beside a second block: one 16-warp block per SM
+  if (wide) G = static_cast<int>((200 * 1024 - sizeof(uint64_t) * 16 * FB_GMAX * K) / (sizeof(float) * Dp));
   if (G > FB_GMAX) G = FB_GMAX;
   if (G < 1) return fail(EMR2A_ERR_UNSUPPORTED, "topk_search(rescore): D=%d too large for the exact re-scan", D);
-  const size_t smem = sizeof(float) * G * Dp + sizeof(uint64_t) * FB_WARPS * G * K;
-  const int fb_blocks = rescore_fallback_blocks();
+  const int nw = wide ? 16 : FB_WARPS;
+  const size_t smem = sizeof(float) * G * Dp + sizeof(uint64_t) * nw * G * K;
+  const int fb_blocks = wide ? sm_count() : rescore_fallback_blocks();      // resident blocks: one / two per SM (the workspace holds two)
   const bool vec = rows_vec(p, src);
   if (src != 0 && !vec) return fail(EMR2A_ERR_UNSUPPORTED, "deferred fp32 rows need 16-byte aligned fp32 query rows with D %% 4 == 0");
-  const int rc = src == 0 ? launch_rescan_src<0>(p, vec, G, smem, fb_blocks, st)
-               : src == 1 ? launch_rescan_src<1>(p, vec, G, smem, fb_blocks, st)
-                          : launch_rescan_src<2>(p, vec, G, smem, fb_blocks, st);
+  int rc;
+  if (wide) rc = src == 0 ? launch_rescan_src<0, 16>(p, vec, G, smem, fb_blocks, st)
+               : src == 1 ? launch_rescan_src<1, 16>(p, vec, G, smem, fb_blocks, st)
+                          : launch_rescan_src<2, 16>(p, vec, G, smem, fb_blocks, st);
+  else rc = src == 0 ? launch_rescan_src<0, FB_WARPS>(p, vec, G, smem, fb_blocks, st)
+          : src == 1 ? launch_rescan_src<1, FB_WARPS>(p, vec, G, smem, fb_blocks, st)
+                     : launch_rescan_src<2, FB_WARPS>(p, vec, G, smem, fb_blocks, st);
   if (rc != EMR2A_OK) return rc;
   rescan_merge_kernel<<<static_cast<unsigned>((static_cast<int64_t>(p.cap) * 32 + 255) / 256), 256, 0, st>>>(p, fb_blocks);
   EMR2A_LAUNCH_CHECK("rescan_merge_kernel");

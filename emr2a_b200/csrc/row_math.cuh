@@ -107,15 +107,41 @@ __device__ __forceinline__ LazyRowCtx lazy_row_ctx(const LazyRows& L, int64_t ro
   return lazy_ctx_from(L, __ldg(reinterpret_cast<const float4*>(L.row_div) + row));
 }
 
-// elements [e, e + 4) of output row `row` (e % 4 == 0; d0 % 4 == 0 so that a chunk never straddles the segments)
+// Raw elements [e, e + 4) of row `row` (e % 4 == 0; d0 % 4 == 0 so that a chunk never straddles the segments).  Plain
+// read-only loads, NOT the `asm volatile` streaming loads of K1: the gather kernels issue the loads of several rows
+// before the arithmetic of the first one, and volatile asm statements may not be reordered against each other.
+template <typename InT> struct RawChunk;
+template <> struct RawChunk<float> {
+  typedef float4 T;
+  static __device__ __forceinline__ T ld(const void* base, int64_t elem) {
+    return __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(base) + elem));
+  }
+  static __device__ __forceinline__ float4 widen(const T& r) { return r; }
+};
+template <> struct RawChunk<__nv_bfloat16> {
+  typedef uint2 T;
+  static __device__ __forceinline__ T ld(const void* base, int64_t elem) {
+    return __ldg(reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(base) + elem));
+  }
+  static __device__ __forceinline__ float4 widen(const T& r) { return Loader<__nv_bfloat16>::widen(r); }
+};
 template <typename InT>
-__device__ __forceinline__ float4 lazy_load4(const LazyRows& L, const LazyRowCtx& c, int64_t row, int e) {
+__device__ __forceinline__ typename RawChunk<InT>::T lazy_raw4(const LazyRows& L, int64_t row, int e) {
+  return e < L.d0 ? RawChunk<InT>::ld(L.seg0, row * L.ld0 + e) : RawChunk<InT>::ld(L.seg1, row * L.ld1 + (e - L.d0));
+}
+// K1's arithmetic on a raw chunk: the fp32 values K1 would have stored for elements [e, e + 4) of the row
+template <typename InT>
+__device__ __forceinline__ float4 lazy_apply4(const LazyRows& L, const LazyRowCtx& c, const typename RawChunk<InT>::T& raw, int e) {
   const bool s0 = e < L.d0;
-  float4 v = s0 ? Loader<InT>::load4(L.seg0, row * L.ld0 + e) : Loader<InT>::load4(L.seg1, row * L.ld1 + (e - L.d0));
+  float4 v = RawChunk<InT>::widen(raw);
   if (c.seg) div4(v, s0 ? c.n0 : c.n1);
   if (c.weight) mul4(v, s0 ? L.w0 : L.w1);
   if (c.row) div4(v, c.dv);
   return v;
+}
+template <typename InT>
+__device__ __forceinline__ float4 lazy_load4(const LazyRows& L, const LazyRowCtx& c, int64_t row, int e) {
+  return lazy_apply4<InT>(L, c, lazy_raw4<InT>(L, row, e), e);
 }
 
 }  // namespace emr2a

@@ -23,6 +23,72 @@ def shard_range(n_rows: int, rank: int, world: int, align: int = 256) -> Tuple[i
     return lo, hi
 
 
+def spread_device(local_rank: int, local_world: int, visible: Optional[int] = None) -> int:
+    """Device index for a rank when FEWER ranks than visible GPUs run on the node: the ranks are spread evenly over the
+    devices (4 ranks on an 8-GPU box -> 0, 2, 4, 6) instead of packed onto the first ones.  GPUs are enumerated in PCI
+    order, so neighbours hang off the same host bridge / socket and share its host-memory bandwidth; measured on this
+    pool's 8-GPU boxes (tools/h2d_probe.py, profiles/r02_h2d_topology.md): GPUs 0-3 together get 93 GB/s from host
+    memory, GPUs 4-7 together 142 GB/s, any single GPU 55.6 GB/s -- so {0, 1, 2, 3} move a host-resident database at
+    half the rate of {0, 2, 4, 6}.  NVLink/NVSwitch bandwidth between any two GPUs is the same, so nothing is lost.
+    ``EMR2A_SPREAD_DEVICES=0`` keeps device = local rank."""
+    if visible is None:
+        visible = torch.cuda.device_count()
+    if os.environ.get("EMR2A_SPREAD_DEVICES", "1") == "0" or local_world <= 0 or visible <= local_world or visible % local_world:
+        return local_rank
+    return local_rank * (visible // local_world)
+
+
+_H2D_RATES: Optional[List[float]] = None
+
+
+def h2d_rates(device, mbytes: int = 256, reps: int = 3) -> List[float]:
+    """Host->device rate (GB/s) of EVERY rank while all ranks copy at once (pinned memory, CUDA events), all-gathered:
+    what each rank's link to host memory delivers under the load of a host-resident multi-GPU search.  Cached."""
+    global _H2D_RATES
+    if _H2D_RATES is not None:
+        return _H2D_RATES
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    n = (mbytes << 20) // 4
+    host = torch.empty(n, dtype=torch.float32).pin_memory()
+    buf = torch.empty(n, dtype=torch.float32, device=device)
+    buf.copy_(host, non_blocking=True)
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        buf.copy_(host, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize(device)
+    mine = torch.tensor([reps * n * 4 / (e0.elapsed_time(e1) / 1e3) / 1e9], dtype=torch.float64, device=device)
+    if world > 1:
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        _H2D_RATES = [float(t) for t in allr]
+    else:
+        _H2D_RATES = [float(mine)]
+    return _H2D_RATES
+
+
+def weighted_ranges(n_rows: int, weights: Sequence[float], align: int = 256) -> List[Tuple[int, int]]:
+    """Contiguous, ``align``-row-aligned row ranges [lo, hi) whose sizes are proportional to ``weights`` (one per
+    rank).  For HOST-resident databases the step is bound by the copy to the device, so a rank whose link to host
+    memory is slower takes proportionally fewer rows (``h2d_rates``) and all ranks finish their copies together."""
+    w = [max(float(x), 0.0) for x in weights]
+    total = sum(w)
+    if total <= 0:
+        w, total = [1.0] * len(w), float(len(w))
+    out, lo, acc = [], 0, 0.0
+    for r, x in enumerate(w):
+        acc += x
+        hi = n_rows if r == len(w) - 1 else min(n_rows, int(round(n_rows * acc / total / align)) * align)
+        hi = max(hi, lo)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
 def gather_keys(local_keys: torch.Tensor, group=None) -> torch.Tensor:
     """All-gather [Q, K] packed keys -> [world, Q, K].  Works for CUDA tensors (NCCL) and for
     CPU tensors (gloo; used by the CPU tests of this plumbing)."""
@@ -59,7 +125,7 @@ def sharded_search_and_vote(eng, db_segs_local: Sequence, q_segs: Sequence, db_l
     world = dist.get_world_size() if dist.is_initialized() else 1
     prec = eng.pick_precision(n_q, max(n_db, 1) * world, dim, k, precision)
     db = eng.prepare(db_segs_local[0], db_segs_local[1] if len(db_segs_local) > 1 else None, 1.0, 1.0, db_flags, prec,
-                     defer_f32=True)
+                     defer_f32=eng.defer_default(dim))
     qs = eng.prepare(q_segs[0], q_segs[1] if len(q_segs) > 1 else None, q_weights[0], q_weights[1], q_flags, prec)
     if prec == "rescore" and world > 1 and cooperative and os.environ.get("EMR2A_COOP_SHARDS", "1") != "0":
         return _cooperative_search_and_vote(eng, qs, db, db_labels_global, q_labels, n_classes, k, row_offset, k_list,

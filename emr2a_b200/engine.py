@@ -86,6 +86,11 @@ def _lazy_arg(op: "Operand"):
 
 
 _DEFER_F32 = os.environ.get("EMR2A_DEFER_F32", "1") != "0"
+# Deferred fp32 rows pay when re-creating elements is rare next to K1's saving.  Every exact re-scan pass re-creates the
+# WHOLE database (2.8x the instructions of a pass over materialised rows: ncu, profiles/r02_rescore_stages.md); with
+# wide rows (C4, D = 5120: ~10 of 10k queries need the re-scan, E grows with D) that costs more than K1 saves, so the
+# pipelines defer only up to this many columns.  ``prepare(defer_f32=True)`` itself always defers when it can.
+_DEFER_MAX_DIM = int(os.environ.get("EMR2A_DEFER_MAX_DIM", 2048))
 
 
 class Engine:
@@ -184,6 +189,11 @@ class Engine:
                 native.ptr(out.inv_norm), native.ptr(out.stats), native.ptr(col_std), native.ptr(row_div), self._stream()))
         self.launches += 1
         return out
+
+    @staticmethod
+    def defer_default(dim: int) -> bool:
+        """What the pipelines (search_and_vote, the sharded search, the host-buffer path) pass as ``defer_f32``."""
+        return _DEFER_F32 and dim <= _DEFER_MAX_DIM
 
     @staticmethod
     def can_defer(a: torch.Tensor, b: Optional[torch.Tensor], flags: int) -> bool:
@@ -572,7 +582,7 @@ class Engine:
         dim = sum(int(s.shape[1]) for s in db_segs if s is not None)
         prec = self.pick_precision(n_q, n_db, dim, k, precision)
         db = self.prepare(db_segs[0], db_segs[1] if len(db_segs) > 1 else None, db_weights[0], db_weights[1], db_flags, prec,
-                          defer_f32=True)      # the database's fp32 rows are re-created for the re-scored candidates only
+                          defer_f32=self.defer_default(dim))      # fp32 rows re-created for the re-scored candidates only
         qs = self.prepare(q_segs[0], q_segs[1] if len(q_segs) > 1 else None, q_weights[0], q_weights[1], q_flags, prec)
         keys = self.topk_search(qs, db, k, prec, q_fold=q_fold, db_fold=db_fold)
         res = self.vote_metrics(keys, db_labels, q_labels, n_classes, k_list=k_list, wacc_f32=wacc_f32,
@@ -782,7 +792,8 @@ class Engine:
             h2d += sum((hi - lo) * int(s.shape[1]) * s.element_size() for s in db_host)
             compute.wait_event(copied[sl])
             segs = [b[:hi - lo] for b in slots[sl]]
-            db = self.prepare(segs[0], segs[1] if len(segs) > 1 else None, 1.0, 1.0, db_flags, prec, defer_f32=True)
+            db = self.prepare(segs[0], segs[1] if len(segs) > 1 else None, 1.0, 1.0, db_flags, prec,
+                              defer_f32=self.defer_default(dim))
             parts.append(self.topk_search(qs, db, k, prec, idx_base=row_offset + lo))
             freed[sl].record(compute)
             n_chunks += 1

@@ -86,6 +86,9 @@ class _StubEngine:
     def pick_precision(self, q, n, d, k, requested="auto"):
         return "fp32"
 
+    def defer_default(self, dim):
+        return False
+
     def prepare(self, s0, s1, w0, w1, flags, prec, defer_f32=False):
         mats = [np.asarray(s0, dtype=np.float32) * np.float32(w0)] + ([np.asarray(s1, dtype=np.float32) * np.float32(w1)] if s1 is not None else [])
         rows = np.concatenate(mats, axis=1)
@@ -355,3 +358,28 @@ def test_cooperative_shards_world2_equal_exact_search():
         # the exchange of the K-th best filter score cuts the re-scoring: fewer candidates than shards x lists hold
         assert wide["rescored"] < 64 * 40
     assert outs[0]["narrow"]["unverified"] == outs[1]["narrow"]["unverified"]
+
+
+def test_spread_device_and_weighted_ranges(monkeypatch):
+    from emr2a_b200.dist import spread_device, weighted_ranges
+    monkeypatch.delenv("EMR2A_SPREAD_DEVICES", raising=False)
+    assert [spread_device(r, 4, 8) for r in range(4)] == [0, 2, 4, 6]          # spread over both host bridges
+    assert [spread_device(r, 2, 8) for r in range(2)] == [0, 4]
+    assert [spread_device(r, 8, 8) for r in range(8)] == list(range(8))
+    assert spread_device(0, 1, 8) == 0 and spread_device(2, 3, 8) == 2          # 8 % 3 != 0: left alone
+    assert [spread_device(r, 4, 4) for r in range(4)] == [0, 1, 2, 3]
+    monkeypatch.setenv("EMR2A_SPREAD_DEVICES", "0")
+    assert [spread_device(r, 4, 8) for r in range(4)] == [0, 1, 2, 3]
+    # shard sizes follow the weights, cover every row once, and stay tile-aligned
+    rates = [23.3, 23.4, 23.3, 23.3, 35.5, 35.4, 35.6, 35.6]                    # the pool's 8-GPU boxes (tools/h2d_probe.py)
+    spans = weighted_ranges(1_000_000, rates)
+    assert spans[0][0] == 0 and spans[-1][1] == 1_000_000
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    assert all(lo % 256 == 0 for lo, _ in spans)
+    sizes = np.array([hi - lo for lo, hi in spans], dtype=np.float64)
+    assert np.allclose(sizes / sizes.sum(), np.array(rates) / sum(rates), atol=3e-4)
+    times = sizes / np.array(rates)
+    assert times.max() / times.min() < 1.01                                       # all copies end together
+    assert weighted_ranges(1000, [1, 1]) == [(0, 512), (512, 1000)]
+    assert weighted_ranges(10, [0, 0, 0]) == [(0, 0), (0, 0), (0, 10)]
+    assert weighted_ranges(0, [1, 2]) == [(0, 0), (0, 0)]

@@ -1,0 +1,13 @@
+#!/bin/bash
+O=gpurun_out/r2o
+mkdir -p $O
+timeout 600 python tools/rescore_stage_probe.py > $O/stage_probe.log 2>&1; echo "probe rc=$?"; cat $O/stage_probe.log | tail -6
+timeout 900 python -m pytest tests/test_gpu_deferred_rows.py tests/test_gpu_coop_shards.py tests/test_gpu_kernels.py tests/test_gpu_rescore_bound.py tests/test_gpu_fullsize_oracle.py -x -q > $O/pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest.log
+timeout 900 python bench.py --workload c4 > $O/bench_c4.json 2> $O/bench_c4.err; echo "c4 rc=$?"
+python - <<'PY'
+import json
+for line in open("gpurun_out/r2o/bench_c4.json"):
+    if line.startswith("{"):
+        d=json.loads(line); r=d["roofline"]
+        print("c4 value",round(d["value"]),"ms",round(d["ms_per_step"],3),"k2_ms",round(r["kernel_ms"],3),"frac",round(r["frac"],3),"e2e",round(d["e2e"]["value"]),"unverified",d["unverified_queries"],d["cpu_baseline"]["parity_on_sample"]["ok"])
+PY
