@@ -179,6 +179,37 @@ def test_topk_search_tensor_core(eng, oracle, prec, tol, Q, N, D, K):
         assert list(idx[1][:2]) == [5, 9]               # identical rows give identical scores: index order decides
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3", "rescore"])
+def test_duplicate_rows_resolve_to_the_lowest_index(eng, oracle, prec):
+    """The documented deviation from the reference (include/emr2a.h "packed key"): among EQUAL
+    scores the lowest database index wins, on every arm and across the K boundary.  The reference's
+    `np.argsort(x)[-k:][::-1]` (utils/cv_evaluator.py:123) leaves that order to numpy's sort -- with a stable sort it
+    lists the HIGHEST index first -- so for duplicated embeddings (identical reports in text_only fusion) its Top-K
+    membership at the boundary is one of several equally valid answers; ours is fixed and independent of tile shape,
+    split count and GPU count."""
+    from emr2a_b200.engine import unpack_keys
+    rng = np.random.default_rng(77)
+    N, D, K = 50000, 128, 3
+    db = oracle.unit_rows(rng.standard_normal((N, D)).astype(np.float32))
+    dups = [10, 500, 900, 40000, 49999]                     # five copies of one case, spread over tiles and splits
+    for j in dups[1:]:
+        db[j] = db[dups[0]]
+    qs = oracle.unit_rows(rng.standard_normal((300, D)).astype(np.float32))
+    qs[7] = db[dups[0]]
+    keys = eng.topk_search(eng.prepare(qs, flags=0, precision=prec), eng.prepare(db, flags=0, precision=prec), K, prec)
+    if prec == "rescore":
+        eng.consume_status()
+    scores, idx = unpack_keys(keys)
+    assert list(idx[7]) == dups[:K]                        # K = 3 of the 5 tied rows: the three LOWEST indices
+    assert scores[7][0] == scores[7][1] == scores[7][2]
+    # what numpy does with the same scores: also three of the five copies -- but which three is the sort's business
+    exact = (db.astype(np.float64) @ qs[7].astype(np.float64)).astype(np.float32)
+    ref = np.argsort(exact)[-K:][::-1]
+    assert set(ref) <= set(dups)
+    stable = np.argsort(exact, kind="stable")[-K:][::-1]
+    assert list(stable) == dups[::-1][:K]                   # a stable sort would have kept the three HIGHEST
+
+
 def test_rescore_unverifiable_queries_are_rescanned_exactly(eng, oracle):
     """Adversarial database: for some queries ~100 rows sit within 5e-3 of the best score (5e-5 apart),
     far inside the bf16 filter's error bound, so the bound cannot verify the selection -> those
