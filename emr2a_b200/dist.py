@@ -89,6 +89,25 @@ def weighted_ranges(n_rows: int, weights: Sequence[float], align: int = 256) -> 
     return out
 
 
+def gather_host_rows(host_mats: Sequence[torch.Tensor], device) -> Tuple[List[torch.Tensor], int]:
+    """Every rank holds the same HOST matrices (the queries of a host-resident search).  Each rank copies only its
+    1/world slice of the rows to ``device`` and the slices are all-gathered (NCCL over NVLink; gloo for CPU tensors in
+    the tests).  Returns (device matrices with all rows, bytes this rank copied from the host)."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    out, copied = [], 0
+    for m in host_mats:
+        n = int(m.shape[0])
+        per = (n + world - 1) // world
+        lo, hi = min(rank * per, n), min(rank * per + per, n)
+        mine = torch.zeros((per,) + tuple(m.shape[1:]), dtype=m.dtype, device=device)
+        if hi > lo:
+            mine[:hi - lo].copy_(m[lo:hi], non_blocking=True)
+            copied += (hi - lo) * int(m[0].numel()) * m.element_size()
+        out.append(gather_keys(mine).reshape((world * per,) + tuple(m.shape[1:]))[:n])
+    return out, copied
+
+
 def gather_keys(local_keys: torch.Tensor, group=None) -> torch.Tensor:
     """All-gather [Q, K] packed keys -> [world, Q, K].  Works for CUDA tensors (NCCL) and for
     CPU tensors (gloo; used by the CPU tests of this plumbing)."""

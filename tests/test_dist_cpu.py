@@ -383,3 +383,41 @@ def test_spread_device_and_weighted_ranges(monkeypatch):
     assert weighted_ranges(1000, [1, 1]) == [(0, 512), (512, 1000)]
     assert weighted_ranges(10, [0, 0, 0]) == [(0, 0), (0, 0), (0, 10)]
     assert weighted_ranges(0, [1, 2]) == [(0, 0), (0, 0)]
+
+
+def test_plan_chunks_covers_rows_and_tapers():
+    from emr2a_b200.engine import plan_chunks
+    for n, c in [(98816, 32768), (1_000_000, 32768), (5000, 32768), (0, 32768), (2500, 1000), (1500, 1000), (1001, 1000),
+                 (999, 1000), (300, 256), (7, 3), (1, 1), (125_184, 32768)]:
+        ch = plan_chunks(n, c)
+        assert (not ch and n == 0) or (ch[0][0] == 0 and ch[-1][1] == n)
+        assert all(a[1] == b[0] for a, b in zip(ch, ch[1:]))
+        assert all(0 < hi - lo <= c for lo, hi in ch)                   # every piece fits a chunk-sized staging slot
+    sizes = [hi - lo for lo, hi in plan_chunks(1_000_000, 32768)]
+    assert sizes[0] == 32768 and sizes[-1] <= 8192 and sorted(sizes, reverse=True) == sizes
+
+
+def _gather_rows_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from emr2a_b200.dist import gather_host_rows
+    rng = np.random.default_rng(3)                       # same host matrices on every rank
+    mats = [torch.from_numpy(rng.standard_normal((101, 7)).astype(np.float32)),        # 101 rows: ragged last slice
+            torch.from_numpy(rng.standard_normal((101, 3)).astype(np.float32))]
+    got, copied = gather_host_rows(mats, torch.device("cpu"))
+    q.put((rank, all(torch.equal(g, m) for g, m in zip(got, mats)), copied))
+    dist.destroy_process_group()
+
+
+def test_gather_host_rows_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 35500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gather_rows_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert [o[1] for o in out] == [True, True]
+    assert out[0][2] == 51 * 10 * 4 and out[1][2] == 50 * 10 * 4          # each rank copied only its slice from the host
