@@ -741,7 +741,7 @@ def main():
             return eng.search_and_vote_host((h_img, h_txt), (hq_img, hq_txt), h_lab, hq_lab, n_cls, k,
                                             db_flags=flags, q_flags=flags, q_weights=q_weights, k_list=k_list,
                                             precision=args.precision, row_offset=e_lo, reduce_fn=reduce_fn,
-                                            gather_queries=world > 1,
+                                            gather_queries=world > 1 and os.environ.get("EMR2A_E2E_GATHER_Q", "1") != "0",
                                             chunk_rows=(int(os.environ["EMR2A_E2E_CHUNK"]) if "EMR2A_E2E_CHUNK" in os.environ else None))
         for _ in range(2):
             out = e2e_step()

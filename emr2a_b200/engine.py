@@ -755,8 +755,9 @@ class Engine:
         ``gather_queries`` (multi-GPU, every rank holds the same host queries): a rank copies only its 1/world slice of
         the query rows over its host link and the slices are all-gathered over NVLink -- the replicated query copy is
         the one part of the step that does not shrink with the shard (41 MB per rank for C2: 1.8 ms on a 23 GB/s link).
-        The tail of the database is streamed in shrinking chunks (``plan_chunks``): what cannot overlap with a copy is
-        the search of the LAST chunk, so the last chunks are small."""
+        ``EMR2A_HOST_TAPER=1`` streams the tail of the database in shrinking chunks (``plan_chunks``).  It is off by
+        default: the search of a chunk has a cost per QUERY (re-scoring, merge) that does not shrink with the chunk, so
+        small tail chunks make the un-overlapped end of the step longer, not shorter (measured: e2e -2 %)."""
         def as_host(x):
             return torch.from_numpy(x) if isinstance(x, np.ndarray) else x
         db_host = [as_host(s) for s in db_segs_host if s is not None]
@@ -788,7 +789,8 @@ class Engine:
         freed = [torch.cuda.Event(), torch.cuda.Event()]
         parts: List[torch.Tensor] = []
         n_chunks = 0
-        for c, (lo, hi) in enumerate(plan_chunks(n_db, chunk_rows)):
+        taper = os.environ.get("EMR2A_HOST_TAPER", "0") == "1"
+        for c, (lo, hi) in enumerate(plan_chunks(n_db, chunk_rows, min_rows=4096 if taper else chunk_rows)):
             sl = c % 2
             with torch.cuda.stream(copy):
                 if c >= 2:
