@@ -1,6 +1,7 @@
 // C-ABI glue: error text, device check, emr2a_topk_search dispatch.
 #include "common.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace emr2a {
@@ -47,7 +48,8 @@ int tc_planned_splits(int64_t Q, int64_t N, int min_splits);
 
 size_t rescore_workspace_bytes(int64_t Q, int K);
 int rescore_pipeline(const uint64_t* approx, int KP, const uint32_t* tau, const float* q, int64_t ldq, const float* db,
-                     int64_t lddb, const emr2a_lazy_rows* db_lazy, int64_t Q, int64_t N, int D, int64_t idx_base, int K,
+                     int64_t lddb, const emr2a_lazy_rows* db_lazy, const uint16_t* db_hi, int64_t lddb_hi, int64_t Q, int64_t N,
+                     int D, int64_t idx_base, int K,
                      const float* q_stats, const float* db_stats, const uint8_t* q_fold, const uint8_t* db_fold,
                      uint64_t* out_keys, int* status, uint8_t* qflags, void* workspace, size_t ws_bytes, cudaStream_t st);
 
@@ -61,7 +63,9 @@ int rescore_verify_merged(const uint64_t* keys, int K, int64_t Q, const float* b
 size_t exact_rescan_workspace_bytes(int n_flagged, int K);
 int rescore_exact_rescan(const float* q, int64_t ldq, const float* db, int64_t lddb, const emr2a_lazy_rows* db_lazy, int64_t N,
                          int D, int64_t idx_base, int K, const uint8_t* q_fold, const uint8_t* db_fold, const int* flag_list,
-                         int n_flagged, uint64_t* out_compact, void* workspace, size_t ws_bytes, cudaStream_t st);
+                         int n_flagged, uint64_t* out_compact, void* workspace, size_t ws_bytes, const uint16_t* db_hi,
+                         int64_t lddb_hi, const float* q_stats, const float* db_stats, const uint64_t* seed_keys,
+                         cudaStream_t st);
 
 constexpr int RESCORE_KP = 32;    // candidates kept per (query, database split) by the filter; 16 leaves too little slack (measured)
 constexpr int RESCORE_KPM = 64;   // candidates per query re-scored after merging the splits
@@ -118,7 +122,12 @@ static int rescore_filter_stage(const uint16_t* q_hi, int64_t ldq_bf16, const ui
   // A single-tile batch on single CTAs gets one split per SM (148): 8 rows per split are 1184 candidates, more than
   // the 64 that are re-scored, and keep the merge within its 2048-key register variant.
   const int planned = tc_planned_splits(Q, N, 2);
-  const int kp = planned > 128 ? 8 : ((planned >= 8 || K <= 5) ? 16 : RESCORE_KP);
+  int kp = planned > 128 ? 8 : ((planned >= 8 || K <= 5) ? 16 : RESCORE_KP);
+  {   // experiments: EMR2A_RESCORE_KP = 8 / 16 / 32 overrides the list width per split
+    const char* e = getenv("EMR2A_RESCORE_KP");
+    const int v = (e && *e) ? atoi(e) : 0;
+    if (v == 8 || v == 16 || v == 32) kp = v;
+  }
   int rc = tc_topk_search(q_hi, nullptr, db_hi, nullptr, Q, N, D, ldq_bf16, lddb_bf16, q_fold, db_fold, idx_base,
                           kp, 1, nullptr, tc_ws, tc_ws_bytes, debug_scores, st, &parts, fold_sorted, 2);
   if (rc != EMR2A_OK) return rc;
@@ -179,7 +188,7 @@ static int topk_search_impl(const float* q_f32, int64_t ldq_f32, const uint16_t*
       int rc = rescore_filter_stage(q_hi, ldq_bf16, db_hi, lddb_bf16, Q, N, D, q_fold, db_fold, fold_sorted, idx_base, K,
                                     reinterpret_cast<uint64_t*>(ws), ws + a_bytes, t_bytes, debug_scores, st, &cand, &kpm, &tau);
       if (rc != EMR2A_OK) return rc;
-      return rescore_pipeline(cand, kpm, tau, q_f32, ldq_f32, db_f32, lddb_f32, db_lazy, Q, N, D, idx_base, K, q_stats,
+      return rescore_pipeline(cand, kpm, tau, q_f32, ldq_f32, db_f32, lddb_f32, db_lazy, db_hi, lddb_bf16, Q, N, D, idx_base, K, q_stats,
                               db_stats, q_fold, db_fold, out_keys, status, qflags, ws + a_bytes + t_bytes, r_bytes, st);
     }
     default:
@@ -285,7 +294,9 @@ extern "C" size_t emr2a_exact_rescan_workspace_bytes(int n_flagged, int K) { ret
 extern "C" int emr2a_exact_rescan(const float* q_f32, int64_t ldq_f32, const float* db_f32, int64_t lddb_f32, int64_t N, int D,
                                   int64_t idx_base, int K, const uint8_t* q_fold, const uint8_t* db_fold,
                                   const int32_t* flag_list, int n_flagged, uint64_t* out_keys, void* workspace,
-                                  size_t ws_bytes, const emr2a_lazy_rows* db_lazy, void* stream) {
+                                  size_t ws_bytes, const emr2a_lazy_rows* db_lazy, const uint16_t* db_hi,
+                                  int64_t lddb_bf16, const float* q_stats, const float* db_stats,
+                                  const uint64_t* seed_keys, void* stream) {
   if (!q_f32 || (!db_f32 && !db_lazy && N > 0) || !out_keys || N < 0 || D <= 0 || K <= 0 || n_flagged < 0 || ldq_f32 < D ||
       (!db_lazy && N > 0 && lddb_f32 < D) || (n_flagged > 0 && !flag_list))
     return fail(EMR2A_ERR_INVALID, "exact_rescan: bad arguments");
@@ -299,5 +310,5 @@ extern "C" int emr2a_exact_rescan(const float* q_f32, int64_t ldq_f32, const flo
     return EMR2A_OK;
   }
   return rescore_exact_rescan(q_f32, ldq_f32, db_f32, lddb_f32, db_lazy, N, D, idx_base, K, q_fold, db_fold, flag_list,
-                              n_flagged, out_keys, workspace, ws_bytes, st);
+                              n_flagged, out_keys, workspace, ws_bytes, db_hi, lddb_bf16, q_stats, db_stats, seed_keys, st);
 }

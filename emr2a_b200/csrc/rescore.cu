@@ -26,6 +26,7 @@
 //           appended to a flag list and re-searched exactly against the whole database
 //           (exact_rescan_kernel, cost proportional to the number of flagged queries).
 // Roofline: HBM-bound gather: Q * KP * D * 4 bytes (C2: 1.3 GB, ~0.3 ms).
+#include <stdlib.h>
 #include "row_math.cuh"
 
 namespace emr2a {
@@ -58,6 +59,11 @@ struct RescoreParams {
   LazyRows lazy;            // SRC != 0: the database rows are re-created from the raw rows (row_math.cuh), db is unused
   int n_fixed;              // >= 0: the flag list holds exactly this many queries (emr2a_exact_rescan); < 0: status[0]
   int compact;              // != 0: the re-scan writes list i of the flag list to out[i][K] instead of out[flag_list[i]][K]
+  // filtered re-scan (filtered_rescan_kernel): stream the bf16 plane, score exactly only what can reach the Top-K
+  const uint16_t* db_hi;    // [N][lddb_hi] bf16 plane of the database (K1), zero padded; null = unfiltered re-scan
+  int64_t lddb_hi;
+  const uint64_t* seed;     // optional exact keys whose K-th best seeds the cut: [Q][K] (by query) or [n_flagged][K] (seed_compact)
+  int seed_compact;
 };
 
 __device__ __forceinline__ int flagged_count(const RescoreParams& p) {
@@ -434,6 +440,159 @@ __global__ void __launch_bounds__(NW * 32, NW == FB_WARPS ? 2 : 1) exact_rescan_
   }
 }
 
+// Filtered exact re-scan.  The exact re-scan above reads the fp32 rows of the WHOLE database (or re-creates them) to
+// find a handful of rows.  This one streams the bf16 plane instead -- half the bytes, no re-creation -- and computes
+// the filter score s~' = <bf16(q), bf16(d)> on the CUDA cores (exact products, fp32 accumulation: within the same
+// bound E of the exact score s as the tensor-core filter, error_bound()).  A row is scored exactly -- by the warp, in
+// the arithmetic of the re-scoring stage, from the fp32 rows or the deferred rows -- only if s~' >= cut, where
+// cut = (running K-th best EXACT score of this warp's list, or of the seed list) - E.  Any row that belongs to the
+// final Top-K has s >= final K-th best >= running K-th best, hence s~' >= s - E >= cut: it is scored, so the lists
+// are the exact Top-K.  After a short warm-up almost no row passes and the pass is an HBM stream of the plane.
+constexpr int FR_ROWS = 4;
+
+template <int SRC>
+__global__ void __launch_bounds__(FB_WARPS * 32, 2) filtered_rescan_kernel(const RescoreParams p, int G) {
+  extern __shared__ __align__(16) unsigned char fb_smem[];
+  const int n = flagged_count(p);
+  if (n <= 0) return;
+  const int Dh = (p.D + 7) & ~7;                                                    // bf16 columns walked (plane is zero padded)
+  uint16_t* qh = reinterpret_cast<uint16_t*>(fb_smem);                              // [G][Dh] bf16(q)
+  uint64_t* lists = reinterpret_cast<uint64_t*>(fb_smem + ((sizeof(uint16_t) * G * Dh + 15) & ~static_cast<size_t>(15)));   // [FB_WARPS][G][K]
+  __shared__ float e_of[FB_GMAX], seed_of[FB_GMAX];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int K = p.K;
+  const int64_t per = (p.N + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * per;
+  const int64_t r1 = (r0 + per < p.N) ? r0 + per : p.N;
+
+  for (int g0 = 0; g0 < n; g0 += G) {
+    const int gc = (n - g0 < G) ? (n - g0) : G;
+    __syncthreads();
+    for (int e = threadIdx.x; e < gc * Dh; e += blockDim.x) {
+      const int g = e / Dh, c = e - g * Dh;
+      const float x = c < p.D ? p.q[static_cast<int64_t>(p.flag_list[g0 + g]) * p.ldq + c] : 0.f;
+      qh[e] = __bfloat16_as_ushort(__float2bfloat16_rn(x));
+    }
+    for (int e = threadIdx.x; e < FB_WARPS * G * K; e += blockDim.x) lists[e] = 0ull;
+    for (int g = warp; g < gc; g += FB_WARPS) {          // per query: the error bound and the seed of the cut
+      const int64_t qd = p.flag_list[g0 + g];
+      float nq, rq;
+      query_norms<false>(p.q + qd * p.ldq, p.D, lane, p.q_stats, nq, rq);
+      if (lane == 0) {
+        e_of[g] = error_bound(nq, rq, p.db_stats, p.D);
+        float sd = -INFINITY;
+        if (p.seed != nullptr) {
+          const uint64_t k = p.seed[(p.seed_compact ? static_cast<int64_t>(g0 + g) : qd) * K + K - 1];
+          if (k != 0ull) sd = key_score(k);
+        }
+        seed_of[g] = sd;
+      }
+    }
+    __syncthreads();
+    uint64_t kth = 0ull;                                 // lane g: K-th best exact key of (this warp, query g)
+    const int my_fold = (p.q_fold && lane < gc) ? p.q_fold[p.flag_list[g0 + lane]] : -1;
+    const float my_e = lane < gc ? e_of[lane] : 0.f;
+    float my_cut = lane < gc ? seed_of[lane] - my_e : INFINITY;        // lane g: rows of query g below this are skipped
+    for (int64_t rb = r0 + static_cast<int64_t>(warp) * FR_ROWS; rb < r1; rb += FB_WARPS * FR_ROWS) {
+      const int nr = (r1 - rb < FR_ROWS) ? static_cast<int>(r1 - rb) : FR_ROWS;
+      float acc[FR_ROWS][FB_GMAX];
+#pragma unroll
+      for (int r = 0; r < FR_ROWS; ++r)
+#pragma unroll
+        for (int g = 0; g < FB_GMAX; ++g) acc[r][g] = 0.f;
+      for (int c = lane * 8; c < Dh; c += 256) {
+        float y[FR_ROWS][8];
+#pragma unroll
+        for (int r = 0; r < FR_ROWS; ++r) {
+          uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+          if (r < nr) raw = __ldg(reinterpret_cast<const uint4*>(p.db_hi + (rb + r) * p.lddb_hi + c));
+          const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            y[r][2 * j] = __uint_as_float(w[j] << 16);
+            y[r][2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < FB_GMAX; ++g) {
+          if (g < gc) {
+            const uint4 qr = *reinterpret_cast<const uint4*>(qh + g * Dh + c);
+            const uint32_t w[4] = {qr.x, qr.y, qr.z, qr.w};
+            float x[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              x[2 * j] = __uint_as_float(w[j] << 16);
+              x[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+            }
+#pragma unroll
+            for (int r = 0; r < FR_ROWS; ++r)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[r][g] = fmaf(x[j], y[r][j], acc[r][g]);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < FR_ROWS; ++r) {
+        if (r >= nr) break;
+        const int64_t row = rb + r;
+        const int dfold = p.db_fold ? p.db_fold[row] : -2;
+#pragma unroll
+        for (int g = 0; g < FB_GMAX; ++g) {
+          if (g >= gc) break;
+          const float approx = warp_sum(acc[r][g]);
+          const float cut = __shfl_sync(0xffffffffu, my_cut, g);
+          const int qfold = __shfl_sync(0xffffffffu, my_fold, g);
+          if (approx < cut || dfold == qfold) continue;            // warp-uniform: cannot reach the Top-K / inadmissible
+          // exact score, in the order of the re-scoring stage (128-bit chunks, four fused multiply-adds each, warp sum)
+          const float* qrow = p.q + static_cast<int64_t>(p.flag_list[g0 + g]) * p.ldq;
+          float ex = 0.f;
+          LazyRowCtx ctx;
+          if (SRC != 0) ctx = lazy_row_ctx(p.lazy, row);
+          for (int e = lane * 4; e < p.D; e += 128) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(qrow + e));
+            const float4 v = SRC == 0 ? __ldg(reinterpret_cast<const float4*>(p.db + row * p.lddb + e))
+                                      : lazy_load4<typename RawOf<SRC>::T>(p.lazy, ctx, row, e);
+            ex = fmaf(x.x, v.x, ex); ex = fmaf(x.y, v.y, ex); ex = fmaf(x.z, v.z, ex); ex = fmaf(x.w, v.w, ex);
+          }
+          ex = warp_sum(ex);
+          if (lane == g) {
+            const uint64_t key = pack_key(ex, static_cast<uint32_t>(row + p.idx_base));
+            if (key > kth) {
+              uint64_t* mine = lists + (warp * G + g) * K;
+              int pos = K - 1;
+              while (pos > 0 && mine[pos - 1] < key) { mine[pos] = mine[pos - 1]; --pos; }
+              mine[pos] = key;
+              kth = mine[K - 1];
+              if (kth != 0ull) my_cut = fmaxf(my_cut, key_score(kth) - my_e);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // merge the warps' lists of each query: warp w serves queries w, w + FB_WARPS, ...
+    for (int g = warp; g < gc; g += FB_WARPS) {
+      uint64_t bound = ~0ull;
+      for (int rnk = 0; rnk < K; ++rnk) {
+        uint64_t best = 0ull;
+        for (int t = lane; t < FB_WARPS * K; t += 32) {
+          const int w = t / K, j = t - w * K;
+          const uint64_t key = lists[(w * G + g) * K + j];
+          if (key < bound && key > best) best = key;
+        }
+        best = warp_max_u64(best);
+        bound = best;
+        if (lane == 0) p.fb_parts[(static_cast<int64_t>(blockIdx.x) * p.cap + g0 + g) * K + rnk] = best;
+        if (best == 0ull) {
+          for (int r2 = rnk + 1 + lane; r2 < K; r2 += 32)
+            p.fb_parts[(static_cast<int64_t>(blockIdx.x) * p.cap + g0 + g) * K + r2] = 0ull;
+          break;
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) rescan_merge_kernel(const RescoreParams p, int blocks) {
   const int n = flagged_count(p);
   const int lane = threadIdx.x & 31;
@@ -584,8 +743,45 @@ static int launch_rescan_src(const RescoreParams& p, bool vec, int G, size_t sme
   return EMR2A_OK;
 }
 
+static bool rescan_filter_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EMR2A_RESCAN_FILTER");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+template <int SRC>
+static int launch_filtered_src(const RescoreParams& p, int G, size_t smem, int blocks, cudaStream_t st) {
+  EMR2A_CUDA_TRY(cudaFuncSetAttribute(filtered_rescan_kernel<SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  filtered_rescan_kernel<SRC><<<blocks, FB_WARPS * 32, smem, st>>>(p, G);
+  EMR2A_LAUNCH_CHECK("filtered_rescan_kernel");
+  return EMR2A_OK;
+}
+
 static int launch_rescan(const RescoreParams& p, int src, cudaStream_t st) {
   const int D = p.D, K = p.K;
+  // filtered re-scan: needs the bf16 plane, K1's statistics (the bound) and the 128-bit path of the exact scoring
+  // and a seed for the cut (without one every warp would score rows exactly until its OWN list is full of good rows)
+  if (rescan_filter_enabled() && p.seed != nullptr && p.db_hi != nullptr && p.q_stats != nullptr && p.db_stats != nullptr && rows_vec(p, src) &&
+      (p.lddb_hi % 8) == 0 && p.lddb_hi >= ((D + 7) & ~7) && (reinterpret_cast<uintptr_t>(p.db_hi) & 15) == 0) {
+    const int Dh = (D + 7) & ~7;
+    const size_t list_bytes = sizeof(uint64_t) * FB_WARPS * FB_GMAX * K;
+    int G = static_cast<int>((96 * 1024 - list_bytes) / (sizeof(uint16_t) * Dh));
+    if (G > FB_GMAX) G = FB_GMAX;
+    if (G >= 1) {
+      const size_t smem = ((sizeof(uint16_t) * G * Dh + 15) & ~static_cast<size_t>(15)) + sizeof(uint64_t) * FB_WARPS * G * K;
+      const int blocks = rescore_fallback_blocks();
+      const int rc = src == 0 ? launch_filtered_src<0>(p, G, smem, blocks, st)
+                   : src == 1 ? launch_filtered_src<1>(p, G, smem, blocks, st)
+                              : launch_filtered_src<2>(p, G, smem, blocks, st);
+      if (rc != EMR2A_OK) return rc;
+      rescan_merge_kernel<<<static_cast<unsigned>((static_cast<int64_t>(p.cap) * 32 + 255) / 256), 256, 0, st>>>(p, blocks);
+      EMR2A_LAUNCH_CHECK("rescan_merge_kernel");
+      return EMR2A_OK;
+    }
+  }
   const int Dp = (D + 3) & ~3;
   int G = static_cast<int>((96 * 1024) / (sizeof(float) * Dp));
   const bool wide = G < FB_GMAX;            // the query group does not fit beside a second block: one 16-warp block per SM
@@ -612,7 +808,8 @@ static int launch_rescan(const RescoreParams& p, int src, cudaStream_t st) {
 
 // approx: merged approximate keys [Q][KP]; writes exact keys [Q][K]; status[0..1] must be zeroed by the caller.
 int rescore_pipeline(const uint64_t* approx, int KP, const uint32_t* tau, const float* q, int64_t ldq, const float* db,
-                     int64_t lddb, const emr2a_lazy_rows* db_lazy, int64_t Q, int64_t N, int D, int64_t idx_base, int K,
+                     int64_t lddb, const emr2a_lazy_rows* db_lazy, const uint16_t* db_hi, int64_t lddb_hi, int64_t Q, int64_t N,
+                     int D, int64_t idx_base, int K,
                      const float* q_stats, const float* db_stats, const uint8_t* q_fold, const uint8_t* db_fold,
                      uint64_t* out_keys, int* status, uint8_t* qflags, void* workspace, size_t ws_bytes, cudaStream_t st) {
   if (!q_stats || !db_stats) return fail(EMR2A_ERR_INVALID, "topk_search(rescore): q_stats/db_stats (K1 stats) required");
@@ -629,6 +826,8 @@ int rescore_pipeline(const uint64_t* approx, int KP, const uint32_t* tau, const 
   const size_t off = (sizeof(int) * static_cast<size_t>(p.cap) + 255) & ~static_cast<size_t>(255);
   p.fb_parts = reinterpret_cast<uint64_t*>(ws + off);
   p.q_fold = q_fold; p.db_fold = db_fold;
+  p.db_hi = db_hi; p.lddb_hi = lddb_hi;
+  p.seed = out_keys; p.seed_compact = 0;        // the exact Top-K of the candidates seeds the cut of the filtered re-scan
   int rc = lazy_fill(p, db_lazy, D);
   if (rc != EMR2A_OK) return rc;
   const int src = rows_src(db_lazy);
@@ -645,7 +844,9 @@ size_t exact_rescan_workspace_bytes(int n_flagged, int K) {
 
 int rescore_exact_rescan(const float* q, int64_t ldq, const float* db, int64_t lddb, const emr2a_lazy_rows* db_lazy, int64_t N,
                          int D, int64_t idx_base, int K, const uint8_t* q_fold, const uint8_t* db_fold, const int* flag_list,
-                         int n_flagged, uint64_t* out_compact, void* workspace, size_t ws_bytes, cudaStream_t st) {
+                         int n_flagged, uint64_t* out_compact, void* workspace, size_t ws_bytes, const uint16_t* db_hi,
+                         int64_t lddb_hi, const float* q_stats, const float* db_stats, const uint64_t* seed_keys,
+                         cudaStream_t st) {
   if (n_flagged <= 0) return EMR2A_OK;
   if (!workspace || exact_rescan_workspace_bytes(n_flagged, K) > ws_bytes) return fail(EMR2A_ERR_WORKSPACE, "exact_rescan: workspace too small");
   RescoreParams p{};
@@ -653,6 +854,8 @@ int rescore_exact_rescan(const float* q, int64_t ldq, const float* db, int64_t l
   p.flag_list = const_cast<int*>(flag_list); p.cap = n_flagged; p.n_fixed = n_flagged; p.compact = 1;
   p.q_fold = q_fold; p.db_fold = db_fold;
   p.fb_parts = reinterpret_cast<uint64_t*>(workspace);
+  p.db_hi = db_hi; p.lddb_hi = lddb_hi; p.q_stats = q_stats; p.db_stats = db_stats;
+  p.seed = seed_keys; p.seed_compact = 1;
   const int rc = lazy_fill(p, db_lazy, D);
   if (rc != EMR2A_OK) return rc;
   return launch_rescan(p, rows_src(db_lazy), st);

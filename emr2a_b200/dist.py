@@ -216,7 +216,8 @@ def _cooperative_search_and_vote(eng, qs, db, db_labels_global, q_labels, n_clas
     n_flagged = int(status.cpu()[0])    # the step's only host synchronisation; identical on every rank
     if n_flagged:
         idx = torch.nonzero(flags).squeeze(1).to(torch.int32)
-        comp = eng.exact_rescan(qs, db, idx, k, idx_base=row_offset, q_fold=q_fold, db_fold=db_fold_local)
+        comp = eng.exact_rescan(qs, db, idx, k, idx_base=row_offset, q_fold=q_fold, db_fold=db_fold_local,
+                                seed_keys=keys.index_select(0, idx.long()))
         keys.index_copy_(0, idx.long(), eng.topk_merge(gather_keys(comp), k))
         res = vote(keys)
         res["precision"] = "rescore"

@@ -86,11 +86,13 @@ def _lazy_arg(op: "Operand"):
 
 
 _DEFER_F32 = os.environ.get("EMR2A_DEFER_F32", "1") != "0"
-# Deferred fp32 rows pay when re-creating elements is rare next to K1's saving.  Every exact re-scan pass re-creates the
-# WHOLE database (2.8x the instructions of a pass over materialised rows: ncu, profiles/r02_rescore_stages.md); with
-# wide rows (C4, D = 5120: ~10 of 10k queries need the re-scan, E grows with D) that costs more than K1 saves, so the
-# pipelines defer only up to this many columns.  ``prepare(defer_f32=True)`` itself always defers when it can.
-_DEFER_MAX_DIM = int(os.environ.get("EMR2A_DEFER_MAX_DIM", 2048))
+# Deferred fp32 rows pay when re-creating elements is rare next to K1's saving: the re-scoring stage re-creates ~18 rows
+# per query, and the exact re-scan of unverifiable queries is FILTERED (it streams the bf16 plane and re-creates only the
+# rows within the error bound of the known K-th best score), so a pass costs the same on deferred and on materialised
+# rows (profiles/r02_rescore_stages.md).  C4 (D = 5120, bf16 inputs): 174.6 -> 172.8 ms per step and 41 GB of HBM less.
+# The UNFILTERED re-scan (exact_rescan without seed lists) re-creates the whole database at 2.8x the instructions of a
+# pass over materialised rows; the pipelines always have seed lists.  Rows wider than this stay materialised.
+_DEFER_MAX_DIM = int(os.environ.get("EMR2A_DEFER_MAX_DIM", 8192))
 
 
 class Engine:
@@ -463,9 +465,13 @@ class Engine:
         return out
 
     def exact_rescan(self, q: Operand, db: Operand, flag_list: torch.Tensor, k: int, idx_base: int = 0, q_fold=None,
-                     db_fold=None) -> torch.Tensor:
+                     db_fold=None, seed_keys: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Stage 6: exact fp32 search of this shard for the queries in ``flag_list`` (int32, the same on every shard).
-        Returns compact keys [n_flagged, k]."""
+        Returns compact keys [n_flagged, k].  With ``seed_keys`` [n_flagged, k] -- exact keys already known for these
+        queries, e.g. the merged lists -- and operands prepared for the rescore arm (bf16 plane + stats) the re-scan is
+        FILTERED: the plane is streamed and only rows within the error bound of the best known K-th exact score are
+        scored exactly.  Every row of the exact Top-K passes; rows that cannot beat the seed's K-th best are dropped,
+        so a shard may return fewer than k keys -- the merge over the shards is the exact Top-K."""
         flag_list = self.to_device(flag_list, torch.int32)
         n = int(flag_list.shape[0])
         out = torch.zeros((n, k), dtype=torch.int64, device=self.device)
@@ -479,12 +485,20 @@ class Engine:
         if q_fold is not None:
             q_fold = self.to_device(q_fold, torch.uint8)
             db_fold = self.to_device(db_fold, torch.uint8)
+        filtered = seed_keys is not None and db.hi is not None and q.stats is not None and db.stats is not None
+        if seed_keys is not None:
+            seed_keys = seed_keys.contiguous()
+            if tuple(seed_keys.shape) != (n, k):
+                raise ValueError(f"exact_rescan: seed_keys must be [{n}, {k}]")
         with torch.cuda.device(self.device):
             native.check(self.lib.emr2a_exact_rescan(
                 q.f32.data_ptr(), _ld(q.f32), native.ptr(db.f32) if db.n else q.f32.data_ptr(),
                 (_ld(db.f32) if db.f32 is not None else 0) if db.n else q.dim,
                 db.n, q.dim, int(idx_base), int(k), native.ptr(q_fold), native.ptr(db_fold), flag_list.data_ptr(), n,
-                out.data_ptr(), _round_up(ws.data_ptr(), 256), ws_bytes, lazy_arg, self._stream()))
+                out.data_ptr(), _round_up(ws.data_ptr(), 256), ws_bytes, lazy_arg,
+                native.ptr(db.hi) if (filtered and db.n) else None, _ld(db.hi) if (filtered and db.n) else 0,
+                native.ptr(q.stats) if filtered else None, native.ptr(db.stats) if filtered else None,
+                native.ptr(seed_keys) if filtered else None, self._stream()))
         self.launches += 2
         return out
 

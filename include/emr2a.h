@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define EMR2A_ABI_VERSION 10
+#define EMR2A_ABI_VERSION 11
 
 enum emr2a_status {
   EMR2A_OK = 0,
@@ -228,7 +228,14 @@ int emr2a_topk_search(const float* q_f32, int64_t ldq_f32,
  *   6. emr2a_exact_rescan       for the (rare) flagged queries: flag_list [n_flagged] query numbers (identical, in
  *                               the same order, on every shard); exact fp32 search of the whole shard, compact
  *                               lists out_keys [n_flagged, K]; the caller merges them across shards and writes
- *                               them over the flagged rows.
+ *                               them over the flagged rows.  With seed_keys [n_flagged, K] -- exact keys already
+ *                               known for these queries (the merged lists) -- plus db_hi (the shard's bf16 plane),
+ *                               q_stats and db_stats (all nullable together) the search is FILTERED: it streams the
+ *                               plane (half the bytes of the fp32 rows), computes the filter score on the CUDA cores
+ *                               and scores a row exactly only if that score is within the error bound E of the best
+ *                               known K-th exact score (the seed's, then the running one).  Every row that belongs
+ *                               to the exact Top-K passes; a shard may return fewer than K keys (rows that cannot
+ *                               beat the seed's K-th best are dropped), the merge over the shards is the exact Top-K.
  * Results are bit-identical to emr2a_topk_search on the unsharded database (same fp32 re-scoring arithmetic, same
  * tie rule).  Operand requirements are those of EMR2A_PREC_BF16_RESCORE (K <= 10); db_lazy (nullable) replaces db_f32
  * as in emr2a_topk_search.
@@ -253,7 +260,9 @@ int emr2a_exact_rescan(const float* q_f32, int64_t ldq_f32, const float* db_f32,
                        const uint8_t* q_fold, const uint8_t* db_fold,
                        const int32_t* flag_list, int n_flagged,
                        uint64_t* out_keys, void* workspace, size_t ws_bytes,
-                       const emr2a_lazy_rows* db_lazy, void* stream);
+                       const emr2a_lazy_rows* db_lazy,
+                       const uint16_t* db_hi, int64_t lddb_bf16, const float* q_stats, const float* db_stats,
+                       const uint64_t* seed_keys, void* stream);
 
 /*
  * K3 -- merge `parts` partial Top-K lists per query into one.  Every input list must be sorted

@@ -293,7 +293,7 @@ class _CoopStub(_StubEngine):
         n_bad = int((~ok).sum())
         return torch.from_numpy((~ok).astype(np.uint8)), torch.tensor([n_bad, int(n_bad > 0), 0, 0], dtype=torch.int32)
 
-    def exact_rescan(self, qs, db, flag_list, k, idx_base=0, q_fold=None, db_fold=None):
+    def exact_rescan(self, qs, db, flag_list, k, idx_base=0, q_fold=None, db_fold=None, seed_keys=None):
         from emr2a_b200.engine import Operand
         sel = flag_list.long()
         sub = Operand(n=int(sel.numel()), dim=qs.dim, f32=qs.f32[sel])

@@ -40,7 +40,9 @@ def _coop(eng, qs, db, bounds_rows, k, q_fold=None, db_fold=None, force_flag=Non
     assert force_flag is not None or n_status == int(idx.numel())
     assert int(status.cpu()[1]) == (1 if n_status else 0)
     if int(idx.numel()):
-        comp = torch.stack([eng.exact_rescan(qs, s, idx, k, idx_base=lo, q_fold=q_fold, db_fold=f) for s, lo, f in shards])
+        seed = keys.index_select(0, idx.long())           # the merged lists seed the cut of the filtered re-scan (as dist.py does)
+        comp = torch.stack([eng.exact_rescan(qs, s, idx, k, idx_base=lo, q_fold=q_fold, db_fold=f, seed_keys=seed)
+                            for s, lo, f in shards])
         keys.index_copy_(0, idx.long(), eng.topk_merge(comp, k))
     return keys, int(idx.numel())
 

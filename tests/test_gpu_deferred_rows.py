@@ -68,7 +68,18 @@ def test_deferred_rows_give_identical_keys(eng, n, d0, d1, q, k, flag_names, w, 
     assert st_full == st_lazy
     # every row, not only the candidates: the exact re-scan of ALL queries walks the whole database
     every = torch.arange(q, dtype=torch.int32, device=eng.device)[:64]
-    assert torch.equal(eng.exact_rescan(qs, lazy, every, k), eng.exact_rescan(qs, full, every, k))
+    rescanned = eng.exact_rescan(qs, lazy, every, k)            # unfiltered: every row re-created and scored exactly
+    assert torch.equal(rescanned, eng.exact_rescan(qs, full, every, k))
+    assert torch.equal(rescanned, want[:64])                     # and it finds what the verified search found
+    # filtered re-scan (the bf16 plane is streamed, exact scoring on demand), seeded with lists that are deliberately
+    # too low -- the exact Top-K of the FIRST HALF of the database -- so that the scan has better rows to find
+    half = n // 2
+    from emr2a_b200.engine import Operand
+    first = Operand(n=half, dim=full.dim, f32=full.f32[:half], hi=full.hi[:half], stats=full.stats)
+    seed = eng.exact_rescan(qs, first, every, k)
+    for op in (full, lazy):
+        assert torch.equal(eng.exact_rescan(qs, op, every, k, seed_keys=seed), rescanned)
+    assert torch.equal(eng.exact_rescan(qs, lazy, every, k, seed_keys=rescanned), rescanned)   # a perfect seed changes nothing
 
 
 def test_deferred_rows_recreate_every_element(eng):
