@@ -29,6 +29,36 @@ def test_library_exports_every_header_symbol(lib):
     assert int(m.group(1)) == native.ABI_VERSION
 
 
+def test_binding_argument_lists_match_the_header():
+    """Every ctypes signature has as many arguments as the C declaration, pointer / integer / float in the same places
+    (an argument added on one side only would otherwise corrupt the call silently), and the emr2a_lazy_rows struct has
+    the header's field order."""
+    import ctypes as C
+    from emr2a_b200 import native
+    header = open(os.path.join(REPO, "include", "emr2a.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    decls = dict(re.findall(r"\b(?:int|size_t|const char\*)\s+(emr2a_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", header, flags=re.S))
+    assert len(decls) >= 25
+    def kind(param):
+        param = param.strip()
+        if "*" in param:
+            return "p"
+        if re.match(r"(const\s+)?float\b", param):
+            return "f"
+        return "i"
+    for name, params in decls.items():
+        res, args = native._SIGNATURES[name]
+        plist = [] if params.strip() in ("", "void") else [x for x in params.split(",")]
+        assert len(plist) == len(args), (name, len(plist), len(args))
+        for param, ctype in zip(plist, args):
+            want = kind(param)
+            got = "f" if ctype is C.c_float else ("p" if (ctype is C.c_void_p or ctype is C.c_char_p or hasattr(ctype, "contents")) else "i")
+            assert want == got, (name, param.strip(), ctype)
+    m = re.search(r"typedef struct emr2a_lazy_rows \{(.*?)\} emr2a_lazy_rows;", header, flags=re.S)
+    fields = [re.split(r"[\s\*]+", f.strip())[-1] for f in m.group(1).replace(",", ";").split(";") if f.strip()]
+    assert fields == [n for n, _ in native.LazyRows._fields_], fields
+
+
 def test_header_enums_match_binding():
     from emr2a_b200 import native
     header = open(os.path.join(REPO, "include", "emr2a.h")).read()
