@@ -7,7 +7,8 @@ Headline workload ("c2", BASELINE.json configs[1]): 1M-case database, 512-d imag
 embeddings (fp32, synthetic class-structured Gaussians), concat fusion to 1024-d, 10k queries,
 K=10, 3 classes.  A STEP = the whole hot path over that batch:
     K1 normalise+fuse (database shard AND queries) -> K2 similarity + fused Top-K
-    -> K3 merge -> [NCCL all-gather of local Top-K + K3 merge when N > 1] -> K4 vote + metrics.
+    -> K3 merge -> [N > 1, cooperative shards: NCCL all-reduce (MAX) of the K-th best filter score, exact re-scoring,
+    NCCL all-gather of exact Top-K + bounds, K3 merge, verification of the merged lists] -> K4 vote + metrics.
 N > 1: the SAME 1M-row database is sharded row-wise over the ranks (strong scaling), and the line carries a "c5"
 sub-record: BASELINE.json configs[4] (every case a query, 5-fold CV rule, K=5) on all N GPUs -- the full
 10M-case cohort at N = 8, sqrt(N/8)-scaled row counts below (same per-GPU time), see run_c5.
@@ -15,7 +16,8 @@ sub-record: BASELINE.json configs[4] (every case a query, 5-fold CV rule, K=5) o
 value  : queries/sec with the raw embeddings resident in HBM.
 e2e    : queries/sec through Engine.search_and_vote_host with the inputs in PINNED HOST
          memory: every step copies the database shard + queries host->device (chunked,
-         overlapped with compute) and the results device->host.
+         overlapped with compute) and the results device->host.  N > 1: shards sized by each rank's measured
+         concurrent H2D rate, query rows copied once per node and all-gathered over NVLink (emr2a_b200/dist.py).
 roofline: the K2 kernel (tensor pipe): algorithmic FLOPs 2*D*Q*N_local / its CUDA-event time; traffic = DRAM bytes
          of that kernel from the committed ncu capture listed in profiles/k2_traffic.json.
 cpu_baseline: the reference's algorithm (oracle port: per-query np.dot sgemv over every admissible row + full np.argsort

@@ -1,8 +1,16 @@
-"""Row-sharded database across GPUs: one process per GPU, ``torch.distributed`` (NCCL over
-NVLink/NVSwitch) for the single exchange step of the path -- an all-gather of each rank's
-local Top-K keys (Q x K x 8 bytes), merged by the K3 kernel.  Global row indices travel
-inside the keys, and ties break on the global index, so results are bit-identical for any
-GPU count."""
+"""Row-sharded database across GPUs: one process per GPU, ``torch.distributed`` (NCCL over NVLink/NVSwitch) for the
+exchange steps of the path.  Global row indices travel inside the packed keys, ties break on the global index and
+every arm returns exact fp32 scores, so results are bit-identical for any GPU count and any sharding.
+
+* ``sharded_search_and_vote``     queries against a row-sharded database.  Cooperative shards: an all-reduce (MAX) of
+                                  the shards' K-th best filter score, exact re-scoring of what can reach the global
+                                  Top-K, ONE all-gather of exact keys + bounds, verification of the merged lists.
+* ``sharded_cv_search_and_vote``  every case a query (5-fold CV rule) over fold-balanced shards; query blocks of prepared
+                                  rows are broadcast from their owner over NVLink, double-buffered.
+* host-resident databases         ``spread_device`` (ranks spread over the host bridges), ``h2d_rates`` +
+                                  ``weighted_ranges`` (shards sized by each rank's host link), ``gather_host_rows``
+                                  (replicated query rows copied once per node, all-gathered over NVLink).
+"""
 from __future__ import annotations
 
 import os
