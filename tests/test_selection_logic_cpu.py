@@ -121,3 +121,25 @@ def test_cooperative_shards_argument(parts, mode):
         want = _topk(s, k)
         in_lists = np.isin(want, np.concatenate(lists))
         assert np.all(np.isin(want[in_lists], allc))
+
+
+def test_warp_bitonic_network_sorts_descending():
+    """The 15 compare-exchange steps rescore_select_kernel uses to get the K-th best exact score of the first
+    candidates (csrc/rescore.cu: `take_max = ((lane & j) == 0) == ((lane & k2) == 0)`), emulated lane for lane."""
+    rng = np.random.default_rng(0)
+    lane = np.arange(32)
+    for trial in range(500):
+        v = rng.standard_normal(32).astype(np.float32)
+        if trial % 3 == 0:
+            v[rng.integers(0, 32, 20)] = -np.inf                      # empty slots
+        w = v.copy()
+        k2 = 2
+        while k2 <= 32:
+            j = k2 >> 1
+            while j > 0:
+                other = w[lane ^ j]                                    # __shfl_xor_sync(v, j)
+                take_max = ((lane & j) == 0) == ((lane & k2) == 0)
+                w = np.where(take_max, np.maximum(w, other), np.minimum(w, other))
+                j >>= 1
+            k2 <<= 1
+        assert np.array_equal(w, np.sort(v)[::-1])
