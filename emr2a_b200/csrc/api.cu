@@ -45,6 +45,8 @@ int tc_topk_search(const uint16_t* q_hi, const uint16_t* q_lo, const uint16_t* d
                    void* workspace, size_t ws_bytes, float* debug_scores, cudaStream_t st, TcPartials* partials,
                    int fold_sorted, int min_splits);
 int tc_planned_splits(int64_t Q, int64_t N, int min_splits);
+int tc_timing_enable(int on);
+int tc_timing_read(float* ms_out, int cap, int* n_out);
 
 size_t rescore_workspace_bytes(int64_t Q, int K);
 int rescore_pipeline(const uint64_t* approx, int KP, const uint32_t* tau, const float* q, int64_t ldq, const float* db,
@@ -311,4 +313,13 @@ extern "C" int emr2a_exact_rescan(const float* q_f32, int64_t ldq_f32, const flo
   }
   return rescore_exact_rescan(q_f32, ldq_f32, db_f32, lddb_f32, db_lazy, N, D, idx_base, K, q_fold, db_fold, flag_list,
                               n_flagged, out_keys, workspace, ws_bytes, db_hi, lddb_bf16, q_stats, db_stats, seed_keys, st);
+}
+
+// Diagnostics: time the Top-K kernel of every search alone (CUDA events on the launching stream around its launch).
+// enable != 0 starts a fresh series; emr2a_debug_tc_elapsed waits for the timed launches and returns their durations
+// (milliseconds, HOST array, oldest first, the last `cap` at most).
+extern "C" int emr2a_debug_tc_timing(int enable) { return tc_timing_enable(enable); }
+extern "C" int emr2a_debug_tc_elapsed(float* ms_out_host, int cap, int* n_out_host) {
+  if (!ms_out_host || !n_out_host || cap <= 0) return fail(EMR2A_ERR_INVALID, "debug_tc_elapsed: bad arguments");
+  return tc_timing_read(ms_out_host, cap, n_out_host);
 }

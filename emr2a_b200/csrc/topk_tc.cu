@@ -360,6 +360,43 @@ int tc_debug_unit_clocks(unsigned long long* host_out, int64_t cap_units, int64_
   return EMR2A_OK;
 }
 
+// Diagnostics (emr2a_debug_tc_timing / emr2a_debug_tc_elapsed): CUDA events on the launching stream right before and
+// right after the Top-K kernel of every search, so that bench.py can report the duration of the DOMINANT KERNEL ALONE
+// (the C-ABI call also launches memsets, the merge of the partial lists and the re-scoring stage) without a profiler.
+constexpr int TC_EV_RING = 1024;
+static cudaEvent_t g_tc_ev[TC_EV_RING][2];
+static bool g_tc_ev_made[TC_EV_RING];
+static long long g_tc_ev_count = 0;
+static int g_tc_ev_on = 0;
+
+static void tc_ev_record(int which, cudaStream_t st) {
+  if (!g_tc_ev_on) return;
+  const int slot = static_cast<int>(g_tc_ev_count % TC_EV_RING);
+  if (!g_tc_ev_made[slot]) {
+    if (cudaEventCreate(&g_tc_ev[slot][0]) != cudaSuccess || cudaEventCreate(&g_tc_ev[slot][1]) != cudaSuccess) { g_tc_ev_on = 0; return; }
+    g_tc_ev_made[slot] = true;
+  }
+  cudaEventRecord(g_tc_ev[slot][which], st);
+  if (which == 1) ++g_tc_ev_count;
+}
+int tc_timing_enable(int on) {
+  g_tc_ev_on = on ? 1 : 0;
+  g_tc_ev_count = 0;
+  return EMR2A_OK;
+}
+// elapsed milliseconds of the last (up to cap) timed launches, oldest first; waits for them to finish
+int tc_timing_read(float* ms_out, int cap, int* n_out) {
+  long long n = g_tc_ev_count < TC_EV_RING ? g_tc_ev_count : TC_EV_RING;
+  if (n > cap) n = cap;
+  for (long long i = 0; i < n; ++i) {
+    const int slot = static_cast<int>((g_tc_ev_count - n + i) % TC_EV_RING);
+    EMR2A_CUDA_TRY(cudaEventSynchronize(g_tc_ev[slot][1]));
+    EMR2A_CUDA_TRY(cudaEventElapsedTime(ms_out + i, g_tc_ev[slot][0], g_tc_ev[slot][1]));
+  }
+  *n_out = static_cast<int>(n);
+  return EMR2A_OK;
+}
+
 template <int PASSES, int KCAP, bool HAS_FOLD>
 static int tc_launch(const CUtensorMap& mq_hi, const CUtensorMap& mq_lo, const CUtensorMap& md_hi, const CUtensorMap& md_lo,
                      const TcParams& p, int grid, cudaStream_t st) {
@@ -448,6 +485,7 @@ int tc_topk_search(const uint16_t* q_hi, const uint16_t* q_lo, const uint16_t* d
     p.q_fold = q_fold; p.db_fold = fpad; p.fold_sorted = fold_sorted;
   }
   const int kcap = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
+  tc_ev_record(0, st);
   if (pairs) {
     rc = tc2_dispatch(passes, kcap, has_fold, mq_hi, mq_lo, md_hi, md_lo, p, pl.grid, st);
   } else if (passes == 3) {
@@ -459,6 +497,7 @@ int tc_topk_search(const uint16_t* q_hi, const uint16_t* q_lo, const uint16_t* d
     else if (kcap == 16) rc = tc_launch_fold<1, 16>(has_fold, mq_hi, mq_lo, md_hi, md_lo, p, pl.grid, st);
     else rc = tc_launch_fold<1, 32>(has_fold, mq_hi, mq_lo, md_hi, md_lo, p, pl.grid, st);
   }
+  tc_ev_record(1, st);
   if (rc != EMR2A_OK) return rc;
   if (partials) {
     partials->parts = p.keys_out;

@@ -64,6 +64,8 @@ _SIGNATURES = {
     "emr2a_debug_topk_search_dump": (_int, [_p, _p, _p, _p, _i64, _i64, _int, _i64, _i64, _p, _p, _i64, _int, _int,
                                             _p, _p, _sz, _p, _p]),
     "emr2a_debug_unit_clocks": (_int, [_p, _i64, _p]),
+    "emr2a_debug_tc_timing": (_int, [_int]),
+    "emr2a_debug_tc_elapsed": (_int, [_p, _int, _p]),
 }
 
 
