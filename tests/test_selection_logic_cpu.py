@@ -143,3 +143,37 @@ def test_warp_bitonic_network_sorts_descending():
                 j >>= 1
             k2 <<= 1
         assert np.array_equal(w, np.sort(v)[::-1])
+
+
+def _bf16(x):
+    """float32 -> nearest bf16 (ties to even), returned as float32 (what K1's hi plane holds)."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000).astype(np.uint32)
+    return r.view(np.float32)
+
+
+def test_quantisation_terms_of_the_error_bound():
+    """|<bf16(q), bf16(d)> - <q, d>| <= r_q * n_d + (n_q + r_q) * r_d  (csrc/rescore.cu: error_bound, the two
+    Cauchy-Schwarz terms; n = row norm, r = ||row - bf16(row)||), in float64 on the exact bf16 values -- for random rows,
+    for rows whose residuals are aligned on purpose, and with the database-side maxima the kernel actually uses."""
+    rng = np.random.default_rng(5)
+    for d_len in (64, 1024, 5120):
+        db = rng.standard_normal((400, d_len)).astype(np.float32)
+        db /= np.linalg.norm(db, axis=1, keepdims=True)
+        qs = rng.standard_normal((60, d_len)).astype(np.float32)
+        qs /= np.linalg.norm(qs, axis=1, keepdims=True)
+        qs[:10] = db[:10]                                               # self-queries: residuals point the same way
+        res_db = (db - _bf16(db)).astype(np.float64)
+        qs[10:20] = (np.sign(res_db[10:20]) * np.abs(qs[10:20])).astype(np.float32)    # signs aligned with the residuals
+        exact = qs.astype(np.float64) @ db.astype(np.float64).T
+        approx = _bf16(qs).astype(np.float64) @ _bf16(db).astype(np.float64).T
+        n_q = np.linalg.norm(qs.astype(np.float64), axis=1)[:, None]
+        r_q = np.linalg.norm((qs - _bf16(qs)).astype(np.float64), axis=1)[:, None]
+        n_d = np.linalg.norm(db.astype(np.float64), axis=1).max()       # K1 `stats`: maxima over the database rows
+        r_d = np.linalg.norm(res_db, axis=1).max()
+        bound = r_q * n_d + (n_q + r_q) * r_d
+        err = np.abs(approx - exact)
+        assert np.all(err <= bound)
+        assert 3e-3 < float(bound.mean()) < 5e-3                        # ~3.8e-3 for unit rows (r ~ 1.7e-3 each), as DESIGN.md states
+        assert float(np.median(err)) < 0.06 * float(bound.mean())       # typical errors sit far inside the worst case ...
+        assert float(err.max()) < 0.5 * float(bound.mean())             # ... and even sign-aligned residuals reach less than half of it
