@@ -527,10 +527,16 @@ def run_c1(args):
     full = ev.run_cv(ids, labels, emb, fusion="concat", top_k_list=[1, 3, 5, 5])
     t_e2e = time.perf_counter() - t0
     # the same public call as a user gets it by default (preprocess = "auto": scaler + exact PCA on the device
-    # wherever sklearn's own solver choice is deterministic; otherwise sklearn on the host)
+    # wherever sklearn's own solver choice is deterministic; otherwise sklearn on the host).  First call timed
+    # separately: it creates the cuSOLVER handles (one-off, ~0.3 s); the steady-state call is what repeats.
     ev_def = CVRetrievalEvaluator(cv_folds=5, pca_dim=128, top_k=k, seed=42)
     t0 = time.perf_counter()
     ev_def.run_cv(ids, labels, emb, fusion="concat", top_k_list=[1, 3, 5, 5])
+    torch.cuda.synchronize()
+    t_e2e_default_first = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ev_def.run_cv(ids, labels, emb, fusion="concat", top_k_list=[1, 3, 5, 5])
+    torch.cuda.synchronize()
     t_e2e_default = time.perf_counter() - t0
     # the same public call with the per-fold scaler + PCA on the device (deterministic exact basis)
     ev_gpu = CVRetrievalEvaluator(cv_folds=5, pca_dim=128, top_k=k, seed=42)
@@ -565,7 +571,8 @@ def run_c1(args):
                     "api": "CVRetrievalEvaluator.run_cv, preprocess='host' (StratifiedKFold + StandardScaler + PCA by sklearn "
                            f"as in the reference, ~{t_prep:.2f} s; GPU hot path; python list outputs)",
                     "api_hot_path_seconds": t_api, "api_hot_path_qps": n / t_api,
-                    "default_preprocess": {"mode": ev_def.preprocess, "value": n / t_e2e_default, "seconds": t_e2e_default},
+                    "default_preprocess": {"mode": ev_def.preprocess, "value": n / t_e2e_default, "seconds": t_e2e_default,
+                                           "first_call_seconds": t_e2e_default_first},
                     "gpu_preprocess": {"value": n / t_e2e_gpu, "unit": "queries/s", "seconds": t_e2e_gpu,
                                        "api": "CVRetrievalEvaluator.run_cv with preprocess='gpu' (StandardScaler + exact "
                                               "PCA on the device), python list outputs",
